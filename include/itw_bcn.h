@@ -1,0 +1,146 @@
+/*
+ * itw_bcn.h -- C-ABI of the B200-native BCn block encoder (libitw_bcn.so).
+ *
+ * Drop-in boundary: every struct and entry point in the first section has the exact layout,
+ * name, argument meaning and calling convention of the reference's
+ *     3rdParty/Intel/Source/ispc_texcomp.h:19-50  (structs)
+ *     3rdParty/Intel/Source/ispc_texcomp.h:67-87  (GetProfile_*)
+ *     3rdParty/Intel/Source/ispc_texcomp.h:104-107 (CompressBlocksBC1/BC3/BC6H/BC7)
+ * so a host that links ispc_texcomp today (IntelPlugin.cpp's save path through
+ * win32Threads.cpp:289-330) can link this library instead.  The second section is additive.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ */
+#ifndef ITW_BCN_H
+#define ITW_BCN_H
+
+#include <stdint.h>
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------
+ * Section 1 -- the reference's own ABI
+ * ------------------------------------------------------------------------------------------- */
+
+/* ispc_texcomp.h:19-25.  `stride` is in BYTES.  LDR surfaces are RGBA8 (R in byte 0), HDR
+ * surfaces are RGBA16F (half R,G,B at +0,+2,+4; A ignored).  width/height multiples of 4. */
+typedef struct rgba_surface {
+    uint8_t* ptr;
+    int32_t  width;
+    int32_t  height;
+    int32_t  stride;
+} rgba_surface;
+
+/* ispc_texcomp.h:27-41 (64 bytes) */
+typedef struct bc7_enc_settings {
+    bool mode_selection[4];      /* {modes 0+2, modes 1+3+7, modes 4+5, mode 6} */
+    int  refineIterations[8];    /* per BC7 mode */
+    bool skip_mode2;
+    int  fastSkipTreshold_mode1; /* (sic) number of ranked 2-subset partitions tried */
+    int  fastSkipTreshold_mode3;
+    int  fastSkipTreshold_mode7;
+    int  mode45_channel0;        /* first rotation tried by modes 4/5 */
+    int  refineIterations_channel;
+    int  channels;               /* 3 = ignore alpha, 4 = RGBA */
+} bc7_enc_settings;
+
+/* ispc_texcomp.h:43-50 (16 bytes) */
+typedef struct bc6h_enc_settings {
+    bool slow_mode;
+    bool fast_mode;
+    int  refineIterations_1p;
+    int  refineIterations_2p;
+    int  fastSkipTreshold;
+} bc6h_enc_settings;
+
+/* ispc_texcomp.h:67-71 -- RGB profiles (alpha ignored); ispc_texcomp.cpp:20-189 */
+void GetProfile_ultrafast(bc7_enc_settings* settings);
+void GetProfile_veryfast(bc7_enc_settings* settings);
+void GetProfile_fast(bc7_enc_settings* settings);
+void GetProfile_basic(bc7_enc_settings* settings);
+void GetProfile_slow(bc7_enc_settings* settings);
+/* ispc_texcomp.h:74-78 -- RGBA profiles; ispc_texcomp.cpp:191-365 */
+void GetProfile_alpha_ultrafast(bc7_enc_settings* settings);
+void GetProfile_alpha_veryfast(bc7_enc_settings* settings);
+void GetProfile_alpha_fast(bc7_enc_settings* settings);
+void GetProfile_alpha_basic(bc7_enc_settings* settings);
+void GetProfile_alpha_slow(bc7_enc_settings* settings);
+/* ispc_texcomp.h:81-85 -- BC6H profiles; ispc_texcomp.cpp:367-410 */
+void GetProfile_bc6h_veryfast(bc6h_enc_settings* settings);
+void GetProfile_bc6h_fast(bc6h_enc_settings* settings);
+void GetProfile_bc6h_basic(bc6h_enc_settings* settings);
+void GetProfile_bc6h_slow(bc6h_enc_settings* settings);
+void GetProfile_bc6h_veryslow(bc6h_enc_settings* settings);
+
+/* ispc_texcomp.h:104-107; ispc_texcomp.cpp:417-435 -> kernel.ispc:598/607/3132/2030.
+ * dst receives (width/4)*(height/4) blocks, tightly packed in raster block order
+ * (8 bytes/block for BC1, 16 for BC3/BC6H/BC7).  `src->ptr` and `dst` may each be host or
+ * device memory (detected per call); host buffers are staged through pinned memory.
+ * void return as in the reference: failures are reported through itw_get_last_error(). */
+void CompressBlocksBC1(const rgba_surface* src, uint8_t* dst);
+void CompressBlocksBC3(const rgba_surface* src, uint8_t* dst);
+void CompressBlocksBC6H(const rgba_surface* src, uint8_t* dst, bc6h_enc_settings* settings);
+void CompressBlocksBC7(const rgba_surface* src, uint8_t* dst, bc7_enc_settings* settings);
+
+/* ---------------------------------------------------------------------------------------------
+ * Section 2 -- additive entry points (not in the reference header)
+ * ------------------------------------------------------------------------------------------- */
+
+/* BC4 (R -> 8 B/block) and BC5 (R,G -> 16 B/block) of an RGBA8 surface.  In the reference these
+ * formats go through DirectX::Compress (IntelPlugin.cpp:272) to D3DXEncodeBC4U / D3DXEncodeBC5U
+ * (DirectXTex/BC4BC5.cpp:403, :481); same surface/dst conventions as above. */
+void CompressBlocksBC4(const rgba_surface* src, uint8_t* dst);
+void CompressBlocksBC5(const rgba_surface* src, uint8_t* dst);
+
+/* Format selector for the generic entry points below; values are the DXGI_FORMAT enumerants the
+ * plug-in switches on (IntelPlugin.cpp:820-847, win32Threads.cpp:192-209). */
+enum {
+    ITW_FORMAT_BC1 = 71,  /* DXGI_FORMAT_BC1_UNORM  */
+    ITW_FORMAT_BC3 = 77,  /* DXGI_FORMAT_BC3_UNORM  */
+    ITW_FORMAT_BC4 = 80,  /* DXGI_FORMAT_BC4_UNORM  */
+    ITW_FORMAT_BC5 = 83,  /* DXGI_FORMAT_BC5_UNORM  */
+    ITW_FORMAT_BC6H = 95, /* DXGI_FORMAT_BC6H_UF16  */
+    ITW_FORMAT_BC7 = 98   /* DXGI_FORMAT_BC7_UNORM  */
+};
+
+/* Bytes per 4x4 block for a format (win32Threads.cpp:192-209); 0 for an unknown format. */
+int itw_bytes_per_block(int format);
+
+/* Device-resident encode on an explicit CUDA stream (cudaStream_t passed as void*; NULL = the
+ * legacy default stream).  src->ptr and dst MUST be device pointers; nothing is copied and the
+ * call returns as soon as the kernel is enqueued.  `settings` is a bc7_enc_settings* for BC7, a
+ * bc6h_enc_settings* for BC6H and ignored otherwise; it is read before the call returns.
+ * Returns 0 on success, a negative value on error (see itw_get_last_error). */
+int itw_encode_device(int format, const rgba_surface* src, uint8_t* dst, const void* settings,
+                      void* cuda_stream);
+
+/* Batched encode of `count` independent surfaces (config C5's tile stream; the coarse seam the
+ * plug-in's CompressImageMT/ST offer, win32Threads.h:57-58).  Host surfaces are pipelined
+ * H2D / encode / D2H over internal streams; dst[i] receives surface i's blocks. */
+int itw_encode_batch(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count,
+                     const void* settings);
+
+/* Select the CUDA device used by this thread's subsequent calls (default: current device). */
+int itw_set_device(int device);
+
+/* Last error message of the calling thread ("" if none).  The CompressBlocks* entry points keep
+ * the reference's void signature, so this is the only error channel for them. */
+const char* itw_get_last_error(void);
+
+/* Number of kernel launches issued by this library since load (all threads); bench evidence. */
+uint64_t itw_kernel_launch_count(void);
+
+/* Device time in milliseconds of the most recent encode issued by this thread, measured with CUDA
+ * events on the launching stream around the kernel(s) only (no copies).  Valid after the call
+ * has completed (the CompressBlocks* entry points are synchronous for host buffers). */
+float itw_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ITW_BCN_H */
