@@ -1,0 +1,147 @@
+"""ctypes binding of include/itw_bcn.h (same names, argument meaning and error behaviour)."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path():
+    return os.path.join(HERE, "libitw_bcn.so")
+
+
+class RgbaSurface(ctypes.Structure):          # ispc_texcomp.h:19-25
+    _fields_ = [("ptr", ctypes.c_void_p), ("width", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("stride", ctypes.c_int32)]
+
+
+class Bc7Settings(ctypes.Structure):          # ispc_texcomp.h:27-41
+    _fields_ = [("mode_selection", ctypes.c_bool * 4), ("refineIterations", ctypes.c_int * 8),
+                ("skip_mode2", ctypes.c_bool), ("fastSkipTreshold_mode1", ctypes.c_int),
+                ("fastSkipTreshold_mode3", ctypes.c_int), ("fastSkipTreshold_mode7", ctypes.c_int),
+                ("mode45_channel0", ctypes.c_int), ("refineIterations_channel", ctypes.c_int),
+                ("channels", ctypes.c_int)]
+
+
+class Bc6hSettings(ctypes.Structure):         # ispc_texcomp.h:43-50
+    _fields_ = [("slow_mode", ctypes.c_bool), ("fast_mode", ctypes.c_bool),
+                ("refineIterations_1p", ctypes.c_int), ("refineIterations_2p", ctypes.c_int),
+                ("fastSkipTreshold", ctypes.c_int)]
+
+
+BC7_PROFILES = ("ultrafast", "veryfast", "fast", "basic", "slow",
+                "alpha_ultrafast", "alpha_veryfast", "alpha_fast", "alpha_basic", "alpha_slow")
+BC6H_PROFILES = ("bc6h_veryfast", "bc6h_fast", "bc6h_basic", "bc6h_slow", "bc6h_veryslow")
+
+# name -> (DXGI format id, bytes per block, bytes per texel, settings kind)
+FORMATS = {
+    "BC1": (71, 8, 4, None), "BC3": (77, 16, 4, None), "BC4": (80, 8, 4, None), "BC5": (83, 16, 4, None),
+    "BC6H": (95, 16, 8, "bc6h"), "BC7": (98, 16, 4, "bc7"),
+}
+
+EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "CompressBlocksBC5",
+            "CompressBlocksBC6H", "CompressBlocksBC7", "itw_bytes_per_block", "itw_encode_device",
+            "itw_encode_batch", "itw_set_device", "itw_get_last_error", "itw_kernel_launch_count",
+            "itw_last_kernel_ms"]
+           + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
+
+
+class EncoderApi:
+    """A loaded library exporting the reference C-ABI (optionally with a symbol prefix).
+
+    Used for the product (prefix "") and, by tests only, for the oracle ("oracle_"), the
+    reference-source build ("") and the CPU emulation ("emu_")."""
+
+    def __init__(self, path, prefix=""):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing -- build it first (python __graft_entry__.py build)")
+        self.path = path
+        self.prefix = prefix
+        self.lib = ctypes.CDLL(path)
+
+    def fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def profile(self, name):
+        """Settings struct filled by GetProfile_<name> (zero-initialised first, like the canonical model)."""
+        s = Bc6hSettings() if name.startswith("bc6h_") else Bc7Settings()
+        f = self.fn("GetProfile_" + name)
+        f.restype = None
+        f(ctypes.byref(s))
+        return s
+
+    def _call(self, fmt, surf, dst_ptr, settings):
+        f = self.fn("CompressBlocks" + fmt)
+        f.restype = None
+        kind = FORMATS[fmt][3]
+        if kind is None:
+            f(ctypes.byref(surf), ctypes.c_void_p(dst_ptr))
+        else:
+            if settings is None:
+                raise ValueError(f"{fmt} needs a settings struct")
+            f(ctypes.byref(surf), ctypes.c_void_p(dst_ptr), ctypes.byref(settings))
+
+    def encode(self, fmt, image, settings=None):
+        """Encode a host numpy image (H x W x 4, uint8 for LDR / uint16 half bits for BC6H)."""
+        _, bpb, texel, _ = FORMATS[fmt]
+        h, w = image.shape[:2]
+        assert image.strides[1] == texel and image.shape[2] * image.itemsize == texel, "RGBA8 / RGBA16F texels expected"
+        surf = RgbaSurface(image.ctypes.data, w, h, image.strides[0])
+        out = np.zeros((h // 4) * (w // 4) * bpb, dtype=np.uint8)
+        self._call(fmt, surf, out.ctypes.data, settings)
+        self.check()
+        return out
+
+    def encode_raw(self, fmt, ptr, width, height, stride, dst_ptr, settings=None):
+        """CompressBlocks<fmt> on raw addresses (host or device)."""
+        self._call(fmt, RgbaSurface(ptr, width, height, stride), dst_ptr, settings)
+        self.check()
+
+    def check(self):
+        pass
+
+
+class ItwBcn(EncoderApi):
+    """The product library.  Raises on any reported error; never falls back to a CPU path."""
+
+    def __init__(self, path=None):
+        super().__init__(path or library_path())
+        L = self.lib
+        L.itw_get_last_error.restype = ctypes.c_char_p
+        L.itw_kernel_launch_count.restype = ctypes.c_uint64
+        L.itw_last_kernel_ms.restype = ctypes.c_float
+        L.itw_encode_device.restype = ctypes.c_int
+        L.itw_encode_device.argtypes = [ctypes.c_int, ctypes.POINTER(RgbaSurface), ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]
+        L.itw_encode_batch.restype = ctypes.c_int
+        L.itw_bytes_per_block.restype = ctypes.c_int
+        L.itw_set_device.restype = ctypes.c_int
+
+    def last_error(self):
+        return self.lib.itw_get_last_error().decode()
+
+    def check(self):
+        e = self.last_error()
+        if e:
+            raise RuntimeError("libitw_bcn: " + e)
+
+    def set_device(self, index):
+        if self.lib.itw_set_device(int(index)) != 0:
+            self.check()
+
+    def launch_count(self):
+        return int(self.lib.itw_kernel_launch_count())
+
+    def last_kernel_ms(self):
+        return float(self.lib.itw_last_kernel_ms())
+
+    def encode_device(self, fmt, ptr, width, height, stride, dst_ptr, settings=None, stream=0):
+        """Enqueue the encode of a device-resident surface on a CUDA stream (no copies, no sync)."""
+        surf = RgbaSurface(ptr, width, height, stride)
+        sp = ctypes.cast(ctypes.byref(settings), ctypes.c_void_p) if settings is not None else None
+        rc = self.lib.itw_encode_device(FORMATS[fmt][0], ctypes.byref(surf), ctypes.c_void_p(dst_ptr), sp,
+                                        ctypes.c_void_p(stream))
+        if rc != 0:
+            self.check()
+            raise RuntimeError("itw_encode_device failed")

@@ -1,0 +1,255 @@
+// bc1_bc3.cuh -- BC1 / BC3 encoder kernels (reference: kernel.ispc:231-614, cited as K:line).
+//
+// Mapping: one thread owns one 4x4 block (the reference's own lane<->block mapping, K:600-604).
+// A warp covers 32 horizontally adjacent blocks, so each of the four texel rows is one fully
+// coalesced 512-byte request of 128-bit loads and the packed output is one coalesced 256-byte
+// (BC1) or 512-byte (BC3) store.  BC1's covariance sums are inexact float sums whose order
+// matters on high-variance blocks (K:377-417), so the per-block math stays sequential in one
+// thread; there is no cross-lane traffic at all.
+//
+// Algorithmic traffic per block: 64 B read, 8 B (BC1) / 16 B (BC3) written.
+#pragma once
+#include "itw_device.cuh"
+
+namespace itw {
+
+// ---- RGB565 helpers; K:234-259 ----
+ITW_HD int scale8(int a, int b) { int t = a * b + 128; return (t + (t >> 8)) >> 8; }
+ITW_HD int pack565(float r, float g, float b)
+{
+    int v = (scale8(cvt_x86(r), 31) << 11) + (scale8(cvt_x86(g), 63) << 5) + scale8(cvt_x86(b), 31);
+    return v & 0xFFFF;
+}
+ITW_HD void unpack565(float c[3], int p)
+{
+    int b = p & 31, g = (p >> 5) & 63, r = (p >> 11) & 31;
+    c[0] = (float)((r << 3) + (r >> 2));
+    c[1] = (float)((g << 2) + (g >> 4));
+    c[2] = (float)((b << 3) + (b >> 2));
+}
+
+// Linear 2-bit indices along p0 -> p1; K:308-344 (p0 == p1 -> NaN -> INT_MIN -> index 0)
+ITW_HD u32 bc1_linear_indices(const float (&px)[3][16], int p0, int p1)
+{
+    float a[3], b[3], dir[3];
+    unpack565(a, p0);
+    unpack565(b, p1);
+#pragma unroll
+    for (int c = 0; c < 3; c++) dir[c] = b[c] - a[c];
+    float n2 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) n2 += sq(dir[c]);
+    float inv = 1.0f / n2;
+#pragma unroll
+    for (int c = 0; c < 3; c++) dir[c] *= inv * 3.0f;
+    float bias = 0.5f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) bias -= a[c] * dir[c];
+    u32 bits = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float d = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) d += px[c][k] * dir[c];
+        int q = clampi(cvt_x86(d + bias), 0, 3);
+        bits |= (u32)q << (2 * k);      // == K's bits += q*4^k: the fields never overlap
+    }
+    return bits;
+}
+
+// The colour half shared by BC1 and BC3; K:494-533
+ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
+{
+    // mean, then centred covariance accumulated in texel order; K:377-417
+    float mean[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc += px[c][k];
+        mean[c] = acc / 16.0f;
+    }
+    float crr = 0.0f, crg = 0.0f, crb = 0.0f, cgg = 0.0f, cgb = 0.0f, cbb = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float r = px[0][k] - mean[0], g = px[1][k] - mean[1], b = px[2][k] - mean[2];
+        crr += r * r; crg += r * g; crb += r * b;
+        cgg += g * g; cgb += g * b; cbb += b * b;
+    }
+    const float eps = 0.001f;
+    crr += eps; cgg += eps; cbb += eps;
+
+    // 4 power iterations from (1,1,1), renormalised after iterations 1 and 3; K:184-205
+    float v0 = 1.0f, v1 = 1.0f, v2 = 1.0f;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        float a0 = crr * v0 + crg * v1 + crb * v2;
+        float a1 = crg * v0 + cgg * v1 + cgb * v2;
+        float a2 = crb * v0 + cgb * v1 + cbb * v2;
+        v0 = a0; v1 = a1; v2 = a2;
+        if (it & 1) {
+            float n2 = 0.0f;
+            n2 += a0 * a0; n2 += a1 * a1; n2 += a2 * a2;
+            float rn = 1.0f / sqrtf(n2);
+            v0 *= rn; v1 *= rn; v2 *= rn;
+        }
+    }
+    const float axis[3] = {v0, v1, v2};
+
+    // extreme projections -> endpoints; K:274-306 (min starts at 65536, max at 0)
+    float dmin = 65536.0f, dmax = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float d = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) d += (px[c][k] - mean[c]) * axis[c];
+        dmin = min_sse(dmin, d);
+        dmax = max_sse(dmax, d);
+    }
+    if (dmax - dmin < 1.0f) { dmin -= 0.5f; dmax += 0.5f; }
+    float n2 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) n2 += axis[c] * axis[c];
+    float inv = 1.0f / n2;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        lo[c] = clamp_sse(mean[c] + dmin * inv * axis[c], 0.0f, 255.0f);
+        hi[c] = clamp_sse(mean[c] + dmax * inv * axis[c], 0.0f, 255.0f);
+    }
+    int p0 = pack565(lo[0], lo[1], lo[2]), p1 = pack565(hi[0], hi[1], hi[2]);
+    if (p0 < p1) { int t = p0; p0 = p1; p1 = t; }
+    u32 bits = bc1_linear_indices(px, p0, p1);
+
+    // one least-squares refinement pass; K:419-480, :524-530
+    float ea[3], eb[3];
+    if ((bits ^ (bits * 4u)) < 4u) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) ea[c] = eb[c] = mean[c];
+    } else {
+        float atb1[3] = {0.0f, 0.0f, 0.0f};
+        float sq1 = 0.0f, sqq = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            float q = (float)((bits >> (2 * k)) & 3u);
+            float x = 3.0f - q;
+            sq1 += q;
+            sqq += q * q;
+#pragma unroll
+            for (int c = 0; c < 3; c++) atb1[c] += x * px[c][k];
+        }
+        float cxx = 16.0f * 9.0f - 6.0f * sq1 + sqq;
+        float cyy = sqq;
+        float cxy = 3.0f * sq1 - sqq;
+        float scale = 3.0f * (1.0f / (cxx * cyy - cxy * cxy));
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float total = mean[c] * 16.0f;
+            float atb2 = 3.0f * total - atb1[c];
+            float a = (atb1[c] * cyy - atb2 * cxy) * scale;
+            float b = (atb2 * cxx - atb1[c] * cxy) * scale;
+            ea[c] = clamp_sse(a, 0.0f, 255.0f);
+            eb[c] = clamp_sse(b, 0.0f, 255.0f);
+        }
+    }
+    p0 = pack565(ea[0], ea[1], ea[2]);
+    p1 = pack565(eb[0], eb[1], eb[2]);
+    if (p0 < p1) { int t = p0; p0 = p1; p1 = t; }
+    bits = bc1_linear_indices(px, p0, p1);
+
+    // linear order 0,1,2,3 -> BC1 codes 0,2,3,1; K:482-492
+    u32 lo_bits = bits & 0x55555555u, hi_bits = bits & 0xAAAAAAAAu;
+    w0 = ((u32)p1 << 16) + (u32)p0;
+    w1 = (hi_bits >> 1) + (hi_bits ^ (lo_bits << 1));
+}
+
+// BC3 alpha half; K:535-571
+ITW_HD void bc3_alpha_block(const float (&a)[16], u32& w0, u32& w1)
+{
+    float lo = 255.0f, hi = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { lo = min_sse(lo, a[k]); hi = max_sse(hi, a[k]); }
+    if (lo == hi) hi = lo + 0.1f;
+    unsigned long long idx = 0;
+    float scale = 7.0f / (hi - lo);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float proj = (a[k] - lo) * scale + 0.5f;
+        int q = clampi(cvt_x86(proj), 0, 7);
+        q = 7 - q;
+        if (q > 0) q++;
+        if (q == 8) q = 1;
+        idx |= (unsigned long long)q << (3 * k);
+    }
+    // bytes: alpha0 = max, alpha1 = min, then 48 index bits
+    u32 head = (u32)(clampi(cvt_x86(lo), 0, 255) * 256 + clampi(cvt_x86(hi), 0, 255));
+    w0 = head | ((u32)idx << 16);
+    w1 = (u32)(idx >> 16);
+}
+
+// Fetch the 16 texels of block (bx,by): four 128-bit loads when the surface is 16-byte aligned
+// (any padded or tight RGBA8 surface whose stride is a multiple of 16), else byte-safe loads.
+template <bool kVec16>
+ITW_HD void fetch_rows_rgba8(u32 (&tex)[16], const SurfaceView& s, int bx, int by)
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const uint8_t* p = s.ptr + (size_t)(by * 4 + y) * (size_t)s.stride + (size_t)bx * 16;
+        if (kVec16) {
+#if defined(__CUDA_ARCH__)
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+            tex[4 * y + 0] = v.x; tex[4 * y + 1] = v.y; tex[4 * y + 2] = v.z; tex[4 * y + 3] = v.w;
+#else
+            for (int x = 0; x < 4; x++) tex[4 * y + x] = reinterpret_cast<const u32*>(p)[x];
+#endif
+        } else {
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const uint8_t* t = p + 4 * x;
+                tex[4 * y + x] = (u32)t[0] | ((u32)t[1] << 8) | ((u32)t[2] << 16) | ((u32)t[3] << 24);
+            }
+        }
+    }
+}
+
+// One whole block: 16 packed RGBA8 texels in, 2 (BC1) or 4 (BC3) words out; K:573-596
+template <bool kAlpha>
+ITW_HD void bc1_bc3_encode_block(const u32 (&tex)[16], u32 (&out)[4])
+{
+    float px[3][16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        px[0][k] = (float)(tex[k] & 255u);
+        px[1][k] = (float)((tex[k] >> 8) & 255u);
+        px[2][k] = (float)((tex[k] >> 16) & 255u);
+    }
+    if (kAlpha) {
+        float al[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) al[k] = (float)(tex[k] >> 24);
+        bc3_alpha_block(al, out[0], out[1]);
+        bc1_colour_block(px, out[2], out[3]);
+    } else {
+        bc1_colour_block(px, out[0], out[1]);
+        out[2] = out[3] = 0;
+    }
+}
+
+#if defined(__CUDACC__)
+template <bool kAlpha, bool kVec16>
+__global__ void __launch_bounds__(128) bc1_bc3_kernel(SurfaceView s, uint8_t* __restrict__ dst)
+{
+    const int bw = s.width >> 2, bh = s.height >> 2;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)bw * bh) return;
+    const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
+
+    u32 tex[16], out[4];
+    fetch_rows_rgba8<kVec16>(tex, s, bx, by);
+    bc1_bc3_encode_block<kAlpha>(tex, out);
+    if (kAlpha) reinterpret_cast<uint4*>(dst)[id] = make_uint4(out[0], out[1], out[2], out[3]);
+    else        reinterpret_cast<uint2*>(dst)[id] = make_uint2(out[0], out[1]);
+}
+#endif
+
+}  // namespace itw

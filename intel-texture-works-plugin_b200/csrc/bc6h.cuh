@@ -1,0 +1,469 @@
+// bc6h.cuh -- BC6H (UF16) encoder (reference: kernel.ispc:2039-3139, cited as K:line).
+//
+// Mapping (same scheme as bc7.cuh): one warp owns a batch of kBc6Slots blocks; lanes are spread
+// over (block, shape) for the 32 PCA split bounds, over (block, mode, ranked shape) for the
+// two-region candidates, and over (block, mode) for the refinement chains.  BC6H texels are
+// non-integer floats up to 65535 and the per-texel error is truncated through an x86 float->int
+// conversion that overflows to INT_MIN (K:1178, quirk Q3), so NOTHING here may be re-associated:
+// every float sum stays inside one lane in the reference's texel order.
+//
+// The reference recomputes the 32 split bounds for every two-region mode it tries (K:2257-2273);
+// they only depend on the texels, so they are computed once per block here (same values).
+#pragma once
+#include "bc67_core.cuh"
+
+namespace itw {
+
+struct Bc6Params {
+    int slow_mode, fast_mode, refine_1p, refine_2p, fast_skip;
+};
+
+constexpr int kBc6Slots = 4;
+constexpr int kBc6MaxTwo = 6;    // two-region modes tried per block
+constexpr int kBc6MaxOne = 4;    // one-region modes tried per block
+
+// One mode the block will be encoded with: K's mode index (2..4 / 6..8 carry the wide channel),
+// endpoint precision and the quantised clamp window of K:2302-2330
+struct Bc6Entry {
+    int mode, epb;
+    int qbounds[8];
+};
+struct Bc6Warp {
+    float px[kBc6Slots][64];
+    float lo[kBc6Slots][3], hi[kBc6Slots][3];
+    float max_span[kBc6Slots];
+    int max_span_idx[kBc6Slots];
+    int keys[kBc6Slots][32], order[kBc6Slots][32];
+    Bc6Entry two[kBc6Slots][kBc6MaxTwo], one[kBc6Slots][kBc6MaxOne];
+    int ntwo[kBc6Slots], none[kBc6Slots];
+    float cand_err[kBc6Slots][kBc6MaxTwo][32];
+    int win_pos[kBc6Slots][kBc6MaxTwo];
+    float res_err[kBc6Slots][kBc6MaxTwo + kBc6MaxOne];
+    u32 res_code[kBc6Slots][kBc6MaxTwo + kBc6MaxOne][4];
+    int nvalid;
+};
+
+// ---- format data; K:2080-2125 ----
+ITW_HD int bc6_prefix(int mode)
+{
+    // 5-bit mode prefixes {0,1,2,6,10,14,18,22,26,30,3,7,11,15} packed 5 bits each
+    const unsigned long long lo = 0ull | (1ull << 5) | (2ull << 10) | (6ull << 15) | (10ull << 20) | (14ull << 25) |
+                                  (18ull << 30) | (22ull << 35) | (26ull << 40) | (30ull << 45) | (3ull << 50) | (7ull << 55);
+    if (mode < 12) return (int)((lo >> (5 * mode)) & 31ull);
+    return (mode == 12) ? 11 : 15;
+}
+ITW_HD int bc6_epb(int mode)      // endpoint bits of K's base modes 0,1,2,5,6,9,10..13
+{
+    switch (mode) {
+        case 0: return 10; case 1: return 7; case 2: return 11; case 5: return 9; case 6: return 8; case 9: return 6;
+        case 10: return 10; case 11: return 11; case 12: return 12; default: return 16;
+    }
+}
+// K:2090-2111: a float table read back through an int (truncation, quirk Q4)
+ITW_HD float bc6_span(int mode)
+{
+    const float f = 65535.0f;
+    float v;
+    switch (mode) {
+        case 0: v = 0.9f * f / 64.0f; break;
+        case 1: v = 0.9f * f / 4.0f; break;
+        case 2: v = 0.8f * f / 256.0f; break;
+        case 5: v = 0.9f * f / 32.0f; break;
+        case 6: v = 0.9f * f / 16.0f; break;
+        case 9: case 10: v = f; break;
+        case 11: v = 0.95f * f / 8.0f; break;
+        case 12: v = 0.95f * f / 32.0f; break;
+        default: v = 6.0f; break;
+    }
+    return (float)cvt_x86(v);
+}
+
+// ---- endpoint quantisation; K:2130-2169 ----
+ITW_HD int bc6_dequant(int v, int bits)
+{
+    if (bits >= 15) return v;
+    if (v == 0) return 0;
+    if (v == (1 << bits) - 1) return 0xFFFF;
+    return (int)(((u32)v * 2u + 1u) << (15 - bits));
+}
+ITW_HD int bc6_quant1(float e, int bits)
+{
+    const int top = (1 << bits) - 1;
+    return clampi(cvt_x86(e / (256.0f * 256.0f - 1.0f) * (float)top + 0.5f), 0, top);
+}
+// 8*pairs values: quantise, clamp RGB into the entry's window, decode in place
+ITW_HD void bc6_quant_dequant(const Bc6Entry& E, int* q, float* ep, int pairs)
+{
+    for (int i = 0; i < 2 * pairs; i++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int v = bc6_quant1(ep[4 * i + c], E.epb);
+            if (c < 3) v = clampi(v, E.qbounds[c], E.qbounds[4 + c]);
+            q[4 * i + c] = v;
+            ep[4 * i + c] = (float)bc6_dequant(v, E.epb);
+        }
+    }
+}
+
+// Decide whether `mode` fits the block's range and, if so, fill the entry; K:2332-2365, :2302-2330
+ITW_HD bool bc6_make_entry(Bc6Entry& E, const Bc6Warp& W, int slot, int mode, float margin)
+{
+    const float span = bc6_span(mode);
+    if (W.max_span[slot] * margin > span) return false;
+    const bool wide = !(mode >= 10 || mode <= 1 || mode == 5 || mode == 9);
+    const int widx = W.max_span_idx[slot];
+    E.epb = bc6_epb(mode);
+    E.mode = wide ? mode + widx : mode;
+    float bounds[8];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float sp = span;
+        if (wide) sp *= (c == widx) ? 2.0f : 1.0f;
+        float middle = (W.lo[slot][c] + W.hi[slot][c]) / 2.0f;
+        bounds[c] = middle - sp / 2.0f;
+        bounds[4 + c] = middle + sp / 2.0f;
+    }
+    bounds[3] = bounds[7] = 0.0f;                               // never-written slots read as zero (F6, Q2)
+#pragma unroll
+    for (int i = 0; i < 8; i++) E.qbounds[i] = bc6_quant1(bounds[i], E.epb);
+    return true;
+}
+
+// ---- header layouts -------------------------------------------------------------------------
+// The 5+72 (two-region) or 5+60 (one-region) header bits, LSB first.  Each step copies `n`
+// consecutive bits starting at bit `b` of field f (ascending, or descending when n is negative):
+// f = 0 mode prefix; f = 1 + 3*e + c is component c of endpoint e.  Endpoints 1..3 are stored as
+// differences from endpoint 0 (wrapped by the extraction) except in modes 9 and 10.  Same layout
+// as K:2392-2980, held as data (it is the D3D BC6H format definition).
+struct Bc6Step { int8_t f, b, n; };
+#define S_(f, b, n) {f, b, n}
+#define R0 1
+#define G0 2
+#define B0 3
+#define R1 4
+#define G1 5
+#define B1 6
+#define R2 7
+#define G2 8
+#define B2 9
+#define R3 10
+#define G3 11
+#define B3 12
+#define ITW_BC6_LAYOUT_INIT                                                                                         \
+    /* 0*/ {S_(0,0,2), S_(G2,4,1), S_(B2,4,1), S_(B3,4,1), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,5), S_(G3,4,1), S_(G2,0,4), S_(G1,0,5), S_(B3,0,1), S_(G3,0,4), S_(B1,0,5), S_(B3,1,1), S_(B2,0,4), S_(R2,0,5), S_(B3,2,1), S_(R3,0,5), S_(B3,3,1)}, \
+    /* 1*/ {S_(0,0,2), S_(G2,5,1), S_(G3,4,1), S_(G3,5,1), S_(R0,0,7), S_(B3,0,1), S_(B3,1,1), S_(B2,4,1), S_(G0,0,7), S_(B2,5,1), S_(B3,2,1), S_(G2,4,1), S_(B0,0,7), S_(B3,3,1), S_(B3,5,1), S_(B3,4,1), S_(R1,0,6), S_(G2,0,4), S_(G1,0,6), S_(G3,0,4), S_(B1,0,6), S_(B2,0,4), S_(R2,0,6), S_(R3,0,6)}, \
+    /* 2*/ {S_(0,0,5), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,5), S_(R0,10,1), S_(G2,0,4), S_(G1,0,4), S_(G0,10,1), S_(B3,0,1), S_(G3,0,4), S_(B1,0,4), S_(B0,10,1), S_(B3,1,1), S_(B2,0,4), S_(R2,0,5), S_(B3,2,1), S_(R3,0,5), S_(B3,3,1)}, \
+    /* 3*/ {S_(0,0,5), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,4), S_(R0,10,1), S_(G3,4,1), S_(G2,0,4), S_(G1,0,5), S_(G0,10,1), S_(G3,0,4), S_(B1,0,4), S_(B0,10,1), S_(B3,1,1), S_(B2,0,4), S_(R2,0,4), S_(B3,0,1), S_(B3,2,1), S_(R3,0,4), S_(G2,4,1), S_(B3,3,1)}, \
+    /* 4*/ {S_(0,0,5), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,4), S_(R0,10,1), S_(B2,4,1), S_(G2,0,4), S_(G1,0,4), S_(G0,10,1), S_(B3,0,1), S_(G3,0,4), S_(B1,0,5), S_(B0,10,1), S_(B2,0,4), S_(R2,0,4), S_(B3,1,1), S_(B3,2,1), S_(R3,0,4), S_(B3,4,1), S_(B3,3,1)}, \
+    /* 5*/ {S_(0,0,5), S_(R0,0,9), S_(B2,4,1), S_(G0,0,9), S_(G2,4,1), S_(B0,0,9), S_(B3,4,1), S_(R1,0,5), S_(G3,4,1), S_(G2,0,4), S_(G1,0,5), S_(B3,0,1), S_(G3,0,4), S_(B1,0,5), S_(B3,1,1), S_(B2,0,4), S_(R2,0,5), S_(B3,2,1), S_(R3,0,5), S_(B3,3,1)}, \
+    /* 6*/ {S_(0,0,5), S_(R0,0,8), S_(G3,4,1), S_(B2,4,1), S_(G0,0,8), S_(B3,2,1), S_(G2,4,1), S_(B0,0,8), S_(B3,3,1), S_(B3,4,1), S_(R1,0,6), S_(G2,0,4), S_(G1,0,5), S_(B3,0,1), S_(G3,0,4), S_(B1,0,5), S_(B3,1,1), S_(B2,0,4), S_(R2,0,6), S_(R3,0,6)}, \
+    /* 7*/ {S_(0,0,5), S_(R0,0,8), S_(B3,0,1), S_(B2,4,1), S_(G0,0,8), S_(G2,5,1), S_(G2,4,1), S_(B0,0,8), S_(G3,5,1), S_(B3,4,1), S_(R1,0,5), S_(G3,4,1), S_(G2,0,4), S_(G1,0,6), S_(G3,0,4), S_(B1,0,5), S_(B3,1,1), S_(B2,0,4), S_(R2,0,5), S_(B3,2,1), S_(R3,0,5), S_(B3,3,1)}, \
+    /* 8*/ {S_(0,0,5), S_(R0,0,8), S_(B3,1,1), S_(B2,4,1), S_(G0,0,8), S_(B2,5,1), S_(G2,4,1), S_(B0,0,8), S_(B3,5,1), S_(B3,4,1), S_(R1,0,5), S_(G3,4,1), S_(G2,0,4), S_(G1,0,5), S_(B3,0,1), S_(G3,0,4), S_(B1,0,6), S_(B2,0,4), S_(R2,0,5), S_(B3,2,1), S_(R3,0,5), S_(B3,3,1)}, \
+    /* 9*/ {S_(0,0,5), S_(R0,0,6), S_(G3,4,1), S_(B3,0,1), S_(B3,1,1), S_(B2,4,1), S_(G0,0,6), S_(G2,5,1), S_(B2,5,1), S_(B3,2,1), S_(G2,4,1), S_(B0,0,6), S_(G3,5,1), S_(B3,3,1), S_(B3,5,1), S_(B3,4,1), S_(R1,0,6), S_(G2,0,4), S_(G1,0,6), S_(G3,0,4), S_(B1,0,6), S_(B2,0,4), S_(R2,0,6), S_(R3,0,6)}, \
+    /*10*/ {S_(0,0,5), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,10), S_(G1,0,10), S_(B1,0,10)}, \
+    /*11*/ {S_(0,0,5), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,9), S_(R0,10,1), S_(G1,0,9), S_(G0,10,1), S_(B1,0,9), S_(B0,10,1)}, \
+    /*12*/ {S_(0,0,5), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,8), S_(R0,11,-2), S_(G1,0,8), S_(G0,11,-2), S_(B1,0,8), S_(B0,11,-2)}, \
+    /*13*/ {S_(0,0,5), S_(R0,0,10), S_(G0,0,10), S_(B0,0,10), S_(R1,0,4), S_(R0,15,-6), S_(G1,0,4), S_(G0,15,-6), S_(B1,0,4), S_(B0,15,-6)},
+constexpr int kBc6MaxSteps = 24;
+#if defined(__CUDACC__)
+static __device__ const Bc6Step d_bc6_layout[14][kBc6MaxSteps] = {ITW_BC6_LAYOUT_INIT};
+#endif
+static const Bc6Step h_bc6_layout[14][kBc6MaxSteps] = {ITW_BC6_LAYOUT_INIT};
+#undef S_
+#undef R0
+#undef G0
+#undef B0
+#undef R1
+#undef G1
+#undef B1
+#undef R2
+#undef G2
+#undef B2
+#undef R3
+#undef G3
+#undef B3
+
+ITW_HD void bc6_put_header(BitSink& s, const int* q, int mode)
+{
+    const bool delta = !(mode == 9 || mode == 10);
+#if defined(__CUDA_ARCH__)
+    const Bc6Step* steps = d_bc6_layout[mode];
+#else
+    const Bc6Step* steps = h_bc6_layout[mode];
+#endif
+    for (int i = 0; i < kBc6MaxSteps; i++) {
+        const int f = steps[i].f, b = steps[i].b, n = steps[i].n;
+        if (n == 0) break;
+        int value;
+        if (f == 0) value = bc6_prefix(mode);
+        else {
+            const int e = (f - 1) / 3, c = (f - 1) % 3;
+            value = q[4 * e + c];
+            if (delta && e > 0) value -= q[c];
+        }
+        if (n > 0) s.put(n, (u32)value >> b);
+        else
+            for (int j = 0; j < -n; j++) s.put(1, ((u32)value >> (b - j)) & 1u);
+    }
+}
+
+// ---- candidate / chains; K:2174-2300, :2982-3031 ----
+ITW_HD float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, int* q, u32& idx0, u32& idx1)
+{
+    float ep[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) ep[i] = 0.0f;
+    for (int j = 0; j < 2; j++) fit_segment(ep + 8 * j, px, shape_mask(shape, j), 3, false);
+    bc6_quant_dequant(E, q, ep, 2);
+    return assign_indices(idx0, idx1, px, 3, ep, shape_pattern(shape), 3);
+}
+ITW_HD void bc6_chain_two_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
+{
+    W.res_err[slot][e] = inf_f();
+    const int pos = W.win_pos[slot][e];
+    if (pos < 0) return;
+    const float* px = W.px[slot];
+    const Bc6Entry& E = W.two[slot][e];
+    const int shape = W.order[slot][pos] & 31;
+    int best_q[16];
+    u32 best_i0, best_i1;
+    float best_err = bc6_eval_two_region(px, E, shape, best_q, best_i0, best_i1);
+    for (int it = 0; it < P.refine_2p; it++) {
+        float ep[16];
+        int q[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) ep[i] = 0.0f;
+        for (int j = 0; j < 2; j++) solve_endpoints(ep + 8 * j, px, 3, best_i0, best_i1, shape_mask(shape, j), 3);
+        bc6_quant_dequant(E, q, ep, 2);
+        u32 i0, i1;
+        float err = assign_indices(i0, i1, px, 3, ep, shape_pattern(shape), 3);
+        if (err < best_err) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) best_q[i] = q[i];
+            best_i0 = i0; best_i1 = i1;
+            best_err = err;
+        }
+    }
+    W.res_err[slot][e] = best_err;
+    int flips = orient_subsets(best_q, best_i0, best_i1, 3, 2, shape);
+    BitSink s;
+    s.reset();
+    bc6_put_header(s, best_q, E.mode);
+    s.put(5, (u32)shape);
+    put_indices(s, best_i0, best_i1, 3, flips, shape_anchor(shape, 1), -1);
+    u32* out = W.res_code[slot][e];
+    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
+}
+ITW_HD void bc6_chain_one_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
+{
+    const float* px = W.px[slot];
+    const Bc6Entry& E = W.one[slot][e];
+    const int role = W.ntwo[slot] + e;
+    float ep[8];
+    int q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ep[i] = 0.0f;
+    fit_segment(ep, px, 0xFFFF, 3, false);
+    bc6_quant_dequant(E, q, ep, 1);
+    u32 i0, i1;
+    float err = assign_indices(i0, i1, px, 4, ep, 0u, 3);
+    for (int it = 0; it < P.refine_1p; it++) {
+        solve_endpoints(ep, px, 4, i0, i1, 0xFFFF, 3);
+        bc6_quant_dequant(E, q, ep, 1);
+        err = assign_indices(i0, i1, px, 4, ep, 0u, 3);
+    }
+    W.res_err[slot][role] = err;
+    orient_single(q, 4, i0, i1, 4);
+    BitSink s;
+    s.reset();
+    bc6_put_header(s, q, E.mode);
+    put_indices(s, i0, i1, 4, 0, -1, -1);
+    u32* out = W.res_code[slot][role];
+    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
+}
+
+// =============================================================================================
+// warp program
+// =============================================================================================
+// half bits -> the reference's working scale v = (h/31)*64; K:134-151, :3048
+ITW_HD void bc6_phase_load(int lane, Bc6Warp& W, const SurfaceView& s, long long first_block, int nvalid)
+{
+    const int bw = s.width >> 2;
+    for (int t = lane; t < nvalid * 16; t += 32) {
+        const int slot = t >> 4, k = t & 15;
+        const long long id = first_block + slot;
+        const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
+        const uint8_t* p = s.ptr + (size_t)(by * 4 + (k >> 2)) * (size_t)s.stride + (size_t)(bx * 4 + (k & 3)) * 8;
+        float* px = W.px[slot];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int h = (int)p[2 * c] | ((int)p[2 * c + 1] << 8);
+            px[16 * c + k] = ((float)h / 31.0f) * 64.0f;
+        }
+        px[48 + k] = 0.0f;
+    }
+    if (lane == 0) W.nvalid = nvalid;
+}
+// per-block range, then the list of modes this block is encoded with; K:3036-3107
+ITW_HD void bc6_phase_setup(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    for (int slot = lane; slot < W.nvalid; slot += 32) {
+        const float* px = W.px[slot];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float lo = 65535.0f, hi = 0.0f;
+            for (int k = 0; k < 16; k++) { lo = min_sse(lo, px[16 * c + k]); hi = max_sse(hi, px[16 * c + k]); }
+            W.lo[slot][c] = lo;
+            W.hi[slot][c] = hi;
+        }
+        float max_span = 0.0f;
+        int max_idx = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float sp = W.hi[slot][c] - W.lo[slot][c];
+            if (sp > max_span) { max_idx = c; max_span = sp; }
+        }
+        W.max_span[slot] = max_span;
+        W.max_span_idx[slot] = max_idx;
+
+        int ntwo = 0, none = 0;
+        if (P.slow_mode) {                                       // every mode, margin 0; K:3073-3085
+            const int m2[6] = {0, 1, 2, 5, 6, 9};
+            for (int i = 0; i < 6; i++)
+                if (bc6_make_entry(W.two[slot][ntwo], W, slot, m2[i], 0.0f)) ntwo++;
+            for (int m = 10; m <= 13; m++)
+                if (bc6_make_entry(W.one[slot][none], W, slot, m, 0.0f)) none++;
+        } else {                                                 // the last mode whose span test passes; K:3086-3106
+            if (P.fast_skip > 0) {
+                const float m12 = 1.0f / 1.2f;
+                bc6_make_entry(W.two[slot][0], W, slot, 9, 0.0f);
+                if (P.fast_mode) bc6_make_entry(W.two[slot][0], W, slot, 1, 1.0f);
+                bc6_make_entry(W.two[slot][0], W, slot, 6, m12);
+                bc6_make_entry(W.two[slot][0], W, slot, 5, m12);
+                bc6_make_entry(W.two[slot][0], W, slot, 0, m12);
+                bc6_make_entry(W.two[slot][0], W, slot, 2, 1.0f);
+                ntwo = 1;
+                if (!P.fast_mode && bc6_make_entry(W.two[slot][1], W, slot, 1, 0.0f)) ntwo = 2;
+            }
+            bc6_make_entry(W.one[slot][0], W, slot, 10, 0.0f);
+            bc6_make_entry(W.one[slot][0], W, slot, 11, 1.0f);
+            bc6_make_entry(W.one[slot][0], W, slot, 12, 1.0f);
+            bc6_make_entry(W.one[slot][0], W, slot, 13, 1.0f);
+            none = 1;
+        }
+        W.ntwo[slot] = ntwo;
+        W.none[slot] = none;
+    }
+}
+ITW_HD void bc6_phase_keys(int lane, Bc6Warp& W)
+{
+    for (int t = lane; t < W.nvalid * 32; t += 32) {
+        const int slot = t >> 5, shape = t & 31;
+        float full[15];
+        masked_moments(full, W.px[slot], 0xFFFF, 3);
+        W.keys[slot][shape] = split_bound_key(W.px[slot], shape, full, 3);
+    }
+}
+ITW_HD void bc6_phase_rank(int lane, Bc6Warp& W)
+{
+    for (int t = lane; t < W.nvalid * 32; t += 32) {
+        const int slot = t >> 5, i = t & 31;
+        W.order[slot][rank_of(W.keys[slot], 32, i)] = W.keys[slot][i];
+    }
+}
+ITW_HD void bc6_phase_candidates(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    const int count = P.fast_skip, per = kBc6MaxTwo * count;
+    for (int t = lane; t < W.nvalid * per; t += 32) {
+        const int slot = t / per, r = t - slot * per;
+        const int e = r / count, n = r - e * count;
+        if (e >= W.ntwo[slot]) continue;
+        int q[16];
+        u32 i0, i1;
+        W.cand_err[slot][e][n] = bc6_eval_two_region(W.px[slot], W.two[slot][e], W.order[slot][n] & 31, q, i0, i1);
+    }
+}
+ITW_HD void bc6_phase_winners(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    for (int t = lane; t < W.nvalid * kBc6MaxTwo; t += 32) {
+        const int slot = t / kBc6MaxTwo, e = t - slot * kBc6MaxTwo;
+        int best = -1;
+        float best_err = inf_f();
+        if (e < W.ntwo[slot])
+            for (int n = 0; n < P.fast_skip; n++) {
+                float v = W.cand_err[slot][e][n];
+                if (v < best_err) { best_err = v; best = n; }
+            }
+        W.win_pos[slot][e] = best;
+    }
+}
+ITW_HD void bc6_phase_chain_two(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    for (int t = lane; t < W.nvalid * kBc6MaxTwo; t += 32) {
+        const int slot = t / kBc6MaxTwo, e = t - slot * kBc6MaxTwo;
+        if (e < W.ntwo[slot]) bc6_chain_two_region(W, P, slot, e);
+    }
+}
+ITW_HD void bc6_phase_chain_one(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    for (int t = lane; t < W.nvalid * kBc6MaxOne; t += 32) {
+        const int slot = t / kBc6MaxOne, e = t - slot * kBc6MaxOne;
+        if (e < W.none[slot]) bc6_chain_one_region(W, P, slot, e);
+    }
+}
+ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_block)
+{
+    for (int t = lane; t < W.nvalid; t += 32) {
+        const int nroles = W.ntwo[t] + W.none[t];
+        float best_err = inf_f();
+        u32 code[4] = {0u, 0u, 0u, 0u};
+        for (int r = 0; r < nroles; r++) {
+            float e = W.res_err[t][r];
+            if (e < best_err) {
+                best_err = e;
+#pragma unroll
+                for (int i = 0; i < 4; i++) code[i] = W.res_code[t][r][i];
+            }
+        }
+        u32* out = reinterpret_cast<u32*>(dst + (size_t)(first_block + t) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = code[i];
+    }
+}
+
+#define ITW_BC6_PROGRAM(PHASE)                                             \
+    PHASE(bc6_phase_load(lane, W, surf, first_block, nvalid));             \
+    PHASE(bc6_phase_setup(lane, W, P));                                    \
+    if (P.slow_mode || P.fast_skip > 0) {                                  \
+        PHASE(bc6_phase_keys(lane, W));                                    \
+        PHASE(bc6_phase_rank(lane, W));                                    \
+        PHASE(bc6_phase_candidates(lane, W, P));                           \
+        PHASE(bc6_phase_winners(lane, W, P));                              \
+        PHASE(bc6_phase_chain_two(lane, W, P));                            \
+    }                                                                      \
+    PHASE(bc6_phase_chain_one(lane, W, P));                                \
+    PHASE(bc6_phase_store(lane, W, dst, first_block));
+
+#if defined(__CUDACC__)
+constexpr int kBc6WarpsPerCta = 4;
+
+__global__ void __launch_bounds__(kBc6WarpsPerCta * 32)
+bc6h_kernel(SurfaceView surf, uint8_t* __restrict__ dst, Bc6Params P, long long nblocks)
+{
+    __shared__ Bc6Warp warps[kBc6WarpsPerCta];
+    Bc6Warp& W = warps[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const long long nbatches = (nblocks + kBc6Slots - 1) / kBc6Slots;
+    const long long warp0 = (long long)blockIdx.x * kBc6WarpsPerCta + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kBc6WarpsPerCta;
+    for (long long batch = warp0; batch < nbatches; batch += nwarps) {
+        const long long first_block = batch * kBc6Slots;
+        const int nvalid = (int)((nblocks - first_block < kBc6Slots) ? (nblocks - first_block) : kBc6Slots);
+#define ITW_PHASE_DEVICE(call) call; __syncwarp()
+        ITW_BC6_PROGRAM(ITW_PHASE_DEVICE)
+#undef ITW_PHASE_DEVICE
+    }
+}
+#endif
+
+}  // namespace itw

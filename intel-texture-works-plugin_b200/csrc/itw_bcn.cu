@@ -1,0 +1,284 @@
+// itw_bcn.cu -- host side of libitw_bcn.so: the reference's C-ABI (include/itw_bcn.h section 1,
+// replacing 3rdParty/Intel/Source/ispc_texcomp.cpp:20-435) plus the additive entry points.
+//
+// There is NO CPU fallback in this library: every encode runs the sm_100a kernels or fails with a
+// message retrievable through itw_get_last_error().
+//
+// Threading: the reference is called concurrently from up to 64 pool threads on disjoint row
+// bands (win32Threads.cpp:211-274).  All mutable state here is thread_local (one CUDA stream,
+// one set of staging buffers and timing events per calling thread), so calls are re-entrant.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/itw_bcn.h"
+#include "bc4_bc5.cuh"
+#include "itw_params.h"
+
+using namespace itw;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+struct ThreadCtx {
+    int device = -1;             // device the resources below belong to
+    int wanted_device = -1;      // itw_set_device() request, -1 = keep the current device
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint8_t* d_in = nullptr;  size_t d_in_cap = 0;
+    uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+    int sm_count = 0;
+    std::string err;
+};
+thread_local ThreadCtx tls;
+
+int fail(const char* what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof(buf), "%s", what);
+    tls.err = buf;
+    return -1;
+}
+#define ITW_CUDA(call)                                             \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail(#call, e_);             \
+    } while (0)
+
+int ensure_ctx()
+{
+    ThreadCtx& c = tls;
+    int dev = 0;
+    if (c.wanted_device >= 0) {
+        ITW_CUDA(cudaSetDevice(c.wanted_device));
+        dev = c.wanted_device;
+    } else {
+        ITW_CUDA(cudaGetDevice(&dev));
+    }
+    if (c.device == dev && c.stream) return 0;
+    if (c.stream) {                       // device changed: drop the old resources
+        cudaStreamDestroy(c.stream); cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
+        cudaFree(c.d_in); cudaFree(c.d_out);
+        c = ThreadCtx();
+        c.wanted_device = dev;
+    }
+    cudaDeviceProp prop;
+    ITW_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail("libitw_bcn needs an sm_100a (Blackwell) device");
+    c.sm_count = prop.multiProcessorCount;
+    ITW_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    ITW_CUDA(cudaEventCreate(&c.ev0));
+    ITW_CUDA(cudaEventCreate(&c.ev1));
+    c.device = dev;
+    return 0;
+}
+int grow(uint8_t*& p, size_t& cap, size_t need)
+{
+    if (need <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    ITW_CUDA(cudaMalloc(&p, need));
+    cap = need;
+    return 0;
+}
+bool is_device_pointer(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct FormatInfo { int bpb; int texel_bytes; };
+bool format_info(int format, FormatInfo& f)
+{
+    switch (format) {
+        case ITW_FORMAT_BC1: case ITW_FORMAT_BC4: f = {8, 4}; return true;
+        case ITW_FORMAT_BC3: case ITW_FORMAT_BC5: case ITW_FORMAT_BC7: f = {16, 4}; return true;
+        case ITW_FORMAT_BC6H: f = {16, 8}; return true;
+        default: return false;
+    }
+}
+int check_surface(const rgba_surface* s, const FormatInfo& f)
+{
+    if (!s || !s->ptr) return fail("null surface");
+    if (s->width <= 0 || s->height <= 0 || (s->width & 3) || (s->height & 3))
+        return fail("surface width/height must be positive multiples of 4 (ispc_texcomp.h:93-95)");
+    if ((long long)s->stride < (long long)s->width * f.texel_bytes) return fail("surface stride smaller than a texel row");
+    return 0;
+}
+
+// Enqueue the kernel for one device-resident surface on `stream`.
+int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* settings, cudaStream_t stream)
+{
+    const long long nblocks = (long long)(v.width >> 2) * (v.height >> 2);
+    const bool vec16 = ((reinterpret_cast<uintptr_t>(v.ptr) | (uintptr_t)v.stride) & 15u) == 0;
+    const unsigned grid1 = (unsigned)((nblocks + 127) / 128);
+    switch (format) {
+        case ITW_FORMAT_BC1:
+            if (vec16) bc1_bc3_kernel<false, true><<<grid1, 128, 0, stream>>>(v, d_dst);
+            else       bc1_bc3_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+            break;
+        case ITW_FORMAT_BC3:
+            if (vec16) bc1_bc3_kernel<true, true><<<grid1, 128, 0, stream>>>(v, d_dst);
+            else       bc1_bc3_kernel<true, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+            break;
+        case ITW_FORMAT_BC4:
+            if (vec16) bc4_bc5_kernel<false, true><<<grid1, 128, 0, stream>>>(v, d_dst);
+            else       bc4_bc5_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+            break;
+        case ITW_FORMAT_BC5:
+            if (vec16) bc4_bc5_kernel<true, true><<<grid1, 128, 0, stream>>>(v, d_dst);
+            else       bc4_bc5_kernel<true, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+            break;
+        case ITW_FORMAT_BC7: {
+            if (!settings) return fail("CompressBlocksBC7: null settings");
+            const Bc7Params P = bc7_params_from(*static_cast<const bc7_enc_settings*>(settings));
+            if (const char* why = bc7_params_check(P)) return fail(why);
+            int occ = 1;
+            ITW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bc7_kernel, kBc7WarpsPerCta * 32, 0));
+            const long long want = (nblocks + kBc7Slots * kBc7WarpsPerCta - 1) / (kBc7Slots * kBc7WarpsPerCta);
+            const long long cap = (long long)tls.sm_count * (occ > 0 ? occ : 1);
+            bc7_kernel<<<(unsigned)(want < cap ? want : cap), kBc7WarpsPerCta * 32, 0, stream>>>(v, d_dst, P, nblocks);
+            break;
+        }
+        case ITW_FORMAT_BC6H: {
+            if (!settings) return fail("CompressBlocksBC6H: null settings");
+            const Bc6Params P = bc6_params_from(*static_cast<const bc6h_enc_settings*>(settings));
+            if (const char* why = bc6_params_check(P)) return fail(why);
+            int occ = 1;
+            ITW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bc6h_kernel, kBc6WarpsPerCta * 32, 0));
+            const long long want = (nblocks + kBc6Slots * kBc6WarpsPerCta - 1) / (kBc6Slots * kBc6WarpsPerCta);
+            const long long cap = (long long)tls.sm_count * (occ > 0 ? occ : 1);
+            bc6h_kernel<<<(unsigned)(want < cap ? want : cap), kBc6WarpsPerCta * 32, 0, stream>>>(v, d_dst, P, nblocks);
+            break;
+        }
+        default: return fail("unknown format");
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    ITW_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// The CompressBlocks* path: src and dst may each be host or device memory.
+int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* settings)
+{
+    tls.err.clear();
+    FormatInfo f;
+    if (!format_info(format, f)) return fail("unknown format");
+    if (check_surface(src, f)) return -1;
+    if (!dst) return fail("null dst");
+    if (ensure_ctx()) return -1;
+    ThreadCtx& c = tls;
+    const size_t row_bytes = (size_t)src->width * f.texel_bytes;
+    const size_t out_bytes = (size_t)(src->width >> 2) * (src->height >> 2) * f.bpb;
+    const bool src_dev = is_device_pointer(src->ptr), dst_dev = is_device_pointer(dst);
+
+    SurfaceView v{src->ptr, src->width, src->height, src->stride};
+    if (!src_dev) {                      // H2D of the tightly packed rows (pinned sources copy at PCIe rate)
+        if (grow(c.d_in, c.d_in_cap, row_bytes * src->height)) return -1;
+        ITW_CUDA(cudaMemcpy2DAsync(c.d_in, row_bytes, src->ptr, (size_t)src->stride, row_bytes, (size_t)src->height,
+                                   cudaMemcpyHostToDevice, c.stream));
+        v.ptr = c.d_in;
+        v.stride = (int)row_bytes;
+    }
+    uint8_t* d_dst = dst;
+    const bool dst_ok = dst_dev && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    if (!dst_ok) {
+        if (grow(c.d_out, c.d_out_cap, out_bytes)) return -1;
+        d_dst = c.d_out;
+    }
+    ITW_CUDA(cudaEventRecord(c.ev0, c.stream));
+    if (launch(format, v, d_dst, settings, c.stream)) return -1;
+    ITW_CUDA(cudaEventRecord(c.ev1, c.stream));
+    c.timed = true;
+    if (!dst_ok)
+        ITW_CUDA(cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    ITW_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- profiles (ispc_texcomp.cpp:20-410) ----
+void GetProfile_ultrafast(bc7_enc_settings* s) { bc7_fill_profile(s, 0); }
+void GetProfile_veryfast(bc7_enc_settings* s) { bc7_fill_profile(s, 1); }
+void GetProfile_fast(bc7_enc_settings* s) { bc7_fill_profile(s, 2); }
+void GetProfile_basic(bc7_enc_settings* s) { bc7_fill_profile(s, 3); }
+void GetProfile_slow(bc7_enc_settings* s) { bc7_fill_profile(s, 4); }
+void GetProfile_alpha_ultrafast(bc7_enc_settings* s) { bc7_fill_profile(s, 5); }
+void GetProfile_alpha_veryfast(bc7_enc_settings* s) { bc7_fill_profile(s, 6); }
+void GetProfile_alpha_fast(bc7_enc_settings* s) { bc7_fill_profile(s, 7); }
+void GetProfile_alpha_basic(bc7_enc_settings* s) { bc7_fill_profile(s, 8); }
+void GetProfile_alpha_slow(bc7_enc_settings* s) { bc7_fill_profile(s, 9); }
+void GetProfile_bc6h_veryfast(bc6h_enc_settings* s) { bc6_fill_profile(s, 0); }
+void GetProfile_bc6h_fast(bc6h_enc_settings* s) { bc6_fill_profile(s, 1); }
+void GetProfile_bc6h_basic(bc6h_enc_settings* s) { bc6_fill_profile(s, 2); }
+void GetProfile_bc6h_slow(bc6h_enc_settings* s) { bc6_fill_profile(s, 3); }
+void GetProfile_bc6h_veryslow(bc6h_enc_settings* s) { bc6_fill_profile(s, 4); }
+
+// ---- the reference's encode entry points (ispc_texcomp.cpp:417-435) ----
+void CompressBlocksBC1(const rgba_surface* src, uint8_t* dst) { encode_any(ITW_FORMAT_BC1, src, dst, nullptr); }
+void CompressBlocksBC3(const rgba_surface* src, uint8_t* dst) { encode_any(ITW_FORMAT_BC3, src, dst, nullptr); }
+void CompressBlocksBC6H(const rgba_surface* src, uint8_t* dst, bc6h_enc_settings* settings) { encode_any(ITW_FORMAT_BC6H, src, dst, settings); }
+void CompressBlocksBC7(const rgba_surface* src, uint8_t* dst, bc7_enc_settings* settings) { encode_any(ITW_FORMAT_BC7, src, dst, settings); }
+
+// ---- additive ----
+void CompressBlocksBC4(const rgba_surface* src, uint8_t* dst) { encode_any(ITW_FORMAT_BC4, src, dst, nullptr); }
+void CompressBlocksBC5(const rgba_surface* src, uint8_t* dst) { encode_any(ITW_FORMAT_BC5, src, dst, nullptr); }
+
+int itw_bytes_per_block(int format)
+{
+    FormatInfo f;
+    return format_info(format, f) ? f.bpb : 0;
+}
+
+int itw_encode_device(int format, const rgba_surface* src, uint8_t* dst, const void* settings, void* cuda_stream)
+{
+    tls.err.clear();
+    FormatInfo f;
+    if (!format_info(format, f)) return fail("unknown format");
+    if (check_surface(src, f)) return -1;
+    if (!dst) return fail("null dst");
+    if (reinterpret_cast<uintptr_t>(dst) & 15u) return fail("itw_encode_device: dst must be 16-byte aligned");
+    if (ensure_ctx()) return -1;
+    tls.timed = false;
+    SurfaceView v{src->ptr, src->width, src->height, src->stride};
+    return launch(format, v, dst, settings, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int itw_encode_batch(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings)
+{
+    for (int i = 0; i < count; i++)
+        if (encode_any(format, &srcs[i], dsts[i], settings)) return -1;
+    return 0;
+}
+
+int itw_set_device(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return fail("itw_set_device: no such device");
+    tls.wanted_device = device;
+    return 0;
+}
+
+const char* itw_get_last_error(void) { return tls.err.c_str(); }
+
+uint64_t itw_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+float itw_last_kernel_ms(void)
+{
+    float ms = -1.0f;
+    if (tls.timed && cudaEventElapsedTime(&ms, tls.ev0, tls.ev1) != cudaSuccess) { cudaGetLastError(); ms = -1.0f; }
+    return ms;
+}
+
+}  // extern "C"

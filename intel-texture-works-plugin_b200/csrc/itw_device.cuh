@@ -1,0 +1,109 @@
+// itw_device.cuh -- building blocks shared by the BCn kernels (sm_100a).
+//
+// Float model.  The reference encoder (IntelCompressionPlugin/kernel.ispc, cited as K:line) is
+// float32 code whose results depend on operation order.  The kernels reproduce the canonical
+// strict-IEEE execution of that source (DESIGN.md "Canonical float model"):
+//   * device code is compiled with -fmad=false (no FMA contraction), IEEE division and square
+//     root (-prec-div=true -prec-sqrt=true), denormals kept (-ftz=false);
+//   * float->int goes through cvt_x86(), which reproduces x86 cvttss2si (NaN / out of range ->
+//     INT_MIN) instead of CUDA's saturating conversion;
+//   * min/max use the SSE operand order ((a<b)?a:b, (a>b)?a:b), not fminf/fmaxf.
+// Where a quantity is provably an exact small integer, integer or fused arithmetic may be used
+// instead -- the result is identical by construction and each such place says why.
+//
+// Everything here is __host__ __device__: the kernels' per-lane logic can be executed on the CPU
+// by tests/emu (a TEST-ONLY lane-by-lane emulation used to debug without a GPU).  The product
+// library never runs this code on the host.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define ITW_HD __host__ __device__ __forceinline__
+#define ITW_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define ITW_HD inline
+#define ITW_HD_NOINLINE
+#endif
+
+#include "itw_tables.cuh"
+
+namespace itw {
+
+typedef uint32_t u32;
+
+ITW_HD int cvt_x86(float f)
+{
+    // cvttss2si: truncation; NaN, +-inf and |f| >= 2^31 give 0x80000000
+#if defined(__CUDA_ARCH__)
+    int r = __float2int_rz(f);
+    return (fabsf(f) < 2147483648.0f) ? r : (int)0x80000000;
+#else
+    if (!(f >= -2147483648.0f && f < 2147483648.0f)) return (int)0x80000000;
+    return (int)f;
+#endif
+}
+ITW_HD float min_sse(float a, float b) { return (a < b) ? a : b; }
+ITW_HD float max_sse(float a, float b) { return (a > b) ? a : b; }
+ITW_HD float clamp_sse(float v, float lo, float hi) { return min_sse(max_sse(v, lo), hi); }
+ITW_HD int mini(int a, int b) { return (a < b) ? a : b; }
+ITW_HD int maxi(int a, int b) { return (a > b) ? a : b; }
+ITW_HD int clampi(int v, int lo, int hi) { return mini(maxi(v, lo), hi); }
+ITW_HD float sq(float v) { return v * v; }
+ITW_HD float inf_f()
+{
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(0x7f800000);
+#else
+    return INFINITY;
+#endif
+}
+
+// Shape ids: 0..63 two-subset, 64..127 three-subset (the convention of K:1313-1314).
+ITW_HD u32 shape_pattern(int shape) { return ITW_TABLE(shape_pattern)[shape]; }
+ITW_HD int shape_mask(int shape, int subset)
+{
+    u32 m = ITW_TABLE(shape_mask01)[shape];
+    u32 m0 = m & 0xFFFFu, m1 = m >> 16;
+    return (int)((subset == 0) ? m0 : ((subset == 1) ? m1 : (~(m0 | m1) & 0xFFFFu)));
+}
+ITW_HD int shape_anchor(int shape, int subset)
+{
+    return (subset == 0) ? 0
+                         : ((subset == 1) ? (int)ITW_TABLE(shape_anchor1)[shape] : (int)ITW_TABLE(shape_anchor2)[shape]);
+}
+// BC7 interpolation weight of index q at `bits` bits per index; K:675-686
+ITW_HD int bc7_weight(int bits, int q)
+{
+    int base = (bits == 2) ? 0 : ((bits == 3) ? 4 : 12);
+    return ITW_TABLE(weights)[base + q];
+}
+
+// LSB-first writer into one 128-bit block held in four registers
+struct BitSink {
+    u32 w0, w1, w2, w3;
+    int pos;
+    ITW_HD void reset() { w0 = w1 = w2 = w3 = 0; pos = 0; }
+    ITW_HD void put(int nbits, u32 v)
+    {
+        if (nbits <= 0) return;
+        if (nbits < 32) v &= (1u << nbits) - 1u;
+        unsigned long long wide = (unsigned long long)v << (pos & 31);
+        u32 lo = (u32)wide, hi = (u32)(wide >> 32);
+        int word = pos >> 5;
+        if (word == 0) { w0 |= lo; w1 |= hi; }
+        else if (word == 1) { w1 |= lo; w2 |= hi; }
+        else if (word == 2) { w2 |= lo; w3 |= hi; }
+        else if (word == 3) { w3 |= lo; }
+        pos += nbits;
+    }
+};
+
+struct SurfaceView {
+    const uint8_t* ptr;  // pointer to texel (0,0) (device memory for the kernels)
+    int width, height;   // texels, multiples of 4
+    int stride;          // bytes between rows
+};
+
+}  // namespace itw

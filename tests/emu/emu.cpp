@@ -1,0 +1,65 @@
+// emu.cpp -- TEST-ONLY lane-by-lane CPU execution of the product's kernel logic.
+//
+// The CUDA kernels in intel-texture-works-plugin_b200/csrc/*.cuh are written as per-lane phase
+// functions (__host__ __device__).  This file compiles the very same headers with g++ and drives
+// every phase for lanes 0..31 in turn, with a warp barrier between phases, so the kernels' logic
+// (everything except the GPU's own float instructions) can be checked against the oracle on a
+// machine without a GPU.  It is built by tests/emu/build_emu.py into tests/emu/libitw_emu.so and
+// is loaded only by tests.  The product library never contains or calls this code.
+#include <cstring>
+#include "../../intel-texture-works-plugin_b200/csrc/bc4_bc5.cuh"
+#include "../../intel-texture-works-plugin_b200/csrc/itw_params.h"
+
+using namespace itw;
+
+static SurfaceView view_of(const rgba_surface* s) { return SurfaceView{s->ptr, s->width, s->height, s->stride}; }
+
+template <class F>
+static void per_block(const rgba_surface* src, uint8_t* dst, int bpb, F f)
+{
+    SurfaceView s = view_of(src);
+    const int bw = s.width / 4, bh = s.height / 4;
+    for (int by = 0; by < bh; by++)
+        for (int bx = 0; bx < bw; bx++) {
+            u32 tex[16], out[4];
+            fetch_rows_rgba8<false>(tex, s, bx, by);
+            f(tex, out);
+            memcpy(dst + ((size_t)by * bw + bx) * bpb, out, bpb);
+        }
+}
+
+extern "C" {
+void emu_CompressBlocksBC1(const rgba_surface* src, uint8_t* dst)
+{ per_block(src, dst, 8, [](const u32 (&t)[16], u32 (&o)[4]) { bc1_bc3_encode_block<false>(t, o); }); }
+void emu_CompressBlocksBC3(const rgba_surface* src, uint8_t* dst)
+{ per_block(src, dst, 16, [](const u32 (&t)[16], u32 (&o)[4]) { bc1_bc3_encode_block<true>(t, o); }); }
+void emu_CompressBlocksBC4(const rgba_surface* src, uint8_t* dst)
+{ per_block(src, dst, 8, [](const u32 (&t)[16], u32 (&o)[4]) { bc4_bc5_encode_block<false>(t, o); }); }
+void emu_CompressBlocksBC5(const rgba_surface* src, uint8_t* dst)
+{ per_block(src, dst, 16, [](const u32 (&t)[16], u32 (&o)[4]) { bc4_bc5_encode_block<true>(t, o); }); }
+
+#define ITW_PHASE_EMU(call) for (int lane = 0; lane < 32; lane++) { call; }
+
+void emu_CompressBlocksBC7(const rgba_surface* src, uint8_t* dst, bc7_enc_settings* settings)
+{
+    SurfaceView surf = view_of(src);
+    const Bc7Params P = bc7_params_from(*settings);
+    const long long nblocks = (long long)(surf.width / 4) * (surf.height / 4);
+    static thread_local Bc7Warp W;
+    for (long long first_block = 0; first_block < nblocks; first_block += kBc7Slots) {
+        const int nvalid = (int)((nblocks - first_block < kBc7Slots) ? (nblocks - first_block) : kBc7Slots);
+        ITW_BC7_PROGRAM(ITW_PHASE_EMU)
+    }
+}
+void emu_CompressBlocksBC6H(const rgba_surface* src, uint8_t* dst, bc6h_enc_settings* settings)
+{
+    SurfaceView surf = view_of(src);
+    const Bc6Params P = bc6_params_from(*settings);
+    const long long nblocks = (long long)(surf.width / 4) * (surf.height / 4);
+    static thread_local Bc6Warp W;
+    for (long long first_block = 0; first_block < nblocks; first_block += kBc6Slots) {
+        const int nvalid = (int)((nblocks - first_block < kBc6Slots) ? (nblocks - first_block) : kBc6Slots);
+        ITW_BC6_PROGRAM(ITW_PHASE_EMU)
+    }
+}
+}
