@@ -62,4 +62,11 @@ void emu_CompressBlocksBC6H(const rgba_surface* src, uint8_t* dst, bc6h_enc_sett
         ITW_BC6_PROGRAM(ITW_PHASE_EMU)
     }
 }
+
+// the product's profile tables (csrc/itw_params.h), exported so the emulation is self-contained
+#define EMU_BC7(name, row) void emu_GetProfile_##name(bc7_enc_settings* s) { bc7_fill_profile(s, row); }
+EMU_BC7(ultrafast, 0) EMU_BC7(veryfast, 1) EMU_BC7(fast, 2) EMU_BC7(basic, 3) EMU_BC7(slow, 4)
+EMU_BC7(alpha_ultrafast, 5) EMU_BC7(alpha_veryfast, 6) EMU_BC7(alpha_fast, 7) EMU_BC7(alpha_basic, 8) EMU_BC7(alpha_slow, 9)
+#define EMU_BC6(name, row) void emu_GetProfile_bc6h_##name(bc6h_enc_settings* s) { bc6_fill_profile(s, row); }
+EMU_BC6(veryfast, 0) EMU_BC6(fast, 1) EMU_BC6(basic, 2) EMU_BC6(slow, 3) EMU_BC6(veryslow, 4)
 }
