@@ -97,7 +97,7 @@ ITW_HD void covariance_of(float (&cov)[10], const float (&st)[15], int channels)
 // PCA line through the masked texels, endpoints at the extreme projections; K:834-905.
 // clamp255 = K:896 block_segment (BC7); otherwise K:857 block_segment_core (BC6H).
 // Writes ep[0..channels) and ep[4..4+channels).
-ITW_HD void fit_segment(float* ep, const float* px, int mask, int channels, bool clamp255)
+ITW_HD_NOINLINE void fit_segment(float* ep, const float* px, int mask, int channels, bool clamp255)
 {
     float st[15], cov[10], mean[4], axis[4];
     masked_moments(st, px, mask, channels);
@@ -159,7 +159,7 @@ ITW_HD float residual_bound(float (&cov)[10], int channels)
 }
 // Ranking key of a two-subset shape: shape + 64*(int)(256*sqrt(bound0+bound1)), where subset 1's
 // moments are full - subset 0; K:952-971, :1403-1410
-ITW_HD int split_bound_key(const float* px, int shape, const float (&full)[15], int channels)
+ITW_HD_NOINLINE int split_bound_key(const float* px, int shape, const float (&full)[15], int channels)
 {
     float st[15], c1[10], c2[10];
     masked_moments(st, px, shape_mask(shape, 0), channels);
@@ -181,7 +181,7 @@ ITW_HD int split_bound_key(const float* px, int shape, const float (&full)[15], 
 // entries, decoded with the integer BC7 interpolation.  The per-texel error is truncated through
 // int (cvttss2si) before it is summed -- K:1178-1189, which matters for BC6H (quirk Q3).
 // idx: sixteen 4-bit indices, texel k in nibble k%8 of word k/8.  ep = [subset][A rgba, B rgba].
-ITW_HD float assign_indices(u32& idx0, u32& idx1, const float* px, int bits, const float* ep, u32 pattern,
+ITW_HD_NOINLINE float assign_indices(u32& idx0, u32& idx1, const float* px, int bits, const float* ep, u32 pattern,
                             int channels)
 {
     const int levels = 1 << bits;
@@ -222,7 +222,7 @@ ITW_HD float assign_indices(u32& idx0, u32& idx1, const float* px, int bits, con
 }
 
 // Least-squares endpoints of one subset from its current indices; K:1198-1262
-ITW_HD void solve_endpoints(float* ep, const float* px, int bits, u32 idx0, u32 idx1, int mask, int channels)
+ITW_HD_NOINLINE void solve_endpoints(float* ep, const float* px, int bits, u32 idx0, u32 idx1, int mask, int channels)
 {
     const float top = (float)((1 << bits) - 1);
     float atb1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -273,7 +273,7 @@ ITW_HD int bc7_pairs(int mode) { return (mode == 0 || mode == 2) ? 3 : ((mode ==
 
 // One endpoint pair (8 values), in place: q receives the quantised integers, ep the decoded
 // values.  `channels` = components that vote on the p-bit (K:1011-1020); all four are produced.
-ITW_HD void bc7_quantise_pair(int* q, float* ep, int mode, int channels)
+ITW_HD_NOINLINE void bc7_quantise_pair(int* q, float* ep, int mode, int channels)
 {
     if (mode == 0 || mode == 3 || mode == 6 || mode == 7) {            // unique p-bits; K:983-1022
         const int bits = (mode == 0) ? 4 : ((mode == 7) ? 5 : 7);

@@ -106,7 +106,7 @@ ITW_HD void bc6_quant_dequant(const Bc6Entry& E, int* q, float* ep, int pairs)
 }
 
 // Decide whether `mode` fits the block's range and, if so, fill the entry; K:2332-2365, :2302-2330
-ITW_HD bool bc6_make_entry(Bc6Entry& E, const Bc6Warp& W, int slot, int mode, float margin)
+ITW_HD_NOINLINE bool bc6_make_entry(Bc6Entry& E, const Bc6Warp& W, int slot, int mode, float margin)
 {
     const float span = bc6_span(mode);
     if (W.max_span[slot] * margin > span) return false;
@@ -183,7 +183,7 @@ static const Bc6Step h_bc6_layout[14][kBc6MaxSteps] = {ITW_BC6_LAYOUT_INIT};
 #undef G3
 #undef B3
 
-ITW_HD void bc6_put_header(BitSink& s, const int* q, int mode)
+ITW_HD_NOINLINE void bc6_put_header(BitSink& s, const int* q, int mode)
 {
     const bool delta = !(mode == 9 || mode == 10);
 #if defined(__CUDA_ARCH__)
@@ -208,7 +208,7 @@ ITW_HD void bc6_put_header(BitSink& s, const int* q, int mode)
 }
 
 // ---- candidate / chains; K:2174-2300, :2982-3031 ----
-ITW_HD float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, int* q, u32& idx0, u32& idx1)
+ITW_HD_NOINLINE float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, int* q, u32& idx0, u32& idx1)
 {
     float ep[16];
 #pragma unroll
@@ -217,7 +217,7 @@ ITW_HD float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, 
     bc6_quant_dequant(E, q, ep, 2);
     return assign_indices(idx0, idx1, px, 3, ep, shape_pattern(shape), 3);
 }
-ITW_HD void bc6_chain_two_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
+ITW_HD_NOINLINE void bc6_chain_two_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
 {
     W.res_err[slot][e] = inf_f();
     const int pos = W.win_pos[slot][e];
@@ -254,7 +254,7 @@ ITW_HD void bc6_chain_two_region(Bc6Warp& W, const Bc6Params& P, int slot, int e
     u32* out = W.res_code[slot][e];
     out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
 }
-ITW_HD void bc6_chain_one_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
+ITW_HD_NOINLINE void bc6_chain_one_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
 {
     const float* px = W.px[slot];
     const Bc6Entry& E = W.one[slot][e];

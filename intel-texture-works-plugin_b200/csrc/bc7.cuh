@@ -1,23 +1,32 @@
 // bc7.cuh -- BC7 encoder (reference: kernel.ispc:616-2037, cited as K:line).
 //
-// Mapping.  One WARP owns a batch of kSlots 4x4 blocks; its 32 lanes are spread over the block's
-// independent work items instead of over texels:
-//   * candidate phases: lane <-> (block slot, partition candidate) -- each lane fits the PCA
-//     segments of its candidate, quantises the endpoints and runs the index search alone, reading
-//     the block's texels from shared memory (broadcast), so the reference's texel-order float sums
-//     are reproduced bit for bit;
+// Mapping.  One WARP owns a batch of kBc7Slots 4x4 blocks; its 32 lanes are spread over the
+// blocks' independent work items instead of over texels:
+//   * shape phases: lane <-> (block slot, partition shape).  A lane fits the PCA segments of its
+//     shape ONCE and evaluates both BC7 modes that use that shape (0 and 2 share the three-subset
+//     shapes, 1 and 3 the two-subset shapes; the reference refits per mode, K:1279-1297, with
+//     identical results because the fit does not depend on the mode);
 //   * ranking phase: lane <-> (block slot, two-subset shape) for the 64 PCA split bounds;
-//   * chain phase: lane <-> (block slot, mode) -- the per-mode refinement chains, the mode 4/5
-//     rotation/index-swap candidates and mode 6 are independent of one another in the reference
-//     (each only competes through a strict `<` on the final error, K:1358, :1638, :1650, :1684),
-//     so they run side by side and the winner is the first minimum in the reference's order
-//     mode 0, 2, 1, 3, 7, 4(rot,swap), 5(rot), 6.
-// Batching kSlots blocks per warp keeps the lanes of the short phases (16 mode-0 candidates, <=18
-// chains per block) busy.  All candidate errors are exact integers < 2^23 (K:1178-1189 sums
-// truncated per-texel errors), so "first minimum in list order" is a plain scan.
+//   * chain phase: lane <-> (block slot, role).  The per-mode refinement chains, the mode 4/5
+//     rotation / index-swap candidates and mode 6 are independent of one another in the reference
+//     (they only meet in a strict `<` on the final error, K:1358, :1638, :1650, :1684), so they
+//     all run side by side through ONE generic chain routine, and the block's winner is the first
+//     minimum in the reference's order: mode 0, 2, 1, 3, 7, 4(rotation, swap), 5(rotation), 6.
 //
-// The phases are written as per-lane functions separated by warp barriers; the same functions are
-// driven lane by lane on the CPU by tests/emu (test-only).
+// Exactness.  BC7 texels are 8-bit integers, so most of the reference's float arithmetic is exact
+// integer arithmetic in disguise.  Wherever every intermediate is an integer below 2^24 the kernel
+// uses packed-byte integer instructions instead -- same values, ~6x fewer instructions:
+//   * raw moments of a subset (K:763-803): IDP.4A dot products over channel-planar packed bytes;
+//   * index search (K:1133-1193): the projection numerator / denominator are integer dot
+//     products (then ONE IEEE float division, as in the reference), the two candidate palette
+//     entries are integer interpolations (the reference truncates them through int, K:1172-1173)
+//     and their squared errors are VABSDIFF4 + IDP.4A;
+//   * least-squares sums (K:1198-1230): IDP.4A over index bytes.
+// Everything that rounds (covariance, power iteration, endpoint solve, quantisation) follows the
+// reference's float expression order exactly (DESIGN.md "Canonical float model").
+//
+// The phases are per-lane functions separated by warp barriers; tests/emu drives the same
+// functions lane by lane on the CPU (test-only).
 #pragma once
 #include "bc67_core.cuh"
 
@@ -32,23 +41,28 @@ struct Bc7Params {
 
 constexpr int kBc7Slots = 4;          // blocks per warp batch
 constexpr int kBc7MaxRoles = 18;      // 5 partitioned modes + up to 8 mode-4 + 4 mode-5 + mode 6
+constexpr int kErrNone = 0x7fffffff;  // "no result": loses every strict < comparison
 
+// One 4x4 block in shared memory
+struct Bc7Block {
+    u32 tex[16];       // packed RGBA8 of texel k (R in byte 0)
+    u32 plane[4][4];   // plane[c][i] = channel c of texels 4i..4i+3, one byte each
+};
 // Per-warp scratch in shared memory
 struct Bc7Warp {
-    float px[kBc7Slots][64];                   // planar texels: px[c*16 + k]
-    float cand_err[kBc7Slots][5][64];          // per (mode slot m, list position)
-    int keys[kBc7Slots][2][64];                // split-bound keys: [0] RGB (modes 1,3), [1] profile channels (mode 7)
-    int order[kBc7Slots][2][64];               // keys in ascending order
+    Bc7Block blk[kBc7Slots];
+    int cand_err[kBc7Slots][2][64];            // errors of the mode-slot pair being evaluated: [first/second][list position]
+    int keys[kBc7Slots][64];                   // split-bound keys of the set being ranked (scratch)
+    int order[kBc7Slots][2][64];               // keys in ascending order: [0] RGB (modes 1,3), [1] profile channels (mode 7)
     int win_pos[kBc7Slots][5];                 // winning list position per mode slot, -1 = none
-    float res_err[kBc7Slots][kBc7MaxRoles];
+    int res_err[kBc7Slots][kBc7MaxRoles];
     u32 res_code[kBc7Slots][kBc7MaxRoles][4];
+    u32 palette[24][32];                       // lane-private palette of the index search: [entry][lane]
     int nvalid;
 };
 // mode slots m = 0..4 <-> BC7 modes {0, 2, 1, 3, 7}: the reference's evaluation order
 ITW_HD int bc7_slot_mode(int m) { return (m == 0) ? 0 : ((m == 1) ? 2 : ((m == 2) ? 1 : ((m == 3) ? 3 : 7))); }
-
-ITW_HD int bc7_mode_bits(int mode) { return (mode == 0 || mode == 1) ? 3 : 2; }
-ITW_HD int bc7_mode_channels(int mode) { return (mode == 7) ? 4 : 3; }
+ITW_HD int bc7_mode_bits(int mode) { return (mode == 0 || mode == 1) ? 3 : ((mode == 6) ? 4 : 2); }
 
 // number of candidates mode slot m evaluates under the profile; K:1386-1435
 ITW_HD int bc7_slot_count(const Bc7Params& P, int m)
@@ -66,23 +80,282 @@ ITW_HD int bc7_slot_shape(const Bc7Warp& W, int slot, int m, int n)
     return W.order[slot][(m == 4) ? 1 : 0][n] & 63;             // modes 1/3/7 walk the ranked list
 }
 
-// Fit + quantise + index search of one partition candidate; K:1279-1297
-ITW_HD float bc7_eval_partitioned(const float* px, int mode, int shape, int* q, u32& idx0, u32& idx1)
+// ---------------------------------------------------------------------------------------------
+// Views.  Modes 4/5 encode the block with one colour channel swapped with alpha ("rotation");
+// for RGB profiles the swapped-in plane is the constant 255 (K:1579-1584).  rot = 3: no swap.
+// ---------------------------------------------------------------------------------------------
+struct View {
+    const Bc7Block* b;
+    int rot;      // 0..2 rotated channel, 3 = identity
+    int alpha;    // 1: the swapped-in plane is alpha; 0: it is 255
+};
+ITW_HD u32 view_tex(const View& v, int k)
 {
-    const int pairs = bc7_pairs(mode), channels = bc7_mode_channels(mode);
-    float ep[24];
+    u32 t = v.b->tex[k];
+    if (v.rot < 3) {
+        u32 sel = (0x3210u & ~(0xFu << (4 * v.rot))) | (7u << (4 * v.rot));     // byte `rot` <- byte 3 of the 2nd operand
+        t = byte_perm(t, v.alpha ? t : 0xFFFFFFFFu, sel);
+    }
+    return t;
+}
+ITW_HD u32 view_plane(const View& v, int c, int i)
+{
+    if (c == v.rot) return v.alpha ? v.b->plane[3][i] : 0xFFFFFFFFu;
+    return v.b->plane[c][i];
+}
+ITW_HD u32 nibble_to_bytemask(u32 nib) { return (((nib & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
+// ---------------------------------------------------------------------------------------------
+// raw moments of the masked texels as exact integers; slots as K:763-803
+// ---------------------------------------------------------------------------------------------
+ITW_HD void moments_u8(int (&st)[15], const u32 (&P)[4][4], u32 mask, int channels)
+{
+    u32 s[15];
 #pragma unroll
-    for (int i = 0; i < 24; i++) ep[i] = 0.0f;                 // never-written slots read as zero (F6)
-    for (int j = 0; j < pairs; j++) fit_segment(ep + 8 * j, px, shape_mask(shape, j), channels, true);
-    for (int j = 0; j < pairs; j++) bc7_quantise_pair(q + 8 * j, ep + 8 * j, mode, channels);
-    return assign_indices(idx0, idx1, px, bc7_mode_bits(mode), ep, shape_pattern(shape), channels);
+    for (int i = 0; i < 15; i++) s[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u32 bm = nibble_to_bytemask(mask >> (4 * i));
+        const u32 r = P[0][i] & bm, g = P[1][i] & bm, b = P[2][i] & bm;
+        s[10] = dp4a_u8(r, 0x01010101u, s[10]);
+        s[11] = dp4a_u8(g, 0x01010101u, s[11]);
+        s[12] = dp4a_u8(b, 0x01010101u, s[12]);
+        s[0] = dp4a_u8(r, P[0][i], s[0]);
+        s[1] = dp4a_u8(r, P[1][i], s[1]);
+        s[2] = dp4a_u8(r, P[2][i], s[2]);
+        s[4] = dp4a_u8(g, P[1][i], s[4]);
+        s[5] = dp4a_u8(g, P[2][i], s[5]);
+        s[7] = dp4a_u8(b, P[2][i], s[7]);
+        if (channels == 4) {
+            const u32 a = P[3][i] & bm;
+            s[13] = dp4a_u8(a, 0x01010101u, s[13]);
+            s[3] = dp4a_u8(r, P[3][i], s[3]);
+            s[6] = dp4a_u8(g, P[3][i], s[6]);
+            s[8] = dp4a_u8(b, P[3][i], s[8]);
+            s[9] = dp4a_u8(a, P[3][i], s[9]);
+        }
+    }
+    s[14] = (u32)popcount16(mask & 0xFFFFu);
+#pragma unroll
+    for (int i = 0; i < 15; i++) st[i] = (int)s[i];
+}
+ITW_HD void load_planes(u32 (&P)[4][4], const View& v)
+{
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) P[c][i] = view_plane(v, c, i);
 }
 
-// ---- 128-bit layouts; K:1807-1964 ----
-ITW_HD void bc7_write_partitioned(u32 (&out)[4], int* q, u32 idx0, u32 idx1, int shape, int mode)
+// PCA line through the masked texels, clamped to [0,255]; K:834-905.  ep[0..3] = A, ep[4..7] = B;
+// components >= channels are left untouched.
+ITW_HD_NOINLINE void bc7_fit(float* ep, const Bc7Block* blk, int rot, int alpha, u32 mask, int channels)
 {
-    const int bits = bc7_mode_bits(mode), pairs = bc7_pairs(mode), channels = bc7_mode_channels(mode);
-    int flips = orient_subsets(q, idx0, idx1, bits, pairs, shape);
+    const View v{blk, rot, alpha};
+    u32 P[4][4];
+    load_planes(P, v);
+    int ist[15];
+    moments_u8(ist, P, mask, channels);
+    float st[15], cov[10], mean[4], axis[4];
+#pragma unroll
+    for (int i = 0; i < 15; i++) st[i] = (float)ist[i];
+    covariance_of(cov, st, channels);
+#pragma unroll
+    for (int c = 0; c < 4; c++) mean[c] = (c < channels) ? st[10 + c] / st[14] : 0.0f;
+    const float inv_var = 1.0f / (256.0f * 256.0f);
+#pragma unroll
+    for (int i = 0; i < 10; i++) cov[i] *= inv_var;
+    const float eps = 0.001f * 0.001f;
+    cov[0] += eps; cov[4] += eps; cov[7] += eps; cov[9] += eps;
+    power_axis<8>(axis, cov, channels);
+
+    float lo = inf_f(), hi = -inf_f();
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float d = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (c < channels) d += axis[c] * ((float)((P[c][k >> 2] >> (8 * (k & 3))) & 255u) - mean[c]);
+        if ((mask >> k) & 1u) {
+            lo = min_sse(lo, d);
+            hi = max_sse(hi, d);
+        }
+    }
+    if (hi - lo < 1.0f) { lo -= 0.5f; hi += 0.5f; }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        if (c < channels) {
+            ep[c] = clamp_sse(lo * axis[c] + mean[c], 0.0f, 255.0f);
+            ep[4 + c] = clamp_sse(hi * axis[c] + mean[c], 0.0f, 255.0f);
+        }
+}
+
+// Ranking key of a two-subset shape (K:952-971, :1403-1410); subset 1 = full - subset 0
+ITW_HD_NOINLINE int bc7_split_key(const Bc7Block* blk, int shape, int channels)
+{
+    const View v{blk, 3, 1};
+    u32 P[4][4];
+    load_planes(P, v);
+    int full[15], part[15];
+    moments_u8(full, P, 0xFFFFu, channels);
+    moments_u8(part, P, (u32)shape_mask(shape, 0), channels);
+    float st[15], c1[10], c2[10];
+#pragma unroll
+    for (int i = 0; i < 15; i++) st[i] = (float)part[i];
+    covariance_of(c1, st, channels);
+#pragma unroll
+    for (int i = 0; i < 15; i++) st[i] = (float)(full[i] - part[i]);     // exact: the reference subtracts exact floats
+    covariance_of(c2, st, channels);
+    float b = 0.0f;
+    b += residual_bound(c1, channels);
+    b += residual_bound(c2, channels);
+    return shape + (int)((unsigned)cvt_x86(sqrtf(b) * 256.0f) * 64u);
+}
+
+// Quantise one endpoint pair (K:983-1128) and pack it: out[0],out[1] = decoded A,B as RGBA bytes,
+// out[2],out[3] = quantised A,B as RGBA bytes.  ep is updated to the decoded values.
+ITW_HD_NOINLINE void bc7_quantise(u32* out, float* ep, int mode, int channels)
+{
+    int q[8];
+    bc7_quantise_pair(q, ep, mode, channels);
+    u32 d[2] = {0u, 0u}, p[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            d[i] |= ((u32)ep[4 * i + c] & 255u) << (8 * c);
+            p[i] |= ((u32)q[4 * i + c] & 255u) << (8 * c);
+        }
+    out[0] = d[0]; out[1] = d[1]; out[2] = p[0]; out[3] = p[1];
+}
+
+// Integer interpolation of two packed RGBA endpoints with BC7 weight w (K:1172: ((64-w)a+wb+32)/64
+// truncated), two channels per multiply.
+ITW_HD u32 lerp_rgba(u32 a, u32 b, u32 w)
+{
+    const u32 m = 0x00FF00FFu;
+    u32 rb = (((64u - w) * (a & m) + w * (b & m) + 0x00200020u) >> 6) & m;
+    u32 ga = (((64u - w) * ((a >> 8) & m) + w * ((b >> 8) & m) + 0x00200020u) >> 6) & m;
+    return rb | (ga << 8);
+}
+
+// Index search; K:1133-1193.  ends[2j], ends[2j+1] = decoded endpoints A,B of subset j (RGBA bytes);
+// chmask zeroes the channels that do not take part (0x00FFFFFF for three-channel modes).
+// Returns the summed error (exact integer) and the sixteen 4-bit indices in idx[0..1].
+ITW_HD_NOINLINE int bc7_assign(u32* idx, u32 (*pal)[32], int lane, const Bc7Block* blk, int rot, int alpha, int bits,
+                               int pairs, u32 pattern, const u32* ends, u32 chmask)
+{
+    const View v{blk, rot, alpha};
+    const int levels = 1 << bits;
+    u32 EA[3], EB[3];
+    int cst[3];
+    float fdiv[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        EA[j] = EB[j] = 0u; cst[j] = 0; fdiv[j] = 1.0f;
+        if (j < pairs) {
+            const u32 a = ends[2 * j] & chmask, b = ends[2 * j + 1] & chmask;
+            const u32 aa = dp4a_u8(a, a, 0u), ab = dp4a_u8(a, b, 0u), bb = dp4a_u8(b, b, 0u);
+            EA[j] = a; EB[j] = b;
+            cst[j] = (int)(ab - aa);
+            fdiv[j] = (float)(int)(bb - 2u * ab + aa);          // sum of squared differences, exact
+            for (int q = 0; q < levels; q++) pal[j * levels + q][lane] = lerp_rgba(a, b, (u32)bc7_weight(bits, q));
+        }
+    }
+    const float flevels = (float)levels;
+    int total = 0;
+    u32 out0 = 0u, out1 = 0u;
+#pragma unroll 2
+    for (int k = 0; k < 16; k++) {
+        const u32 t = view_tex(v, k) & chmask;
+        const int j = (int)((pattern >> (2 * k)) & 3u);
+        const u32 ea = (j == 0) ? EA[0] : ((j == 1) ? EA[1] : EA[2]);
+        const u32 eb = (j == 0) ? EB[0] : ((j == 1) ? EB[1] : EB[2]);
+        const int cj = (j == 0) ? cst[0] : ((j == 1) ? cst[1] : cst[2]);
+        const float dj = (j == 0) ? fdiv[0] : ((j == 1) ? fdiv[1] : fdiv[2]);
+        // sum_c (t_c - a_c)(b_c - a_c): integer, |value| < 2^18, so the float it converts to is the
+        // reference's float sum; one IEEE division follows as in K:1158
+        const int num = (int)dp4a_u8(t, eb, 0u) - (int)dp4a_u8(t, ea, 0u) - cj;
+        const float proj = (float)num / dj;
+        // NaN (coincident endpoints, 0/0) converts to INT_MIN on x86 and clamps to 1 (K:1160-1161)
+        const int q1 = clampi(cvt_x86(proj * flevels + 0.5f), 1, levels - 1);
+        const u32 p0 = pal[j * levels + q1 - 1][lane], p1 = pal[j * levels + q1][lane];
+        const u32 d0 = absdiff_u8x4(p0, t), d1 = absdiff_u8x4(p1, t);
+        const int e0 = (int)dp4a_u8(d0, d0, 0u), e1 = (int)dp4a_u8(d1, d1, 0u);
+        const bool first = e0 < e1;
+        total += first ? e0 : e1;
+        const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
+        if (k < 8) out0 += bq; else out1 += bq;
+    }
+    idx[0] = out0;
+    idx[1] = out1;
+    return total;
+}
+
+// Least-squares endpoints of one subset from its indices; K:1198-1262.  The sums are exact integers.
+ITW_HD_NOINLINE void bc7_solve(float* ep, const Bc7Block* blk, int rot, int alpha, int bits, u32 idx0, u32 idx1, u32 mask,
+                               int channels)
+{
+    const View v{blk, rot, alpha};
+    const u32 top = (1u << bits) - 1u;
+    u32 sq1 = 0u, sqq = 0u, sum[4] = {0u, 0u, 0u, 0u}, atb1[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u32 n = (((i < 2) ? idx0 : idx1) >> (16 * (i & 1))) & 0xFFFFu;     // four 4-bit indices
+        n = (n | (n << 8)) & 0x00FF00FFu;
+        n = (n | (n << 4)) & 0x0F0F0F0Fu;                                  // ... one per byte
+        const u32 bm = nibble_to_bytemask(mask >> (4 * i));
+        const u32 qm = n & bm, ones = bm & 0x01010101u;
+        const u32 xm = ((top * 0x01010101u) & bm) - qm;                    // (levels-1) - q, bytewise, no borrows
+        sq1 = dp4a_u8(qm, 0x01010101u, sq1);
+        sqq = dp4a_u8(qm, qm, sqq);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (c < channels) {
+                const u32 p = view_plane(v, c, i);
+                sum[c] = dp4a_u8(ones, p, sum[c]);
+                atb1[c] = dp4a_u8(xm, p, atb1[c]);
+            }
+    }
+    const float ftop = (float)top, count = (float)popcount16(mask & 0xFFFFu);
+    const float fsq1 = (float)sq1, fsqq = (float)sqq;
+    float cxx = count * sq(ftop) - (2.0f * ftop) * fsq1 + fsqq;
+    float cyy = fsqq;
+    float cxy = ftop * fsq1 - fsqq;
+    float det = cxx * cyy - cxy * cxy;
+    float scale = ftop / det;
+    bool flat = fabsf(det) < 0.001f;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        if (c < channels) {
+            const float fs = (float)sum[c], fa1 = (float)atb1[c];
+            float atb2 = ftop * fs - fa1;
+            float a = (fa1 * cyy - atb2 * cxy) * scale;
+            float b = (atb2 * cxx - fa1 * cxy) * scale;
+            if (flat) { a = fs / count; b = a; }
+            ep[c] = a;
+            ep[4 + c] = b;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit layouts; K:1694-1964.  Q[j][0/1] = quantised endpoints A/B of subset j as RGBA bytes.
+// ---------------------------------------------------------------------------------------------
+ITW_HD u32 qcomp(u32 packed, int c) { return (packed >> (8 * c)) & 255u; }
+
+ITW_HD void bc7_write_partitioned(u32* out, u32 (&Q)[3][2], u32 idx0, u32 idx1, int shape, int mode)
+{
+    const int bits = bc7_mode_bits(mode), pairs = bc7_pairs(mode), channels = (mode == 7) ? 4 : 3;
+    const int half = (1 << bits) / 2;
+    int flips = 0;
+    for (int j = 0; j < pairs; j++) {                           // anchor index MSB must be 0; K:1708-1733
+        const int k0 = shape_anchor(shape, j);
+        const int vv = (int)(((k0 < 8 ? idx0 : idx1) >> (4 * (k0 & 7))) & 15u);
+        if (vv >= half) {
+            const u32 t = Q[j][0]; Q[j][0] = Q[j][1]; Q[j][1] = t;
+            flips |= shape_mask(shape, j);
+        }
+    }
     BitSink s;
     s.reset();
     s.put(mode + 1, 1u << mode);
@@ -90,58 +363,73 @@ ITW_HD void bc7_write_partitioned(u32 (&out)[4], int* q, u32 idx0, u32 idx1, int
     const int width = (mode == 0) ? 4 : ((mode == 1) ? 6 : ((mode == 3) ? 7 : 5));
     const int drop = (mode == 2) ? 0 : 1;                      // p-bit modes store the value without its LSB
     for (int c = 0; c < channels; c++)
-        for (int j = 0; j < pairs * 2; j++) s.put(width, (u32)(q[4 * j + c] >> drop));
+        for (int j = 0; j < pairs; j++) {
+            s.put(width, qcomp(Q[j][0], c) >> drop);
+            s.put(width, qcomp(Q[j][1], c) >> drop);
+        }
     if (mode == 1)
-        for (int j = 0; j < 2; j++) s.put(1, (u32)(q[8 * j] & 1));
+        for (int j = 0; j < 2; j++) s.put(1, Q[j][0] & 1u);
     if (mode == 0 || mode == 3 || mode == 7)
-        for (int j = 0; j < pairs * 2; j++) s.put(1, (u32)(q[4 * j] & 1));
+        for (int j = 0; j < pairs; j++) { s.put(1, Q[j][0] & 1u); s.put(1, Q[j][1] & 1u); }
     put_indices(s, idx0, idx1, bits, flips, shape_anchor(shape, 1), (pairs == 3) ? shape_anchor(shape, 2) : -1);
     out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
 }
-
-// ---- chain: refinement of one partitioned mode's winner; K:1329-1362 ----
-ITW_HD void bc7_chain_partitioned(Bc7Warp& W, const Bc7Params& P, int slot, int m)
+// single-subset orientation on packed endpoints; K:1694-1706
+ITW_HD void orient_packed(u32& qa, u32& qb, u32& idx0, u32& idx1, int bits)
 {
-    float& out_err = W.res_err[slot][m];
-    out_err = inf_f();
-    const int pos = W.win_pos[slot][m];
-    if (pos < 0) return;
-    const float* px = W.px[slot];
-    const int mode = bc7_slot_mode(m);
-    const int bits = bc7_mode_bits(mode), pairs = bc7_pairs(mode), channels = bc7_mode_channels(mode);
-    const int shape = bc7_slot_shape(W, slot, m, pos);
-
-    int best_q[24];
-    u32 best_i0, best_i1;
-    // the winner's integers are recomputed here instead of being carried out of the candidate phase
-    float best_err = bc7_eval_partitioned(px, mode, shape, best_q, best_i0, best_i1);
-
-    for (int it = 0; it < P.refine[mode]; it++) {
-        float ep[24];
-        int q[24];
-#pragma unroll
-        for (int i = 0; i < 24; i++) ep[i] = 0.0f;
-        for (int j = 0; j < pairs; j++) solve_endpoints(ep + 8 * j, px, bits, best_i0, best_i1, shape_mask(shape, j), channels);
-        for (int j = 0; j < pairs; j++) bc7_quantise_pair(q + 8 * j, ep + 8 * j, mode, P.channels);   // profile's channels; K:1343
-        u32 i0, i1;
-        float err = assign_indices(i0, i1, px, bits, ep, shape_pattern(shape), channels);
-        if (err < best_err) {
-            for (int i = 0; i < 8 * pairs; i++) best_q[i] = q[i];
-            best_i0 = i0; best_i1 = i1;
-            best_err = err;
-        }
+    const int levels = 1 << bits;
+    if ((int)(idx0 & 15u) >= levels / 2) {
+        const u32 t = qa; qa = qb; qb = t;
+        const u32 all = 0x11111111u * (u32)(levels - 1);
+        idx0 = all - idx0;
+        idx1 = all - idx1;
     }
-    if (mode != 7) {                                           // opaque error of the dropped alpha; K:1267-1277, :1356
-        float opaque = 0.0f;
-        if (P.channels != 3)
-            for (int k = 0; k < 16; k++) opaque += sq(px[48 + k] - 255.0f);
-        best_err += opaque;
+}
+ITW_HD void bc7_write_mode45(u32* out, u32 qa, u32 qb, u32 i0, u32 i1, int aq0, int aq1, u32 a0, u32 a1, int mode,
+                             int rotation, int swap)
+{
+    const int epbits = (mode == 4) ? 5 : 7, aepbits = (mode == 4) ? 6 : 8;
+    const int cbits = 2, sbits = (mode == 4) ? 3 : 2;          // widths of the first / second index set
+    int aq[2] = {aq0, aq1};
+    if (!swap) {
+        orient_packed(qa, qb, i0, i1, cbits);
+        orient_single(aq, 1, a0, a1, sbits);
+    } else {                                                    // the two index sets trade places; K:1903-1908
+        u32 t0 = i0, t1 = i1;
+        i0 = a0; i1 = a1;
+        a0 = t0; a1 = t1;
+        orient_single(aq, 1, i0, i1, cbits);
+        orient_packed(qa, qb, a0, a1, sbits);
     }
-    out_err = best_err;
-    bc7_write_partitioned(W.res_code[slot][m], best_q, best_i0, best_i1, shape, mode);
+    BitSink s;
+    s.reset();
+    s.put(mode + 1, 1u << mode);
+    s.put(2, (u32)((rotation + 1) & 3));
+    if (mode == 4) s.put(1, (u32)swap);
+    for (int c = 0; c < 3; c++) { s.put(epbits, qcomp(qa, c)); s.put(epbits, qcomp(qb, c)); }
+    s.put(aepbits, (u32)aq[0]);
+    s.put(aepbits, (u32)aq[1]);
+    put_indices(s, i0, i1, cbits, 0, -1, -1);
+    put_indices(s, a0, a1, sbits, 0, -1, -1);
+    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
+}
+ITW_HD void bc7_write_mode6(u32* out, u32 qa, u32 qb, u32 i0, u32 i1)
+{
+    orient_packed(qa, qb, i0, i1, 4);
+    BitSink s;
+    s.reset();
+    s.put(7, 64u);
+    for (int c = 0; c < 4; c++) { s.put(7, qcomp(qa, c) >> 1); s.put(7, qcomp(qb, c) >> 1); }
+    s.put(1, qa & 1u);
+    s.put(1, qb & 1u);
+    put_indices(s, i0, i1, 4, 0, -1, -1);
+    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
 }
 
-// ---- scalar channel of modes 4/5; K:1437-1563 ----
+// ---------------------------------------------------------------------------------------------
+// scalar channel of modes 4/5; K:1437-1563.  `a` = byte `shift/8` of the ORIGINAL texels.
+// ---------------------------------------------------------------------------------------------
+ITW_HD float scalar_texel(const Bc7Block* blk, int k, int shift) { return (float)((blk->tex[k] >> shift) & 255u); }
 ITW_HD void scalar_quantise(int (&q)[2], float (&ep)[2], int epbits)
 {
     const int top = (1 << epbits) - 1;
@@ -151,18 +439,19 @@ ITW_HD void scalar_quantise(int (&q)[2], float (&ep)[2], int epbits)
         ep[i] = (float)expand_bits(q[i], epbits);
     }
 }
-ITW_HD float scalar_assign(u32& idx0, u32& idx1, const float* a, int bits, const float (&ep)[2])
+ITW_HD float scalar_assign(u32& idx0, u32& idx1, const Bc7Block* blk, int shift, int bits, const float (&ep)[2])
 {
     const int levels = 1 << bits;
     u32 out[2] = {0u, 0u};
     float total = 0.0f;
     for (int k = 0; k < 16; k++) {
-        float proj = (a[k] - ep[0]) / (ep[1] - ep[0] + 0.001f);
+        const float a = scalar_texel(blk, k, shift);
+        float proj = (a - ep[0]) / (ep[1] - ep[0] + 0.001f);
         int q1 = clampi(cvt_x86(proj * (float)levels + 0.5f), 1, levels - 1);
         float fw0 = (float)bc7_weight(bits, q1 - 1), fw1 = (float)bc7_weight(bits, q1);
         float d0 = (float)cvt_x86(((64.0f - fw0) * ep[0] + fw0 * ep[1] + 32.0f) / 64.0f);
         float d1 = (float)cvt_x86(((64.0f - fw1) * ep[0] + fw1 * ep[1] + 32.0f) / 64.0f);
-        float err0 = sq(d0 - a[k]), err1 = sq(d1 - a[k]);
+        float err0 = sq(d0 - a), err1 = sq(d1 - a);
         int best_err = cvt_x86(err1), best_q = q1;
         if (err0 < err1) { best_err = cvt_x86(err0); best_q = q1 - 1; }
         out[k >> 3] += (u32)best_q << (4 * (k & 7));
@@ -172,17 +461,18 @@ ITW_HD float scalar_assign(u32& idx0, u32& idx1, const float* a, int bits, const
     idx1 = out[1];
     return total;
 }
-ITW_HD void scalar_solve(float (&ep)[2], const float* a, int bits, u32 idx0, u32 idx1)
+ITW_HD void scalar_solve(float (&ep)[2], const Bc7Block* blk, int shift, int bits, u32 idx0, u32 idx1)
 {
     const float top = (float)((1 << bits) - 1);
     float atb1 = 0.0f, sq1 = 0.0f, sqq = 0.0f, sum = 0.0f;
     for (int k = 0; k < 16; k++) {
+        const float a = scalar_texel(blk, k, shift);
         float q = (float)(((k < 8 ? idx0 : idx1) >> (4 * (k & 7))) & 15u);
         float x = (float)cvt_x86(top - q);
         sq1 += q;
         sqq += q * q;
-        sum += a[k];
-        atb1 += x * a[k];
+        sum += a;
+        atb1 += x * a;
     }
     float atb2 = top * sum - atb1;
     float cxx = 16.0f * sq(top) - (2.0f * top) * sq1 + sqq;
@@ -197,120 +487,149 @@ ITW_HD void scalar_solve(float (&ep)[2], const float* a, int bits, u32 idx0, u32
         ep[1] = ep[0];
     }
 }
-
-// ---- chain: one mode 4/5 candidate (rotation, index swap); K:1565-1621, :1879-1939 ----
-ITW_HD void bc7_chain_mode45(Bc7Warp& W, const Bc7Params& P, int slot, int role, int mode, int rotation, int swap)
+ITW_HD_NOINLINE int bc7_scalar_channel(int* aq, u32* aidx, const Bc7Block* blk, int rotation, int abits, int aepbits, int rch)
 {
-    const float* src = W.px[slot];
-    int bits = 2, abits = (mode == 4) ? 3 : 2;
-    const int aepbits = (mode == 4) ? 6 : 8;
-    if (swap == 1) { bits = 3; abits = 2; }
-
-    // rotated copy of the colour planes: the rotated-in plane is alpha, or 255 for RGB profiles
-    float px[48];
+    const int shift = 8 * rotation;
+    float ep[2] = {255.0f, 0.0f};
     for (int k = 0; k < 16; k++) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float v = src[16 * c + k];
-            if (c == rotation) v = (P.channels == 4) ? src[48 + k] : 255.0f;
-            px[16 * c + k] = v;
-        }
+        const float a = scalar_texel(blk, k, shift);
+        ep[0] = min_sse(ep[0], a);
+        ep[1] = max_sse(ep[1], a);
     }
-    float ep[8];
-    int q[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) ep[i] = 0.0f;
-    fit_segment(ep, px, 0xFFFF, 3, true);
-    bc7_quantise_pair(q, ep, mode, 3);
-    u32 i0, i1;
-    float err = assign_indices(i0, i1, px, bits, ep, 0u, 3);
-    for (int it = 0; it < P.refine[mode]; it++) {
-        solve_endpoints(ep, px, bits, i0, i1, 0xFFFF, 3);
-        bc7_quantise_pair(q, ep, mode, 3);
-        err = assign_indices(i0, i1, px, bits, ep, 0u, 3);
-    }
-    // the channel that was rotated out (always the ORIGINAL plane `rotation`; K:1608)
-    const float* a = src + 16 * rotation;
-    float aep[2] = {255.0f, 0.0f};
-    for (int k = 0; k < 16; k++) { aep[0] = min_sse(aep[0], a[k]); aep[1] = max_sse(aep[1], a[k]); }
-    int aq[2];
+    int q[2];
     u32 a0, a1;
-    scalar_quantise(aq, aep, aepbits);
-    float aerr = scalar_assign(a0, a1, a, abits, aep);
-    for (int it = 0; it < P.rch; it++) {
-        scalar_solve(aep, a, abits, a0, a1);
-        scalar_quantise(aq, aep, aepbits);
-        aerr = scalar_assign(a0, a1, a, abits, aep);
+    scalar_quantise(q, ep, aepbits);
+    float err = scalar_assign(a0, a1, blk, shift, abits, ep);
+    for (int it = 0; it < rch; it++) {
+        scalar_solve(ep, blk, shift, abits, a0, a1);
+        scalar_quantise(q, ep, aepbits);
+        err = scalar_assign(a0, a1, blk, shift, abits, ep);
     }
-    err += aerr;
-    W.res_err[slot][role] = err;
-
-    // layout; K:1879-1939
-    const int epbits = (mode == 4) ? 5 : 7;
-    const int cbits = 2, sbits = (mode == 4) ? 3 : 2;          // widths of the first / second index set
-    if (!swap) {
-        orient_single(q, 4, i0, i1, cbits);
-        orient_single(aq, 1, a0, a1, sbits);
-    } else {                                                    // the two index sets trade places
-        u32 t0 = i0, t1 = i1;
-        i0 = a0; i1 = a1;
-        a0 = t0; a1 = t1;
-        orient_single(aq, 1, i0, i1, cbits);
-        orient_single(q, 4, a0, a1, sbits);
-    }
-    BitSink s;
-    s.reset();
-    s.put(mode + 1, 1u << mode);
-    s.put(2, (u32)((rotation + 1) & 3));
-    if (mode == 4) s.put(1, (u32)swap);
-#pragma unroll
-    for (int c = 0; c < 3; c++) { s.put(epbits, (u32)q[c]); s.put(epbits, (u32)q[4 + c]); }
-    s.put(aepbits, (u32)aq[0]);
-    s.put(aepbits, (u32)aq[1]);
-    put_indices(s, i0, i1, cbits, 0, -1, -1);
-    put_indices(s, a0, a1, sbits, 0, -1, -1);
-    u32* out = W.res_code[slot][role];
-    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
+    aq[0] = q[0]; aq[1] = q[1];
+    aidx[0] = a0; aidx[1] = a1;
+    return (int)err;                                            // exact: a sum of 16 truncated integers
 }
 
-// ---- chain: mode 6; K:1657-1689, :1941-1964 ----
-ITW_HD void bc7_chain_mode6(Bc7Warp& W, const Bc7Params& P, int slot, int role)
+// ---------------------------------------------------------------------------------------------
+// The generic chain: initial fit + refinement + encode of one (block, role); K:1299-1363 (modes
+// 0-3,7), :1565-1655 (modes 4,5), :1657-1689 (mode 6).
+// ---------------------------------------------------------------------------------------------
+struct Role {
+    int kind;      // 0 partitioned, 1 mode 4/5, 2 mode 6
+    int mode, shape, rotation, swap;
+};
+ITW_HD int bc7_rotations(const Bc7Params& P) { return P.sel[2] ? maxi(P.channels - P.ch0, 0) : 0; }
+ITW_HD int bc7_role_count(const Bc7Params& P) { return 5 + 3 * bc7_rotations(P) + (P.sel[3] ? 1 : 0); }
+
+ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slot, int r)
 {
-    const float* px = W.px[slot];
-    const int channels = P.channels;
-    float ep[8];
-    int q[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) ep[i] = 0.0f;
-    fit_segment(ep, px, 0xFFFF, channels, true);
-    if (channels == 3) ep[3] = ep[7] = 255.0f;
-    bc7_quantise_pair(q, ep, 6, channels);
-    u32 i0, i1;
-    float err = assign_indices(i0, i1, px, 4, ep, 0u, channels);
-    for (int it = 0; it < P.refine[6]; it++) {
-        solve_endpoints(ep, px, 4, i0, i1, 0xFFFF, channels);
-        bc7_quantise_pair(q, ep, 6, channels);
-        err = assign_indices(i0, i1, px, 4, ep, 0u, channels);
+    const Bc7Block* blk = &W.blk[slot];
+    const int nrot = bc7_rotations(P);
+    Role role;
+    role.rotation = 3; role.swap = 0; role.shape = 0;
+    if (r < 5) {
+        role.kind = 0;
+        role.mode = bc7_slot_mode(r);
+        const int pos = W.win_pos[slot][r];
+        if (pos < 0) { W.res_err[slot][r] = kErrNone; return; }
+        role.shape = bc7_slot_shape(W, slot, r, pos);
+    } else if (r < 5 + 2 * nrot) {
+        role.kind = 1; role.mode = 4; role.rotation = P.ch0 + ((r - 5) >> 1); role.swap = (r - 5) & 1;
+    } else if (r < 5 + 3 * nrot) {
+        role.kind = 1; role.mode = 5; role.rotation = P.ch0 + (r - 5 - 2 * nrot);
+    } else {
+        role.kind = 2; role.mode = 6;
     }
-    W.res_err[slot][role] = err;
-    orient_single(q, 4, i0, i1, 4);
-    BitSink s;
-    s.reset();
-    s.put(7, 64u);
+    const int mode = role.mode;
+    const int pairs = bc7_pairs(mode);
+    int bits = bc7_mode_bits(mode);
+    if (role.kind == 1 && role.swap) bits = 3;
+    // channels fitted / searched, and the count that votes on p-bits during refinement (K:1343)
+    const int channels = (role.kind == 2) ? P.channels : ((mode == 7) ? 4 : 3);
+    const int vote_refine = (role.kind == 0) ? P.channels : channels;
+    const u32 chmask = (channels == 4) ? 0xFFFFFFFFu : 0x00FFFFFFu;
+    // view: rotation 3 (alpha itself rotated "with itself") is the identity
+    const int rot = (role.kind == 1 && role.rotation < 3) ? role.rotation : 3;
+    const int alpha = (P.channels == 4) ? 1 : 0;
+    const u32 pattern = (role.kind == 0) ? shape_pattern(role.shape) : 0u;
+
+    u32 ends[6], Q[3][2], idx[2], best_idx[2];
+    float ep[8];
+    // initial candidate
 #pragma unroll
-    for (int c = 0; c < 4; c++) { s.put(7, (u32)(q[c] >> 1)); s.put(7, (u32)(q[4 + c] >> 1)); }
-    s.put(1, (u32)(q[0] & 1));
-    s.put(1, (u32)(q[4] & 1));
-    put_indices(s, i0, i1, 4, 0, -1, -1);
-    u32* out = W.res_code[slot][role];
-    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
+    for (int j = 0; j < 3; j++) {
+        Q[j][0] = Q[j][1] = 0u;
+        ends[2 * j] = ends[2 * j + 1] = 0u;
+    }
+    float tail_a = 0.0f, tail_b = 0.0f;                          // ep[3], ep[7] carried between iterations (quirk Q5)
+    for (int j = 0; j < pairs; j++) {
+        u32 packed[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) ep[i] = 0.0f;                // never-written slots read as zero (F6)
+        const u32 mask = (role.kind == 0) ? (u32)shape_mask(role.shape, j) : 0xFFFFu;
+        bc7_fit(ep, blk, rot, alpha, mask, channels);
+        if (role.kind == 2 && channels == 3) ep[3] = ep[7] = 255.0f;     // K:1664-1667
+        bc7_quantise(packed, ep, mode, channels);
+        tail_a = ep[3]; tail_b = ep[7];
+        if (j == 0) { ends[0] = packed[0]; ends[1] = packed[1]; Q[0][0] = packed[2]; Q[0][1] = packed[3]; }
+        else if (j == 1) { ends[2] = packed[0]; ends[3] = packed[1]; Q[1][0] = packed[2]; Q[1][1] = packed[3]; }
+        else { ends[4] = packed[0]; ends[5] = packed[1]; Q[2][0] = packed[2]; Q[2][1] = packed[3]; }
+    }
+    int best_err = bc7_assign(best_idx, W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends, chmask);
+
+    const int refine = P.refine[mode];
+    for (int it = 0; it < refine; it++) {
+        u32 nQ[3][2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) nQ[j][0] = nQ[j][1] = 0u;
+        for (int j = 0; j < pairs; j++) {
+            u32 packed[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) ep[i] = 0.0f;
+            if (role.kind != 0) { ep[3] = tail_a; ep[7] = tail_b; }      // these arrays live across iterations in K
+            const u32 mask = (role.kind == 0) ? (u32)shape_mask(role.shape, j) : 0xFFFFu;
+            bc7_solve(ep, blk, rot, alpha, bits, best_idx[0], best_idx[1], mask, channels);
+            bc7_quantise(packed, ep, mode, vote_refine);
+            tail_a = ep[3]; tail_b = ep[7];
+            if (j == 0) { ends[0] = packed[0]; ends[1] = packed[1]; nQ[0][0] = packed[2]; nQ[0][1] = packed[3]; }
+            else if (j == 1) { ends[2] = packed[0]; ends[3] = packed[1]; nQ[1][0] = packed[2]; nQ[1][1] = packed[3]; }
+            else { ends[4] = packed[0]; ends[5] = packed[1]; nQ[2][0] = packed[2]; nQ[2][1] = packed[3]; }
+        }
+        const int err = bc7_assign(idx, W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends, chmask);
+        // partitioned modes keep the best iterate (K:1348); modes 4,5,6 keep the last (K:1598-1603, :1677-1682)
+        if (role.kind != 0 || err < best_err) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) { Q[j][0] = nQ[j][0]; Q[j][1] = nQ[j][1]; }
+            best_idx[0] = idx[0]; best_idx[1] = idx[1];
+            best_err = err;
+        }
+    }
+
+    u32* out = W.res_code[slot][r];
+    if (role.kind == 0) {
+        if (mode != 7 && P.channels != 3) {                       // opaque error of the dropped alpha; K:1267-1277, :1356
+            int opaque = 0;
+            for (int k = 0; k < 16; k++) { const int d = (int)(blk->tex[k] >> 24) - 255; opaque += d * d; }
+            best_err += opaque;
+        }
+        bc7_write_partitioned(out, Q, best_idx[0], best_idx[1], role.shape, mode);
+    } else if (role.kind == 1) {
+        const int abits = (mode == 4 && !role.swap) ? 3 : 2, aepbits = (mode == 4) ? 6 : 8;
+        int aq[2];
+        u32 aidx[2];
+        best_err += bc7_scalar_channel(aq, aidx, blk, role.rotation, abits, aepbits, P.rch);
+        bc7_write_mode45(out, Q[0][0], Q[0][1], best_idx[0], best_idx[1], aq[0], aq[1], aidx[0], aidx[1], mode, role.rotation,
+                         role.swap);
+    } else {
+        bc7_write_mode6(out, Q[0][0], Q[0][1], best_idx[0], best_idx[1]);
+    }
+    W.res_err[slot][r] = best_err;
 }
 
 // =============================================================================================
 // Warp program: per-lane phase functions.  A phase reads what earlier phases wrote to W and
 // writes disjoint locations; the caller separates phases with a warp barrier.
 // =============================================================================================
-// texels of `nvalid` consecutive blocks starting at first_block -> W.px
 ITW_HD void bc7_phase_load(int lane, Bc7Warp& W, const SurfaceView& s, long long first_block, int nvalid)
 {
     const int bw = s.width >> 2;
@@ -319,24 +638,69 @@ ITW_HD void bc7_phase_load(int lane, Bc7Warp& W, const SurfaceView& s, long long
         const long long id = first_block + slot;
         const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
         const uint8_t* p = s.ptr + (size_t)(by * 4 + (k >> 2)) * (size_t)s.stride + (size_t)(bx * 4 + (k & 3)) * 4;
-        float* px = W.px[slot];
-        px[k] = (float)p[0];
-        px[16 + k] = (float)p[1];
-        px[32 + k] = (float)p[2];
-        px[48 + k] = (float)p[3];
+        W.blk[slot].tex[k] = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
     }
     if (lane == 0) W.nvalid = nvalid;
+    for (int t = lane; t < kBc7Slots * 5; t += 32) W.win_pos[t / 5][t % 5] = -1;
 }
-// candidates of mode slot m (m = 0,1 need no ranking; m = 2,3,4 need bc7_phase_rank first)
-ITW_HD void bc7_phase_candidates(int lane, Bc7Warp& W, const Bc7Params& P, int m)
+// channel planes from the packed texels (a 4x4 byte transpose per group of four texels)
+ITW_HD void bc7_phase_planes(int lane, Bc7Warp& W)
 {
-    const int count = bc7_slot_count(P, m);
-    const int mode = bc7_slot_mode(m);
+    for (int t = lane; t < W.nvalid * 16; t += 32) {
+        const int slot = t >> 4, c = (t >> 2) & 3, i = t & 3;
+        const u32* x = &W.blk[slot].tex[4 * i];
+        u32 v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v |= ((x[j] >> (8 * c)) & 255u) << (8 * j);
+        W.blk[slot].plane[c][i] = v;
+    }
+}
+// One shape, both modes of a mode-slot pair (ma, mb): fits once, quantises and searches per mode.
+ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, int n, int ma, bool do_a, int mb, bool do_b)
+{
+    const Bc7Block* blk = &W.blk[slot];
+    const int mode_a = bc7_slot_mode(ma), mode_b = bc7_slot_mode(mb);
+    const int pairs = bc7_pairs(mode_a);
+    const int channels = (mode_a == 7) ? 4 : 3;
+    const u32 chmask = (channels == 4) ? 0xFFFFFFFFu : 0x00FFFFFFu;
+    u32 ends_a[6], ends_b[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) ends_a[i] = ends_b[i] = 0u;
+    for (int j = 0; j < pairs; j++) {
+        float ep[8], ep2[8];
+        u32 packed[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) ep[i] = 0.0f;
+        bc7_fit(ep, blk, 3, 1, (u32)shape_mask(shape, j), channels);
+#pragma unroll
+        for (int i = 0; i < 8; i++) ep2[i] = ep[i];
+        if (do_a) {
+            bc7_quantise(packed, ep, mode_a, channels);
+            if (j == 0) { ends_a[0] = packed[0]; ends_a[1] = packed[1]; }
+            else if (j == 1) { ends_a[2] = packed[0]; ends_a[3] = packed[1]; }
+            else { ends_a[4] = packed[0]; ends_a[5] = packed[1]; }
+        }
+        if (do_b) {
+            bc7_quantise(packed, ep2, mode_b, channels);
+            if (j == 0) { ends_b[0] = packed[0]; ends_b[1] = packed[1]; }
+            else if (j == 1) { ends_b[2] = packed[0]; ends_b[3] = packed[1]; }
+            else { ends_b[4] = packed[0]; ends_b[5] = packed[1]; }
+        }
+    }
+    const u32 pattern = shape_pattern(shape);
+    u32 idx[2];
+    if (do_a) W.cand_err[slot][0][n] = bc7_assign(idx, W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_a), pairs, pattern, ends_a, chmask);
+    if (do_b) W.cand_err[slot][1][n] = bc7_assign(idx, W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_b), pairs, pattern, ends_b, chmask);
+}
+// shapes of a pair of mode slots that walk the same list: (0,1) three-subset, (2,3) ranked two-subset,
+// (4,4) mode 7
+ITW_HD void bc7_phase_shapes(int lane, Bc7Warp& W, const Bc7Params& P, int ma, int mb)
+{
+    const int ca = bc7_slot_count(P, ma), cb = (mb != ma) ? bc7_slot_count(P, mb) : 0;
+    const int count = maxi(ca, cb);
     for (int t = lane; t < W.nvalid * count; t += 32) {
         const int slot = t / count, n = t - slot * count;
-        int q[24];
-        u32 i0, i1;
-        W.cand_err[slot][m][n] = bc7_eval_partitioned(W.px[slot], mode, bc7_slot_shape(W, slot, m, n), q, i0, i1);
+        bc7_eval_shape(W, lane, slot, bc7_slot_shape(W, slot, ma, n), n, ma, n < ca, mb, n < cb);
     }
 }
 // split-bound keys of the 64 two-subset shapes; set 0 = RGB (modes 1,3), set 1 = profile channels (mode 7)
@@ -350,62 +714,46 @@ ITW_HD void bc7_phase_keys(int lane, Bc7Warp& W, const Bc7Params& P, int set)
     const int channels = (set == 0) ? 3 : P.channels;
     for (int t = lane; t < W.nvalid * 64; t += 32) {
         const int slot = t >> 6, shape = t & 63;
-        float full[15];
-        masked_moments(full, W.px[slot], 0xFFFF, channels);
-        W.keys[slot][set][shape] = split_bound_key(W.px[slot], shape, full, channels);
+        W.keys[slot][shape] = bc7_split_key(&W.blk[slot], shape, channels);
     }
 }
 ITW_HD void bc7_phase_rank(int lane, Bc7Warp& W, int set)
 {
     for (int t = lane; t < W.nvalid * 64; t += 32) {
         const int slot = t >> 6, i = t & 63;
-        W.order[slot][set][rank_of(W.keys[slot][set], 64, i)] = W.keys[slot][set][i];
+        W.order[slot][set][rank_of(W.keys[slot], 64, i)] = W.keys[slot][i];
     }
 }
-// first minimum of each mode slot's candidate list; K:1320 (strict <)
-ITW_HD void bc7_phase_winners(int lane, Bc7Warp& W, const Bc7Params& P)
+// first minimum of the candidate lists just evaluated for mode slots (ma, mb); K:1320 (strict <)
+ITW_HD void bc7_phase_winners(int lane, Bc7Warp& W, const Bc7Params& P, int ma, int mb)
 {
-    for (int t = lane; t < W.nvalid * 5; t += 32) {
-        const int slot = t / 5, m = t - slot * 5;
+    const int nm = (mb != ma) ? 2 : 1;
+    for (int t = lane; t < W.nvalid * nm; t += 32) {
+        const int slot = t / nm, which = t - slot * nm;
+        const int m = which ? mb : ma;
         const int count = bc7_slot_count(P, m);
-        int best = -1;
-        float best_err = inf_f();
+        int best = -1, best_err = kErrNone;
         for (int n = 0; n < count; n++) {
-            float e = W.cand_err[slot][m][n];
+            const int e = W.cand_err[slot][which][n];
             if (e < best_err) { best_err = e; best = n; }
         }
         W.win_pos[slot][m] = best;
     }
 }
-ITW_HD void bc7_phase_chain_partitioned(int lane, Bc7Warp& W, const Bc7Params& P)
+ITW_HD void bc7_phase_chains(int lane, Bc7Warp& W, const Bc7Params& P)
 {
-    for (int t = lane; t < W.nvalid * 5; t += 32) bc7_chain_partitioned(W, P, t / 5, t % 5);
-}
-ITW_HD int bc7_rotations(const Bc7Params& P) { return P.sel[2] ? maxi(P.channels - P.ch0, 0) : 0; }
-ITW_HD void bc7_phase_chain_mode45(int lane, Bc7Warp& W, const Bc7Params& P)
-{
-    const int nrot = bc7_rotations(P), per = 3 * nrot;        // 2*nrot mode-4 roles then nrot mode-5 roles
-    for (int t = lane; t < W.nvalid * per; t += 32) {
-        const int slot = t / per, r = t - slot * per;
-        if (r < 2 * nrot) bc7_chain_mode45(W, P, slot, 5 + r, 4, P.ch0 + (r >> 1), r & 1);
-        else              bc7_chain_mode45(W, P, slot, 5 + r, 5, P.ch0 + (r - 2 * nrot), 0);
-    }
-}
-ITW_HD void bc7_phase_chain_mode6(int lane, Bc7Warp& W, const Bc7Params& P)
-{
-    if (!P.sel[3]) return;
-    const int role = 5 + 3 * bc7_rotations(P);
-    for (int t = lane; t < W.nvalid; t += 32) bc7_chain_mode6(W, P, t, role);
+    const int nroles = bc7_role_count(P);
+    for (int t = lane; t < W.nvalid * nroles; t += 32) bc7_chain(W, P, lane, t / nroles, t % nroles);
 }
 // first strict minimum over the roles in the reference's order, then the 16-byte store; K:2027
 ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* dst, long long first_block)
 {
-    const int nroles = 5 + 3 * bc7_rotations(P) + (P.sel[3] ? 1 : 0);
+    const int nroles = bc7_role_count(P);
     for (int t = lane; t < W.nvalid; t += 32) {
-        float best_err = inf_f();
+        int best_err = kErrNone;
         u32 code[4] = {0u, 0u, 0u, 0u};
         for (int r = 0; r < nroles; r++) {
-            float e = W.res_err[t][r];
+            const int e = W.res_err[t][r];
             if (e < best_err) {
                 best_err = e;
 #pragma unroll
@@ -418,27 +766,27 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
     }
 }
 
-// The whole program for one batch, as a list of (phase, barrier) pairs.  SYNC is __syncwarp() on
-// the device; the CPU emulation runs each phase for lanes 0..31 in turn.
+// The whole program for one batch, as a list of (phase, barrier) pairs.
 #define ITW_BC7_PROGRAM(PHASE)                                                         \
     PHASE(bc7_phase_load(lane, W, surf, first_block, nvalid));                         \
-    PHASE(bc7_phase_candidates(lane, W, P, 0));                                        \
-    PHASE(bc7_phase_candidates(lane, W, P, 1));                                        \
+    PHASE(bc7_phase_planes(lane, W));                                                  \
+    if (P.sel[0]) {                                                                    \
+        PHASE(bc7_phase_shapes(lane, W, P, 0, 1));                                     \
+        PHASE(bc7_phase_winners(lane, W, P, 0, 1));                                    \
+    }                                                                                  \
     if (bc7_needs_keys(P, 0)) {                                                        \
         PHASE(bc7_phase_keys(lane, W, P, 0));                                          \
         PHASE(bc7_phase_rank(lane, W, 0));                                             \
-        PHASE(bc7_phase_candidates(lane, W, P, 2));                                    \
-        PHASE(bc7_phase_candidates(lane, W, P, 3));                                    \
+        PHASE(bc7_phase_shapes(lane, W, P, 2, 3));                                     \
+        PHASE(bc7_phase_winners(lane, W, P, 2, 3));                                    \
     }                                                                                  \
     if (bc7_needs_keys(P, 1)) {                                                        \
         PHASE(bc7_phase_keys(lane, W, P, 1));                                          \
         PHASE(bc7_phase_rank(lane, W, 1));                                             \
-        PHASE(bc7_phase_candidates(lane, W, P, 4));                                    \
+        PHASE(bc7_phase_shapes(lane, W, P, 4, 4));                                     \
+        PHASE(bc7_phase_winners(lane, W, P, 4, 4));                                    \
     }                                                                                  \
-    PHASE(bc7_phase_winners(lane, W, P));                                              \
-    PHASE(bc7_phase_chain_partitioned(lane, W, P));                                    \
-    PHASE(bc7_phase_chain_mode45(lane, W, P));                                         \
-    PHASE(bc7_phase_chain_mode6(lane, W, P));                                          \
+    PHASE(bc7_phase_chains(lane, W, P));                                               \
     PHASE(bc7_phase_store(lane, W, P, dst, first_block));
 
 #if defined(__CUDACC__)

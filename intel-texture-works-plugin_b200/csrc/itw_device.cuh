@@ -24,7 +24,7 @@
 #define ITW_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define ITW_HD inline
-#define ITW_HD_NOINLINE
+#define ITW_HD_NOINLINE inline __attribute__((noinline))
 #endif
 
 #include "itw_tables.cuh"
@@ -57,6 +57,49 @@ ITW_HD float inf_f()
     return __int_as_float(0x7f800000);
 #else
     return INFINITY;
+#endif
+}
+
+// ---- packed-byte integer helpers (single SASS instructions on sm_100a: IDP.4A, VABSDIFF4, PRMT) ----
+ITW_HD u32 dp4a_u8(u32 a, u32 b, u32 c)          // c + sum over the four bytes of a.byte * b.byte
+{
+#if defined(__CUDA_ARCH__)
+    return __dp4a(a, b, c);
+#else
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+    return c;
+#endif
+}
+ITW_HD u32 absdiff_u8x4(u32 a, u32 b)            // per-byte |a - b|
+{
+#if defined(__CUDA_ARCH__)
+    return __vabsdiffu4(a, b);
+#else
+    u32 r = 0;
+    for (int i = 0; i < 4; i++) {
+        int x = (int)((a >> (8 * i)) & 255u) - (int)((b >> (8 * i)) & 255u);
+        r |= (u32)(x < 0 ? -x : x) << (8 * i);
+    }
+    return r;
+#endif
+}
+ITW_HD u32 byte_perm(u32 a, u32 b, u32 sel)      // PRMT: result byte i = byte (sel nibble i) of {b:a}
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    unsigned long long w = ((unsigned long long)b << 32) | a;
+    u32 r = 0;
+    for (int i = 0; i < 4; i++) r |= (u32)((w >> (8 * ((sel >> (4 * i)) & 7u))) & 255u) << (8 * i);
+    return r;
+#endif
+}
+ITW_HD int popcount16(u32 v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
 #endif
 }
 
