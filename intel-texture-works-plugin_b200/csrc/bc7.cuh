@@ -147,35 +147,85 @@ ITW_HD void load_planes(u32 (&P)[4][4], const View& v)
         for (int i = 0; i < 4; i++) P[c][i] = view_plane(v, c, i);
 }
 
-// PCA line through the masked texels, clamped to [0,255]; K:834-905.  ep[0..3] = A, ep[4..7] = B;
-// components >= channels are left untouched.
-ITW_HD_NOINLINE void bc7_fit(float* ep, const Bc7Block* blk, int rot, int alpha, u32 mask, int channels)
+// Power iteration on a packed symmetric matrix [xx xy xz xw yy yz yw zz zw ww]; K:207-229.  The loop is
+// kept rolled on purpose: the kernel is instruction-cache bound and this body runs 8 (or 4) times.
+template <int CH, int kIterations>
+ITW_HD void bc7_power_axis(float (&axis)[4], const float (&m)[10])
 {
-    const View v{blk, rot, alpha};
+    float v0 = 1.0f, v1 = 1.0f, v2 = 1.0f, v3 = 1.0f;
+#pragma unroll 1
+    for (int it = 0; it < kIterations; it++) {
+        float a0, a1, a2, a3 = 0.0f;
+        if (CH == 3) {
+            a0 = m[0] * v0 + m[1] * v1 + m[2] * v2;
+            a1 = m[1] * v0 + m[4] * v1 + m[5] * v2;
+            a2 = m[2] * v0 + m[5] * v1 + m[7] * v2;
+        } else {
+            a0 = m[0] * v0 + m[1] * v1 + m[2] * v2 + m[3] * v3;
+            a1 = m[1] * v0 + m[4] * v1 + m[5] * v2 + m[6] * v3;
+            a2 = m[2] * v0 + m[5] * v1 + m[7] * v2 + m[8] * v3;
+            a3 = m[3] * v0 + m[6] * v1 + m[8] * v2 + m[9] * v3;
+        }
+        v0 = a0; v1 = a1; v2 = a2; v3 = a3;
+        if (it & 1) {                                  // renormalise every other iteration: 1/sqrt, two exact ops
+            float n2 = a0 * a0;
+            n2 += a1 * a1;
+            n2 += a2 * a2;
+            if (CH == 4) n2 += a3 * a3;
+            const float rn = 1.0f / sqrtf(n2);
+            v0 *= rn; v1 *= rn; v2 *= rn; v3 *= rn;
+        }
+    }
+    axis[0] = v0; axis[1] = v1; axis[2] = v2; axis[3] = v3;
+}
+// cov = sum(xy) - sum(x)*sum(y)/n on exact integer moments; K:805-823.  sum(x)*sum(y) < 2^24 is an
+// exact integer, so the division by the count can use the slow-path-free exact quotient.
+template <int CH>
+ITW_HD void bc7_covariance(float (&cov)[10], float (&mean)[4], const int (&st)[15])
+{
+    const float n = (float)st[14], rn = 1.0f / n;
+    float s[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) s[c] = (float)st[10 + c];
+#pragma unroll
+    for (int i = 0; i < 10; i++) cov[i] = 0.0f;
+    cov[0] = (float)st[0] - div_by_rcp(s[0] * s[0], n, rn);
+    cov[1] = (float)st[1] - div_by_rcp(s[0] * s[1], n, rn);
+    cov[2] = (float)st[2] - div_by_rcp(s[0] * s[2], n, rn);
+    cov[4] = (float)st[4] - div_by_rcp(s[1] * s[1], n, rn);
+    cov[5] = (float)st[5] - div_by_rcp(s[1] * s[2], n, rn);
+    cov[7] = (float)st[7] - div_by_rcp(s[2] * s[2], n, rn);
+    if (CH == 4) {
+        cov[3] = (float)st[3] - div_by_rcp(s[0] * s[3], n, rn);
+        cov[6] = (float)st[6] - div_by_rcp(s[1] * s[3], n, rn);
+        cov[8] = (float)st[8] - div_by_rcp(s[2] * s[3], n, rn);
+        cov[9] = (float)st[9] - div_by_rcp(s[3] * s[3], n, rn);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) mean[c] = (c < CH) ? div_by_rcp(s[c], n, rn) : 0.0f;
+}
+template <int CH>
+ITW_HD void bc7_fit_impl(float* ep, const View& v, u32 mask)
+{
     u32 P[4][4];
     load_planes(P, v);
     int ist[15];
-    moments_u8(ist, P, mask, channels);
-    float st[15], cov[10], mean[4], axis[4];
-#pragma unroll
-    for (int i = 0; i < 15; i++) st[i] = (float)ist[i];
-    covariance_of(cov, st, channels);
-#pragma unroll
-    for (int c = 0; c < 4; c++) mean[c] = (c < channels) ? st[10 + c] / st[14] : 0.0f;
+    moments_u8(ist, P, mask, CH);
+    float cov[10], mean[4], axis[4];
+    bc7_covariance<CH>(cov, mean, ist);
     const float inv_var = 1.0f / (256.0f * 256.0f);
 #pragma unroll
     for (int i = 0; i < 10; i++) cov[i] *= inv_var;
     const float eps = 0.001f * 0.001f;
     cov[0] += eps; cov[4] += eps; cov[7] += eps; cov[9] += eps;
-    power_axis<8>(axis, cov, channels);
+    bc7_power_axis<CH, 8>(axis, cov);
 
     float lo = inf_f(), hi = -inf_f();
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         float d = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (c < channels) d += axis[c] * ((float)((P[c][k >> 2] >> (8 * (k & 3))) & 255u) - mean[c]);
+        for (int c = 0; c < CH; c++) d += axis[c] * ((float)((P[c][k >> 2] >> (8 * (k & 3))) & 255u) - mean[c]);
         if ((mask >> k) & 1u) {
             lo = min_sse(lo, d);
             hi = max_sse(hi, d);
@@ -183,50 +233,131 @@ ITW_HD_NOINLINE void bc7_fit(float* ep, const Bc7Block* blk, int rot, int alpha,
     }
     if (hi - lo < 1.0f) { lo -= 0.5f; hi += 0.5f; }
 #pragma unroll
-    for (int c = 0; c < 4; c++)
-        if (c < channels) {
-            ep[c] = clamp_sse(lo * axis[c] + mean[c], 0.0f, 255.0f);
-            ep[4 + c] = clamp_sse(hi * axis[c] + mean[c], 0.0f, 255.0f);
-        }
+    for (int c = 0; c < CH; c++) {
+        ep[c] = clamp_sse(lo * axis[c] + mean[c], 0.0f, 255.0f);
+        ep[4 + c] = clamp_sse(hi * axis[c] + mean[c], 0.0f, 255.0f);
+    }
+}
+// PCA line through the masked texels, clamped to [0,255]; K:834-905.  ep[0..3] = A, ep[4..7] = B;
+// components >= channels are left untouched.
+ITW_HD_NOINLINE void bc7_fit(float* ep, const Bc7Block* blk, int rot, int alpha, u32 mask, int channels)
+{
+    const View v{blk, rot, alpha};
+    if (channels == 4) bc7_fit_impl<4>(ep, v, mask);
+    else bc7_fit_impl<3>(ep, v, mask);
 }
 
+// trace - lambda_max of a covariance; K:907-939 (eps on three diagonal slots only, K:918-920)
+template <int CH>
+ITW_HD float bc7_residual_bound(float (&cov)[10])
+{
+    const float inv_var = 1.0f / (256.0f * 256.0f);
+#pragma unroll
+    for (int i = 0; i < 10; i++) cov[i] *= inv_var;
+    const float eps = 0.001f * 0.001f;
+    cov[0] += eps; cov[4] += eps; cov[7] += eps;
+    float axis[4];
+    bc7_power_axis<CH, 4>(axis, cov);
+    float mv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (CH == 3) {
+        mv[0] = cov[0] * axis[0] + cov[1] * axis[1] + cov[2] * axis[2];
+        mv[1] = cov[1] * axis[0] + cov[4] * axis[1] + cov[5] * axis[2];
+        mv[2] = cov[2] * axis[0] + cov[5] * axis[1] + cov[7] * axis[2];
+    } else {
+        mv[0] = cov[0] * axis[0] + cov[1] * axis[1] + cov[2] * axis[2] + cov[3] * axis[3];
+        mv[1] = cov[1] * axis[0] + cov[4] * axis[1] + cov[5] * axis[2] + cov[6] * axis[3];
+        mv[2] = cov[2] * axis[0] + cov[5] * axis[1] + cov[7] * axis[2] + cov[8] * axis[3];
+        mv[3] = cov[3] * axis[0] + cov[6] * axis[1] + cov[8] * axis[2] + cov[9] * axis[3];
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CH; c++) sum += sq(mv[c]);
+    float bound = cov[0] + cov[4] + cov[7];
+    if (CH == 4) bound += cov[9];
+    bound -= sqrtf(sum);
+    return max_sse(bound, 0.0f);
+}
 // Ranking key of a two-subset shape (K:952-971, :1403-1410); subset 1 = full - subset 0
-ITW_HD_NOINLINE int bc7_split_key(const Bc7Block* blk, int shape, int channels)
+template <int CH>
+ITW_HD int bc7_split_key_impl(const Bc7Block* blk, int shape)
 {
     const View v{blk, 3, 1};
     u32 P[4][4];
     load_planes(P, v);
-    int full[15], part[15];
-    moments_u8(full, P, 0xFFFFu, channels);
-    moments_u8(part, P, (u32)shape_mask(shape, 0), channels);
-    float st[15], c1[10], c2[10];
+    int full[15], part[15], rest[15];
+    moments_u8(full, P, 0xFFFFu, CH);
+    moments_u8(part, P, (u32)shape_mask(shape, 0), CH);
 #pragma unroll
-    for (int i = 0; i < 15; i++) st[i] = (float)part[i];
-    covariance_of(c1, st, channels);
-#pragma unroll
-    for (int i = 0; i < 15; i++) st[i] = (float)(full[i] - part[i]);     // exact: the reference subtracts exact floats
-    covariance_of(c2, st, channels);
+    for (int i = 0; i < 15; i++) rest[i] = full[i] - part[i];            // exact: the reference subtracts exact floats
+    float c1[10], c2[10], mean[4];
+    bc7_covariance<CH>(c1, mean, part);
+    bc7_covariance<CH>(c2, mean, rest);
     float b = 0.0f;
-    b += residual_bound(c1, channels);
-    b += residual_bound(c2, channels);
+    b += bc7_residual_bound<CH>(c1);
+    b += bc7_residual_bound<CH>(c2);
     return shape + (int)((unsigned)cvt_x86(sqrtf(b) * 256.0f) * 64u);
 }
-
-// Quantise one endpoint pair (K:983-1128) and pack it: out[0],out[1] = decoded A,B as RGBA bytes,
-// out[2],out[3] = quantised A,B as RGBA bytes.  ep is updated to the decoded values.
-ITW_HD_NOINLINE void bc7_quantise(u32* out, float* ep, int mode, int channels)
+ITW_HD_NOINLINE int bc7_split_key(const Bc7Block* blk, int shape, int channels)
 {
-    int q[8];
-    bc7_quantise_pair(q, ep, mode, channels);
-    u32 d[2] = {0u, 0u}, p[2] = {0u, 0u};
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            d[i] |= ((u32)ep[4 * i + c] & 255u) << (8 * c);
-            p[i] |= ((u32)q[4 * i + c] & 255u) << (8 * c);
+    return (channels == 4) ? bc7_split_key_impl<4>(blk, shape) : bc7_split_key_impl<3>(blk, shape);
+}
+
+// Quantise one endpoint pair; K:983-1128.  out[0],out[1] = decoded A,B as RGBA bytes, out[2],out[3] =
+// quantised A,B as RGBA bytes.  `channels` = components that vote on the p-bit (K:1011-1020); all four
+// components are always produced (a never-written component is quantised from 0, rule F6).
+// One rolled loop over the 8 components serves all three families:
+//   modes 0,3,6,7  one p-bit per endpoint   K:983-1022   (the vote compares against the RAW quantised value
+//                                                         except in mode 0 -- reference behaviour, K:1003-1009)
+//   mode 1         one p-bit per pair        K:1024-1052  (a single running error sum over both endpoints)
+//   modes 2,4,5    no p-bit                  K:1054-1065
+ITW_HD_NOINLINE void bc7_quantise(u32* out, const float* ep, int mode, int channels)
+{
+    const int family = (mode == 1) ? 1 : ((mode == 2 || mode == 4 || mode == 5) ? 2 : 0);
+    // stored bits per component including the p-bit: 2^qbits - 1 is K's `levels2` (p-bit modes) or `levels-1`
+    const int qbits = (mode == 0 || mode == 2 || mode == 4) ? 5 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 8));
+    const int top = (1 << qbits) - 1;
+    const float ftop = (float)top;
+    const int vote_bits = (mode == 0) ? 5 : ((mode == 1) ? 7 : 8);       // expand_bits(v, 8) == v
+    const int votes = (mode == 1) ? 3 : channels;
+    u32 cand0[2] = {0u, 0u}, cand1[2] = {0u, 0u};
+    bool pick1[2] = {false, false};
+    float e0 = 0.0f, e1 = 0.0f;
+#pragma unroll 1
+    for (int n = 0; n < 8; n++) {
+        const int i = n >> 2, c = n & 3;
+        if (family == 0 && c == 0) { e0 = 0.0f; e1 = 0.0f; }
+        const float x = ep[n];
+        const float t = div255(x) * ftop;
+        int v0, v1;
+        if (family == 2) {
+            v0 = v1 = clampi(cvt_x86(t + 0.5f), 0, top);
+        } else {                                                          // ((t - b)/2 + 0.5) truncated, *2 + b
+            v0 = clampi((int)((unsigned)cvt_x86(t * 0.5f + 0.5f) * 2u), 0, top - 1);
+            v1 = clampi((int)((unsigned)cvt_x86((t - 1.0f) * 0.5f + 0.5f) * 2u + 1u), 1, top);
         }
-    out[0] = d[0]; out[1] = d[1]; out[2] = p[0]; out[3] = p[1];
+        if (i == 0) { cand0[0] |= (u32)v0 << (8 * c); cand1[0] |= (u32)v1 << (8 * c); }
+        else        { cand0[1] |= (u32)v0 << (8 * c); cand1[1] |= (u32)v1 << (8 * c); }
+        if (c < votes) {
+            e0 += sq(x - (float)expand_bits(v0, vote_bits));
+            e1 += sq(x - (float)expand_bits(v1, vote_bits));
+        }
+        if (c == 3) {
+            const bool p = !(e0 < e1);
+            if (i == 0) pick1[0] = p; else pick1[1] = p;
+        }
+    }
+    if (family == 1) pick1[0] = pick1[1];                                // decided after both endpoints
+    if (family == 2) pick1[0] = pick1[1] = false;
+    // decode all four bytes at once (K:1093-1122): v << (8-d) | that >> d, bytewise
+    const int dbits = (mode == 3 || mode == 6) ? 8 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 5));
+    const u32 lowmask = 0x01010101u * (0xFFu >> dbits);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const u32 q = pick1[i] ? cand1[i] : cand0[i];
+        const u32 vv = q << (8 - dbits);
+        out[i] = vv + ((vv >> dbits) & lowmask);
+        out[2 + i] = q;
+    }
 }
 
 // Integer interpolation of two packed RGBA endpoints with BC7 weight w (K:1172: ((64-w)a+wb+32)/64
@@ -249,16 +380,17 @@ ITW_HD_NOINLINE int bc7_assign(u32* idx, u32 (*pal)[32], int lane, const Bc7Bloc
     const int levels = 1 << bits;
     u32 EA[3], EB[3];
     int cst[3];
-    float fdiv[3];
+    float fdiv[3], frcp[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        EA[j] = EB[j] = 0u; cst[j] = 0; fdiv[j] = 1.0f;
+        EA[j] = EB[j] = 0u; cst[j] = 0; fdiv[j] = 1.0f; frcp[j] = 1.0f;
         if (j < pairs) {
             const u32 a = ends[2 * j] & chmask, b = ends[2 * j + 1] & chmask;
             const u32 aa = dp4a_u8(a, a, 0u), ab = dp4a_u8(a, b, 0u), bb = dp4a_u8(b, b, 0u);
             EA[j] = a; EB[j] = b;
             cst[j] = (int)(ab - aa);
             fdiv[j] = (float)(int)(bb - 2u * ab + aa);          // sum of squared differences, exact
+            frcp[j] = 1.0f / fdiv[j];                           // inf when the endpoints coincide (-> NaN below, as 0/0)
             for (int q = 0; q < levels; q++) pal[j * levels + q][lane] = lerp_rgba(a, b, (u32)bc7_weight(bits, q));
         }
     }
@@ -273,10 +405,12 @@ ITW_HD_NOINLINE int bc7_assign(u32* idx, u32 (*pal)[32], int lane, const Bc7Bloc
         const u32 eb = (j == 0) ? EB[0] : ((j == 1) ? EB[1] : EB[2]);
         const int cj = (j == 0) ? cst[0] : ((j == 1) ? cst[1] : cst[2]);
         const float dj = (j == 0) ? fdiv[0] : ((j == 1) ? fdiv[1] : fdiv[2]);
+        const float rj = (j == 0) ? frcp[0] : ((j == 1) ? frcp[1] : frcp[2]);
         // sum_c (t_c - a_c)(b_c - a_c): integer, |value| < 2^18, so the float it converts to is the
-        // reference's float sum; one IEEE division follows as in K:1158
+        // reference's float sum; the division of K:1158 is the exact FMA-corrected quotient (proved
+        // equal to IEEE num/div on this integer domain, tests/test_exact_division.py)
         const int num = (int)dp4a_u8(t, eb, 0u) - (int)dp4a_u8(t, ea, 0u) - cj;
-        const float proj = (float)num / dj;
+        const float proj = div_by_rcp((float)num, dj, rj);
         // NaN (coincident endpoints, 0/0) converts to INT_MIN on x86 and clamps to 1 (K:1160-1161)
         const int q1 = clampi(cvt_x86(proj * flevels + 0.5f), 1, levels - 1);
         const u32 p0 = pal[j * levels + q1 - 1][lane], p1 = pal[j * levels + q1][lane];
@@ -444,6 +578,7 @@ ITW_HD float scalar_assign(u32& idx0, u32& idx1, const Bc7Block* blk, int shift,
     const int levels = 1 << bits;
     u32 out[2] = {0u, 0u};
     float total = 0.0f;
+#pragma unroll 1
     for (int k = 0; k < 16; k++) {
         const float a = scalar_texel(blk, k, shift);
         float proj = (a - ep[0]) / (ep[1] - ep[0] + 0.001f);
@@ -465,6 +600,7 @@ ITW_HD void scalar_solve(float (&ep)[2], const Bc7Block* blk, int shift, int bit
 {
     const float top = (float)((1 << bits) - 1);
     float atb1 = 0.0f, sq1 = 0.0f, sqq = 0.0f, sum = 0.0f;
+#pragma unroll 1
     for (int k = 0; k < 16; k++) {
         const float a = scalar_texel(blk, k, shift);
         float q = (float)(((k < 8 ? idx0 : idx1) >> (4 * (k & 7))) & 15u);
@@ -491,6 +627,7 @@ ITW_HD_NOINLINE int bc7_scalar_channel(int* aq, u32* aidx, const Bc7Block* blk, 
 {
     const int shift = 8 * rotation;
     float ep[2] = {255.0f, 0.0f};
+#pragma unroll 1
     for (int k = 0; k < 16; k++) {
         const float a = scalar_texel(blk, k, shift);
         ep[0] = min_sse(ep[0], a);
@@ -500,6 +637,7 @@ ITW_HD_NOINLINE int bc7_scalar_channel(int* aq, u32* aidx, const Bc7Block* blk, 
     u32 a0, a1;
     scalar_quantise(q, ep, aepbits);
     float err = scalar_assign(a0, a1, blk, shift, abits, ep);
+#pragma unroll 1
     for (int it = 0; it < rch; it++) {
         scalar_solve(ep, blk, shift, abits, a0, a1);
         scalar_quantise(q, ep, aepbits);
@@ -570,7 +708,7 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
         bc7_fit(ep, blk, rot, alpha, mask, channels);
         if (role.kind == 2 && channels == 3) ep[3] = ep[7] = 255.0f;     // K:1664-1667
         bc7_quantise(packed, ep, mode, channels);
-        tail_a = ep[3]; tail_b = ep[7];
+        tail_a = (float)(packed[0] >> 24); tail_b = (float)(packed[1] >> 24);
         if (j == 0) { ends[0] = packed[0]; ends[1] = packed[1]; Q[0][0] = packed[2]; Q[0][1] = packed[3]; }
         else if (j == 1) { ends[2] = packed[0]; ends[3] = packed[1]; Q[1][0] = packed[2]; Q[1][1] = packed[3]; }
         else { ends[4] = packed[0]; ends[5] = packed[1]; Q[2][0] = packed[2]; Q[2][1] = packed[3]; }
@@ -590,7 +728,7 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
             const u32 mask = (role.kind == 0) ? (u32)shape_mask(role.shape, j) : 0xFFFFu;
             bc7_solve(ep, blk, rot, alpha, bits, best_idx[0], best_idx[1], mask, channels);
             bc7_quantise(packed, ep, mode, vote_refine);
-            tail_a = ep[3]; tail_b = ep[7];
+            tail_a = (float)(packed[0] >> 24); tail_b = (float)(packed[1] >> 24);
             if (j == 0) { ends[0] = packed[0]; ends[1] = packed[1]; nQ[0][0] = packed[2]; nQ[0][1] = packed[3]; }
             else if (j == 1) { ends[2] = packed[0]; ends[3] = packed[1]; nQ[1][0] = packed[2]; nQ[1][1] = packed[3]; }
             else { ends[4] = packed[0]; ends[5] = packed[1]; nQ[2][0] = packed[2]; nQ[2][1] = packed[3]; }
@@ -667,13 +805,11 @@ ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, i
 #pragma unroll
     for (int i = 0; i < 6; i++) ends_a[i] = ends_b[i] = 0u;
     for (int j = 0; j < pairs; j++) {
-        float ep[8], ep2[8];
+        float ep[8];
         u32 packed[4];
 #pragma unroll
         for (int i = 0; i < 8; i++) ep[i] = 0.0f;
         bc7_fit(ep, blk, 3, 1, (u32)shape_mask(shape, j), channels);
-#pragma unroll
-        for (int i = 0; i < 8; i++) ep2[i] = ep[i];
         if (do_a) {
             bc7_quantise(packed, ep, mode_a, channels);
             if (j == 0) { ends_a[0] = packed[0]; ends_a[1] = packed[1]; }
@@ -681,7 +817,7 @@ ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, i
             else { ends_a[4] = packed[0]; ends_a[5] = packed[1]; }
         }
         if (do_b) {
-            bc7_quantise(packed, ep2, mode_b, channels);
+            bc7_quantise(packed, ep, mode_b, channels);
             if (j == 0) { ends_b[0] = packed[0]; ends_b[1] = packed[1]; }
             else if (j == 1) { ends_b[2] = packed[0]; ends_b[3] = packed[1]; }
             else { ends_b[4] = packed[0]; ends_b[5] = packed[1]; }

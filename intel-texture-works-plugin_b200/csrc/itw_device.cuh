@@ -60,6 +60,28 @@ ITW_HD float inf_f()
 #endif
 }
 
+// ---- exact division without the IEEE-division slow path -------------------------------------------
+// q = RN(x * RN(1/d)), r = x - q*d (exact in one FMA), result = RN(q + r * RN(1/d)): the classic
+// FMA-corrected quotient.  It is NOT correctly rounded for arbitrary operands, so it is only used
+// where tests/test_exact_division.py proves it equal to IEEE x/d over the whole operand domain:
+//   * d = 255 and any finite x (differs from x/255 only for x = -0 -> +0, which no caller can see);
+//   * integer x in [0, 2^24] with d in 1..16 (moment / count);
+//   * integer |x| <= 2^18 with integer d in [1, 2^18] (index-search projection; d = 0 gives NaN like 0/0).
+ITW_HD float fma_rn(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+ITW_HD float div_by_rcp(float x, float d, float rcp_d)
+{
+    const float q = x * rcp_d;
+    return fma_rn(fma_rn(-q, d, x), rcp_d, q);
+}
+ITW_HD float div255(float x) { return div_by_rcp(x, 255.0f, 1.0f / 255.0f); }
+
 // ---- packed-byte integer helpers (single SASS instructions on sm_100a: IDP.4A, VABSDIFF4, PRMT) ----
 ITW_HD u32 dp4a_u8(u32 a, u32 b, u32 c)          // c + sum over the four bytes of a.byte * b.byte
 {
