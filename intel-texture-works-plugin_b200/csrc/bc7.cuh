@@ -319,32 +319,39 @@ ITW_HD_NOINLINE void bc7_quantise(u32* out, const float* ep, int mode, int chann
     const float ftop = (float)top;
     const int vote_bits = (mode == 0) ? 5 : ((mode == 1) ? 7 : 8);       // expand_bits(v, 8) == v
     const int votes = (mode == 1) ? 3 : channels;
+    // Conversions: |ep| < 2^31 always holds here -- the fit clamps to [0,255] and the least-squares
+    // solve divides by an exact non-zero INTEGER determinant (bc7_solve), which bounds |ep| by ~1.2e7 --
+    // so the x86 overflow rule of cvt_x86() can never trigger and a plain truncation is identical.
+    // t*0.5 and (t-1)*0.5 are exact (power-of-two scaling), so fusing the +0.5 rounds once, exactly like
+    // the reference's separate multiply and add.
     u32 cand0[2] = {0u, 0u}, cand1[2] = {0u, 0u};
     bool pick1[2] = {false, false};
     float e0 = 0.0f, e1 = 0.0f;
 #pragma unroll 1
-    for (int n = 0; n < 8; n++) {
-        const int i = n >> 2, c = n & 3;
-        if (family == 0 && c == 0) { e0 = 0.0f; e1 = 0.0f; }
-        const float x = ep[n];
-        const float t = div255(x) * ftop;
-        int v0, v1;
-        if (family == 2) {
-            v0 = v1 = clampi(cvt_x86(t + 0.5f), 0, top);
-        } else {                                                          // ((t - b)/2 + 0.5) truncated, *2 + b
-            v0 = clampi((int)((unsigned)cvt_x86(t * 0.5f + 0.5f) * 2u), 0, top - 1);
-            v1 = clampi((int)((unsigned)cvt_x86((t - 1.0f) * 0.5f + 0.5f) * 2u + 1u), 1, top);
+    for (int i = 0; i < 2; i++) {
+        if (family == 0) { e0 = 0.0f; e1 = 0.0f; }
+        u32 c0 = 0u, c1 = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float x = ep[4 * i + c];
+            const float t = div255(x) * ftop;
+            int v0, v1;
+            if (family == 2) {
+                v0 = v1 = clampi(trunc_i(t + 0.5f), 0, top);
+            } else {                                                      // ((t - b)/2 + 0.5) truncated, *2 + b
+                v0 = clampi(trunc_i(fma_rn(t, 0.5f, 0.5f)) * 2, 0, top - 1);
+                v1 = clampi(trunc_i(fma_rn(t - 1.0f, 0.5f, 0.5f)) * 2 + 1, 1, top);
+            }
+            c0 |= (u32)v0 << (8 * c);
+            c1 |= (u32)v1 << (8 * c);
+            if (c < votes) {
+                e0 += sq(x - (float)expand_bits(v0, vote_bits));
+                e1 += sq(x - (float)expand_bits(v1, vote_bits));
+            }
         }
-        if (i == 0) { cand0[0] |= (u32)v0 << (8 * c); cand1[0] |= (u32)v1 << (8 * c); }
-        else        { cand0[1] |= (u32)v0 << (8 * c); cand1[1] |= (u32)v1 << (8 * c); }
-        if (c < votes) {
-            e0 += sq(x - (float)expand_bits(v0, vote_bits));
-            e1 += sq(x - (float)expand_bits(v1, vote_bits));
-        }
-        if (c == 3) {
-            const bool p = !(e0 < e1);
-            if (i == 0) pick1[0] = p; else pick1[1] = p;
-        }
+        const bool p = !(e0 < e1);
+        if (i == 0) { cand0[0] = c0; cand1[0] = c1; pick1[0] = p; }
+        else        { cand0[1] = c0; cand1[1] = c1; pick1[1] = p; }
     }
     if (family == 1) pick1[0] = pick1[1];                                // decided after both endpoints
     if (family == 2) pick1[0] = pick1[1] = false;
@@ -411,8 +418,10 @@ ITW_HD_NOINLINE int bc7_assign(u32* idx, u32 (*pal)[32], int lane, const Bc7Bloc
         // equal to IEEE num/div on this integer domain, tests/test_exact_division.py)
         const int num = (int)dp4a_u8(t, eb, 0u) - (int)dp4a_u8(t, ea, 0u) - cj;
         const float proj = div_by_rcp((float)num, dj, rj);
-        // NaN (coincident endpoints, 0/0) converts to INT_MIN on x86 and clamps to 1 (K:1160-1161)
-        const int q1 = clampi(cvt_x86(proj * flevels + 0.5f), 1, levels - 1);
+        // |proj*levels| < 2^23, so truncation never overflows; NaN (coincident endpoints, 0/0) becomes
+        // INT_MIN on x86 and 0 here -- both clamp to 1 (K:1160-1161).  proj*levels is exact, so the fused
+        // form rounds once like the reference's multiply-then-add.
+        const int q1 = clampi(trunc_i(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);
         const u32 p0 = pal[j * levels + q1 - 1][lane], p1 = pal[j * levels + q1][lane];
         const u32 d0 = absdiff_u8x4(p0, t), d1 = absdiff_u8x4(p1, t);
         const int e0 = (int)dp4a_u8(d0, d0, 0u), e1 = (int)dp4a_u8(d1, d1, 0u);
@@ -926,21 +935,30 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
     PHASE(bc7_phase_store(lane, W, P, dst, first_block));
 
 #if defined(__CUDACC__)
-constexpr int kBc7WarpsPerCta = 4;
+// All warps of a CTA walk the phases in lock step (block barrier between phases) and one CTA fills an
+// SM: at any moment every warp of the SM is inside the same few hundred instructions, which is what
+// the instruction cache needs -- the first version of this kernel lost 90 % of its issue slots to
+// instruction fetch (profiles/r1_bc7_v1_ncu.txt).  Work per phase is the same for every warp, so the
+// barriers cost little.
+constexpr int kBc7WarpsPerCta = 16;
+constexpr size_t kBc7SmemBytes = sizeof(Bc7Warp) * kBc7WarpsPerCta;
 
-__global__ void __launch_bounds__(kBc7WarpsPerCta * 32)
+__global__ void __launch_bounds__(kBc7WarpsPerCta * 32, 1)
 bc7_kernel(SurfaceView surf, uint8_t* __restrict__ dst, Bc7Params P, long long nblocks)
 {
-    __shared__ Bc7Warp warps[kBc7WarpsPerCta];
-    Bc7Warp& W = warps[threadIdx.x >> 5];
+    extern __shared__ __align__(16) unsigned char bc7_smem[];
+    Bc7Warp& W = reinterpret_cast<Bc7Warp*>(bc7_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const long long nbatches = (nblocks + kBc7Slots - 1) / kBc7Slots;
     const long long warp0 = (long long)blockIdx.x * kBc7WarpsPerCta + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kBc7WarpsPerCta;
-    for (long long batch = warp0; batch < nbatches; batch += nwarps) {
+    const long long rounds = (nbatches + nwarps - 1) / nwarps;            // same trip count for every warp of the CTA
+    for (long long round = 0; round < rounds; round++) {
+        const long long batch = warp0 + round * nwarps;
         const long long first_block = batch * kBc7Slots;
-        const int nvalid = (int)((nblocks - first_block < kBc7Slots) ? (nblocks - first_block) : kBc7Slots);
-#define ITW_PHASE_DEVICE(call) call; __syncwarp()
+        const long long left = nblocks - first_block;
+        const int nvalid = (int)(left <= 0 ? 0 : (left < kBc7Slots ? left : kBc7Slots));
+#define ITW_PHASE_DEVICE(call) call; __syncthreads()
         ITW_BC7_PROGRAM(ITW_PHASE_DEVICE)
 #undef ITW_PHASE_DEVICE
     }

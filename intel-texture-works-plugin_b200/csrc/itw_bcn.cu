@@ -141,11 +141,12 @@ int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* setting
             if (!settings) return fail("CompressBlocksBC7: null settings");
             const Bc7Params P = bc7_params_from(*static_cast<const bc7_enc_settings*>(settings));
             if (const char* why = bc7_params_check(P)) return fail(why);
-            int occ = 1;
-            ITW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bc7_kernel, kBc7WarpsPerCta * 32, 0));
+            // per-device attribute; cheap enough to set on every (millisecond-scale) launch
+            ITW_CUDA(cudaFuncSetAttribute(bc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc7SmemBytes));
+            // one 16-warp CTA per SM, persistent over the batches
             const long long want = (nblocks + kBc7Slots * kBc7WarpsPerCta - 1) / (kBc7Slots * kBc7WarpsPerCta);
-            const long long cap = (long long)tls.sm_count * (occ > 0 ? occ : 1);
-            bc7_kernel<<<(unsigned)(want < cap ? want : cap), kBc7WarpsPerCta * 32, 0, stream>>>(v, d_dst, P, nblocks);
+            const long long cap = (long long)tls.sm_count;
+            bc7_kernel<<<(unsigned)(want < cap ? want : cap), kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks);
             break;
         }
         case ITW_FORMAT_BC6H: {

@@ -44,6 +44,16 @@ ITW_HD int cvt_x86(float f)
     return (int)f;
 #endif
 }
+// plain truncation; only where the operand is proved to be in int range (NaN -> 0 on the GPU, INT_MIN on
+// the host emulation: callers must make that difference invisible)
+ITW_HD int trunc_i(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float2int_rz(f);
+#else
+    return (f == f) ? (int)f : (int)0x80000000;
+#endif
+}
 ITW_HD float min_sse(float a, float b) { return (a < b) ? a : b; }
 ITW_HD float max_sse(float a, float b) { return (a > b) ? a : b; }
 ITW_HD float clamp_sse(float v, float lo, float hi) { return min_sse(max_sse(v, lo), hi); }
