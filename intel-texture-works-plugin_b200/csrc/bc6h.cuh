@@ -7,8 +7,9 @@
 // conversion that overflows to INT_MIN (K:1178, quirk Q3), so NOTHING here may be re-associated:
 // every float sum stays inside one lane in the reference's texel order.
 //
-// The reference recomputes the 32 split bounds for every two-region mode it tries (K:2257-2273);
-// they only depend on the texels, so they are computed once per block here (same values).
+// The reference recomputes the 32 split bounds AND the PCA segments of each ranked shape for every
+// two-region mode it tries (K:2257-2273, :2174-2193); both depend only on the texels, so they are
+// computed once per block here (same values) and the six modes share them.
 #pragma once
 #include "bc67_core.cuh"
 
@@ -18,7 +19,7 @@ struct Bc6Params {
     int slow_mode, fast_mode, refine_1p, refine_2p, fast_skip;
 };
 
-constexpr int kBc6Slots = 4;
+constexpr int kBc6Slots = 2;
 constexpr int kBc6MaxTwo = 6;    // two-region modes tried per block
 constexpr int kBc6MaxOne = 4;    // one-region modes tried per block
 
@@ -36,6 +37,7 @@ struct Bc6Warp {
     int keys[kBc6Slots][32], order[kBc6Slots][32];
     Bc6Entry two[kBc6Slots][kBc6MaxTwo], one[kBc6Slots][kBc6MaxOne];
     int ntwo[kBc6Slots], none[kBc6Slots];
+    float fit[kBc6Slots][32][16];                 // unquantised segments of ranked shape n: [subset][A rgb., B rgb.]
     float cand_err[kBc6Slots][kBc6MaxTwo][32];
     int win_pos[kBc6Slots][kBc6MaxTwo];
     float res_err[kBc6Slots][kBc6MaxTwo + kBc6MaxOne];
@@ -208,12 +210,12 @@ ITW_HD_NOINLINE void bc6_put_header(BitSink& s, const int* q, int mode)
 }
 
 // ---- candidate / chains; K:2174-2300, :2982-3031 ----
-ITW_HD_NOINLINE float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, int* q, u32& idx0, u32& idx1)
+// Quantise a stored (mode-independent) fit for entry E and run the index search; K:2188-2191
+ITW_HD_NOINLINE float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, const float* fit, int* q, u32& idx0, u32& idx1)
 {
     float ep[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) ep[i] = 0.0f;
-    for (int j = 0; j < 2; j++) fit_segment(ep + 8 * j, px, shape_mask(shape, j), 3, false);
+    for (int i = 0; i < 16; i++) ep[i] = fit[i];
     bc6_quant_dequant(E, q, ep, 2);
     return assign_indices(idx0, idx1, px, 3, ep, shape_pattern(shape), 3);
 }
@@ -227,7 +229,7 @@ ITW_HD_NOINLINE void bc6_chain_two_region(Bc6Warp& W, const Bc6Params& P, int sl
     const int shape = W.order[slot][pos] & 31;
     int best_q[16];
     u32 best_i0, best_i1;
-    float best_err = bc6_eval_two_region(px, E, shape, best_q, best_i0, best_i1);
+    float best_err = bc6_eval_two_region(px, E, shape, W.fit[slot][pos], best_q, best_i0, best_i1);
     for (int it = 0; it < P.refine_2p; it++) {
         float ep[16];
         int q[16];
@@ -371,6 +373,19 @@ ITW_HD void bc6_phase_rank(int lane, Bc6Warp& W)
         W.order[slot][rank_of(W.keys[slot], 32, i)] = W.keys[slot][i];
     }
 }
+// PCA segments of the first fast_skip ranked shapes, once per block; K:2181-2186
+ITW_HD void bc6_phase_fits(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    const int count = P.fast_skip;
+    for (int t = lane; t < W.nvalid * count; t += 32) {
+        const int slot = t / count, n = t - slot * count;
+        const int shape = W.order[slot][n] & 31;
+        float* ep = W.fit[slot][n];
+#pragma unroll
+        for (int i = 0; i < 16; i++) ep[i] = 0.0f;               // never-written slots read as zero (F6)
+        for (int j = 0; j < 2; j++) fit_segment(ep + 8 * j, W.px[slot], shape_mask(shape, j), 3, false);
+    }
+}
 ITW_HD void bc6_phase_candidates(int lane, Bc6Warp& W, const Bc6Params& P)
 {
     const int count = P.fast_skip, per = kBc6MaxTwo * count;
@@ -380,7 +395,7 @@ ITW_HD void bc6_phase_candidates(int lane, Bc6Warp& W, const Bc6Params& P)
         if (e >= W.ntwo[slot]) continue;
         int q[16];
         u32 i0, i1;
-        W.cand_err[slot][e][n] = bc6_eval_two_region(W.px[slot], W.two[slot][e], W.order[slot][n] & 31, q, i0, i1);
+        W.cand_err[slot][e][n] = bc6_eval_two_region(W.px[slot], W.two[slot][e], W.order[slot][n] & 31, W.fit[slot][n], q, i0, i1);
     }
 }
 ITW_HD void bc6_phase_winners(int lane, Bc6Warp& W, const Bc6Params& P)
@@ -437,6 +452,7 @@ ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_
     if (P.slow_mode || P.fast_skip > 0) {                                  \
         PHASE(bc6_phase_keys(lane, W));                                    \
         PHASE(bc6_phase_rank(lane, W));                                    \
+        PHASE(bc6_phase_fits(lane, W, P));                                 \
         PHASE(bc6_phase_candidates(lane, W, P));                           \
         PHASE(bc6_phase_winners(lane, W, P));                              \
         PHASE(bc6_phase_chain_two(lane, W, P));                            \
@@ -445,21 +461,26 @@ ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_
     PHASE(bc6_phase_store(lane, W, dst, first_block));
 
 #if defined(__CUDACC__)
-constexpr int kBc6WarpsPerCta = 4;
+// Lock-step phases over one 16-warp CTA per SM, for instruction-cache locality (see bc7.cuh).
+constexpr int kBc6WarpsPerCta = 16;
+constexpr size_t kBc6SmemBytes = sizeof(Bc6Warp) * kBc6WarpsPerCta;
 
-__global__ void __launch_bounds__(kBc6WarpsPerCta * 32)
+__global__ void __launch_bounds__(kBc6WarpsPerCta * 32, 1)
 bc6h_kernel(SurfaceView surf, uint8_t* __restrict__ dst, Bc6Params P, long long nblocks)
 {
-    __shared__ Bc6Warp warps[kBc6WarpsPerCta];
-    Bc6Warp& W = warps[threadIdx.x >> 5];
+    extern __shared__ __align__(16) unsigned char bc6_smem[];
+    Bc6Warp& W = reinterpret_cast<Bc6Warp*>(bc6_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const long long nbatches = (nblocks + kBc6Slots - 1) / kBc6Slots;
     const long long warp0 = (long long)blockIdx.x * kBc6WarpsPerCta + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kBc6WarpsPerCta;
-    for (long long batch = warp0; batch < nbatches; batch += nwarps) {
+    const long long rounds = (nbatches + nwarps - 1) / nwarps;
+    for (long long round = 0; round < rounds; round++) {
+        const long long batch = warp0 + round * nwarps;
         const long long first_block = batch * kBc6Slots;
-        const int nvalid = (int)((nblocks - first_block < kBc6Slots) ? (nblocks - first_block) : kBc6Slots);
-#define ITW_PHASE_DEVICE(call) call; __syncwarp()
+        const long long left = nblocks - first_block;
+        const int nvalid = (int)(left <= 0 ? 0 : (left < kBc6Slots ? left : kBc6Slots));
+#define ITW_PHASE_DEVICE(call) call; __syncthreads()
         ITW_BC6_PROGRAM(ITW_PHASE_DEVICE)
 #undef ITW_PHASE_DEVICE
     }

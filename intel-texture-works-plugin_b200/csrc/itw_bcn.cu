@@ -153,11 +153,10 @@ int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* setting
             if (!settings) return fail("CompressBlocksBC6H: null settings");
             const Bc6Params P = bc6_params_from(*static_cast<const bc6h_enc_settings*>(settings));
             if (const char* why = bc6_params_check(P)) return fail(why);
-            int occ = 1;
-            ITW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bc6h_kernel, kBc6WarpsPerCta * 32, 0));
+            ITW_CUDA(cudaFuncSetAttribute(bc6h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc6SmemBytes));
             const long long want = (nblocks + kBc6Slots * kBc6WarpsPerCta - 1) / (kBc6Slots * kBc6WarpsPerCta);
-            const long long cap = (long long)tls.sm_count * (occ > 0 ? occ : 1);
-            bc6h_kernel<<<(unsigned)(want < cap ? want : cap), kBc6WarpsPerCta * 32, 0, stream>>>(v, d_dst, P, nblocks);
+            const long long cap = (long long)tls.sm_count;
+            bc6h_kernel<<<(unsigned)(want < cap ? want : cap), kBc6WarpsPerCta * 32, kBc6SmemBytes, stream>>>(v, d_dst, P, nblocks);
             break;
         }
         default: return fail("unknown format");
