@@ -19,7 +19,7 @@ struct Bc6Params {
     int slow_mode, fast_mode, refine_1p, refine_2p, fast_skip;
 };
 
-constexpr int kBc6Slots = 2;
+constexpr int kBc6Slots = 3;
 constexpr int kBc6MaxTwo = 6;    // two-region modes tried per block
 constexpr int kBc6MaxOne = 4;    // one-region modes tried per block
 
@@ -36,6 +36,8 @@ struct Bc6Warp {
     int max_span_idx[kBc6Slots];
     int keys[kBc6Slots][32], order[kBc6Slots][32];
     Bc6Entry two[kBc6Slots][kBc6MaxTwo], one[kBc6Slots][kBc6MaxOne];
+    Bc6Entry tmp[kBc6Slots][10];                  // the ten base modes, filled in parallel by the setup phase
+    int tmp_fits[kBc6Slots][10];                  // 1 if the mode's span test passed under the profile's margin
     int ntwo[kBc6Slots], none[kBc6Slots];
     float fit[kBc6Slots][32][16];                 // unquantised segments of ranked shape n: [subset][A rgb., B rgb.]
     float cand_err[kBc6Slots][kBc6MaxTwo][32];
@@ -111,7 +113,7 @@ ITW_HD void bc6_quant_dequant(const Bc6Entry& E, int* q, float* ep, int pairs)
 ITW_HD_NOINLINE bool bc6_make_entry(Bc6Entry& E, const Bc6Warp& W, int slot, int mode, float margin)
 {
     const float span = bc6_span(mode);
-    if (W.max_span[slot] * margin > span) return false;
+    const bool fits = !(W.max_span[slot] * margin > span);     // the entry is filled either way (mode 1 is also used untested, K:3098)
     const bool wide = !(mode >= 10 || mode <= 1 || mode == 5 || mode == 9);
     const int widx = W.max_span_idx[slot];
     E.epb = bc6_epb(mode);
@@ -128,7 +130,7 @@ ITW_HD_NOINLINE bool bc6_make_entry(Bc6Entry& E, const Bc6Warp& W, int slot, int
     bounds[3] = bounds[7] = 0.0f;                               // never-written slots read as zero (F6, Q2)
 #pragma unroll
     for (int i = 0; i < 8; i++) E.qbounds[i] = bc6_quant1(bounds[i], E.epb);
-    return true;
+    return fits;
 }
 
 // ---- header layouts -------------------------------------------------------------------------
@@ -209,78 +211,142 @@ ITW_HD_NOINLINE void bc6_put_header(BitSink& s, const int* q, int mode)
     }
 }
 
-// ---- candidate / chains; K:2174-2300, :2982-3031 ----
-// Quantise a stored (mode-independent) fit for entry E and run the index search; K:2188-2191
-ITW_HD_NOINLINE float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, const float* fit, int* q, u32& idx0, u32& idx1)
+// ---- index search, three channels, decoded endpoints are integers 0..65535; K:1133-1193 ----
+// dq = decoded endpoints [subset][A r,g,b,-, B r,g,b,-].  The two palette entries are computed with
+// integer arithmetic: (64-w)*a + w*b + 32 < 2^23 is exact in the reference's float evaluation and its
+// (int) cast is a floor, so the integer shift gives the same value.  Everything that involves the
+// (non-integer) texels stays in float, in the reference's order, with the x86 conversion rule.
+ITW_HD_NOINLINE float bc6_assign(u32* idx, const float* px, int bits, const int* dq, u32 pattern)
 {
+    const int levels = 1 << bits;
+    const float flevels = (float)levels;
+    int ea[2][3], eb[2][3];
+    float div[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        float d2 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            ea[j][c] = dq[8 * j + c];
+            eb[j][c] = dq[8 * j + 4 + c];
+            d2 += sq((float)(eb[j][c] - ea[j][c]));          // K:1155; the difference of two exact integers is exact
+        }
+        div[j] = d2;
+    }
+    float total = 0.0f;
+    u32 out0 = 0u, out1 = 0u;
+#pragma unroll 2
+    for (int k = 0; k < 16; k++) {
+        const bool second = ((pattern >> (2 * k)) & 3u) != 0u;
+        int a[3], b[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { a[c] = second ? ea[1][c] : ea[0][c]; b[c] = second ? eb[1][c] : eb[0][c]; }
+        float t[3], proj = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            t[c] = px[16 * c + k];
+            proj += (t[c] - (float)a[c]) * (float)(b[c] - a[c]);
+        }
+        proj /= (second ? div[1] : div[0]);
+        const int q1 = clampi(cvt_x86(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);   // proj*levels is exact
+        const int w0 = bc7_weight(bits, q1 - 1), w1 = bc7_weight(bits, q1);
+        float err0 = 0.0f, err1 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float d0 = (float)(((64 - w0) * a[c] + w0 * b[c] + 32) >> 6);
+            const float d1 = (float)(((64 - w1) * a[c] + w1 * b[c] + 32) >> 6);
+            err0 += sq(d0 - t[c]);
+            err1 += sq(d1 - t[c]);
+        }
+        const bool first = err0 < err1;
+        const int best_err = cvt_x86(first ? err0 : err1);                             // K:1178-1183 (quirk Q3)
+        const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
+        if (k < 8) out0 += bq; else out1 += bq;
+        total += (float)best_err;
+    }
+    idx[0] = out0;
+    idx[1] = out1;
+    return total;
+}
+// Quantise 8*pairs float endpoints for entry E (K:2139-2169): q = quantised, dq = decoded integers
+ITW_HD void bc6_quantise(const Bc6Entry& E, int* q, int* dq, const float* ep, int pairs)
+{
+    for (int i = 0; i < 2 * pairs; i++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int v = bc6_quant1(ep[4 * i + c], E.epb);
+            if (c < 3) v = clampi(v, E.qbounds[c], E.qbounds[4 + c]);
+            q[4 * i + c] = v;
+            dq[4 * i + c] = bc6_dequant(v, E.epb);
+        }
+    }
+}
+// One candidate of the two-region search: stored fit -> quantise for E -> index search; K:2188-2191
+ITW_HD_NOINLINE float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, const float* fit)
+{
+    int q[16], dq[16];
+    u32 idx[2];
+    bc6_quantise(E, q, dq, fit, 2);
+    return bc6_assign(idx, px, 3, dq, shape_pattern(shape));
+}
+
+// ---- the generic chain: initial candidate + refinement + encode of one (block, role) ----
+// roles 0..ntwo-1: two-region entries (K:2195-2255); then the one-region entries (K:2275-2300)
+ITW_HD_NOINLINE void bc6_chain(Bc6Warp& W, const Bc6Params& P, int slot, int r)
+{
+    const float* px = W.px[slot];
+    const bool two = r < W.ntwo[slot];
+    const Bc6Entry& E = two ? W.two[slot][r] : W.one[slot][r - W.ntwo[slot]];
+    const int pairs = two ? 2 : 1, bits = two ? 3 : 4;
+    int shape = 0;
     float ep[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) ep[i] = fit[i];
-    bc6_quant_dequant(E, q, ep, 2);
-    return assign_indices(idx0, idx1, px, 3, ep, shape_pattern(shape), 3);
-}
-ITW_HD_NOINLINE void bc6_chain_two_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
-{
-    W.res_err[slot][e] = inf_f();
-    const int pos = W.win_pos[slot][e];
-    if (pos < 0) return;
-    const float* px = W.px[slot];
-    const Bc6Entry& E = W.two[slot][e];
-    const int shape = W.order[slot][pos] & 31;
-    int best_q[16];
-    u32 best_i0, best_i1;
-    float best_err = bc6_eval_two_region(px, E, shape, W.fit[slot][pos], best_q, best_i0, best_i1);
-    for (int it = 0; it < P.refine_2p; it++) {
-        float ep[16];
+    for (int i = 0; i < 16; i++) ep[i] = 0.0f;
+    if (two) {
+        const int pos = W.win_pos[slot][r];
+        if (pos < 0) { W.res_err[slot][r] = inf_f(); return; }
+        shape = W.order[slot][pos] & 31;
+        for (int i = 0; i < 16; i++) ep[i] = W.fit[slot][pos][i];
+    } else {
+        fit_segment(ep, px, 0xFFFF, 3, false);
+    }
+    const u32 pattern = two ? shape_pattern(shape) : 0u;
+    int best_q[16], dq[16];
+    u32 best_idx[2];
+    bc6_quantise(E, best_q, dq, ep, pairs);
+    float best_err = bc6_assign(best_idx, px, bits, dq, pattern);
+
+    const int refine = two ? P.refine_2p : P.refine_1p;
+    for (int it = 0; it < refine; it++) {
         int q[16];
+        u32 idx[2];
 #pragma unroll
-        for (int i = 0; i < 16; i++) ep[i] = 0.0f;
-        for (int j = 0; j < 2; j++) solve_endpoints(ep + 8 * j, px, 3, best_i0, best_i1, shape_mask(shape, j), 3);
-        bc6_quant_dequant(E, q, ep, 2);
-        u32 i0, i1;
-        float err = assign_indices(i0, i1, px, 3, ep, shape_pattern(shape), 3);
-        if (err < best_err) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) best_q[i] = q[i];
-            best_i0 = i0; best_i1 = i1;
+        for (int i = 0; i < 16; i++) ep[i] = 0.0f;           // two-region: fresh array (F6); one-region: slots 3,7 hold decoded zeros
+        for (int j = 0; j < pairs; j++)
+            solve_endpoints(ep + 8 * j, px, bits, best_idx[0], best_idx[1], two ? shape_mask(shape, j) : 0xFFFF, 3);
+        bc6_quantise(E, q, dq, ep, pairs);
+        const float err = bc6_assign(idx, px, bits, dq, pattern);
+        // two-region keeps the best iterate (K:2242); one-region keeps the last (K:2288-2293)
+        if (!two || err < best_err) {
+            for (int i = 0; i < 8 * pairs; i++) best_q[i] = q[i];
+            best_idx[0] = idx[0]; best_idx[1] = idx[1];
             best_err = err;
         }
     }
-    W.res_err[slot][e] = best_err;
-    int flips = orient_subsets(best_q, best_i0, best_i1, 3, 2, shape);
+    W.res_err[slot][r] = best_err;
     BitSink s;
     s.reset();
-    bc6_put_header(s, best_q, E.mode);
-    s.put(5, (u32)shape);
-    put_indices(s, best_i0, best_i1, 3, flips, shape_anchor(shape, 1), -1);
-    u32* out = W.res_code[slot][e];
-    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
-}
-ITW_HD_NOINLINE void bc6_chain_one_region(Bc6Warp& W, const Bc6Params& P, int slot, int e)
-{
-    const float* px = W.px[slot];
-    const Bc6Entry& E = W.one[slot][e];
-    const int role = W.ntwo[slot] + e;
-    float ep[8];
-    int q[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) ep[i] = 0.0f;
-    fit_segment(ep, px, 0xFFFF, 3, false);
-    bc6_quant_dequant(E, q, ep, 1);
-    u32 i0, i1;
-    float err = assign_indices(i0, i1, px, 4, ep, 0u, 3);
-    for (int it = 0; it < P.refine_1p; it++) {
-        solve_endpoints(ep, px, 4, i0, i1, 0xFFFF, 3);
-        bc6_quant_dequant(E, q, ep, 1);
-        err = assign_indices(i0, i1, px, 4, ep, 0u, 3);
+    if (two) {                                                  // K:2982-3010
+        const int flips = orient_subsets(best_q, best_idx[0], best_idx[1], 3, 2, shape);
+        bc6_put_header(s, best_q, E.mode);
+        s.put(5, (u32)shape);
+        put_indices(s, best_idx[0], best_idx[1], 3, flips, shape_anchor(shape, 1), -1);
+    } else {                                                    // K:3012-3031
+        orient_single(best_q, 4, best_idx[0], best_idx[1], 4);
+        bc6_put_header(s, best_q, E.mode);
+        put_indices(s, best_idx[0], best_idx[1], 4, 0, -1, -1);
     }
-    W.res_err[slot][role] = err;
-    orient_single(q, 4, i0, i1, 4);
-    BitSink s;
-    s.reset();
-    bc6_put_header(s, q, E.mode);
-    put_indices(s, i0, i1, 4, 0, -1, -1);
-    u32* out = W.res_code[slot][role];
+    u32* out = W.res_code[slot][r];
     out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
 }
 
@@ -306,18 +372,21 @@ ITW_HD void bc6_phase_load(int lane, Bc6Warp& W, const SurfaceView& s, long long
     }
     if (lane == 0) W.nvalid = nvalid;
 }
-// per-block range, then the list of modes this block is encoded with; K:3036-3107
-ITW_HD void bc6_phase_setup(int lane, Bc6Warp& W, const Bc6Params& P)
+// per-block range; K:3036-3067
+ITW_HD void bc6_phase_range(int lane, Bc6Warp& W)
+{
+    for (int t = lane; t < W.nvalid * 3; t += 32) {
+        const int slot = t / 3, c = t - slot * 3;
+        const float* px = W.px[slot];
+        float lo = 65535.0f, hi = 0.0f;
+        for (int k = 0; k < 16; k++) { lo = min_sse(lo, px[16 * c + k]); hi = max_sse(hi, px[16 * c + k]); }
+        W.lo[slot][c] = lo;
+        W.hi[slot][c] = hi;
+    }
+}
+ITW_HD void bc6_phase_span(int lane, Bc6Warp& W)
 {
     for (int slot = lane; slot < W.nvalid; slot += 32) {
-        const float* px = W.px[slot];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float lo = 65535.0f, hi = 0.0f;
-            for (int k = 0; k < 16; k++) { lo = min_sse(lo, px[16 * c + k]); hi = max_sse(hi, px[16 * c + k]); }
-            W.lo[slot][c] = lo;
-            W.hi[slot][c] = hi;
-        }
         float max_span = 0.0f;
         int max_idx = 0;
 #pragma unroll
@@ -327,30 +396,53 @@ ITW_HD void bc6_phase_setup(int lane, Bc6Warp& W, const Bc6Params& P)
         }
         W.max_span[slot] = max_span;
         W.max_span_idx[slot] = max_idx;
-
+    }
+}
+// The ten base modes in the reference's order {0,1,2,5,6,9 | 10,11,12,13} and the margin each is tested with.
+ITW_HD int bc6_base_mode(int i) { return (i < 3) ? i : ((i == 3) ? 5 : ((i == 4) ? 6 : ((i == 5) ? 9 : i + 4))); }
+ITW_HD float bc6_margin(const Bc6Params& P, int i)
+{
+    if (P.slow_mode) return 0.0f;                               // K:3075-3084
+    const float m12 = 1.0f / 1.2f;                              // K:3090-3104
+    switch (i) {
+        case 0: return m12; case 1: return 1.0f; case 2: return 1.0f; case 3: return m12; case 4: return m12; case 5: return 0.0f;
+        case 6: return 0.0f; default: return 1.0f;
+    }
+}
+// lane <-> (block, base mode): span test + clamp window; K:2332-2365
+ITW_HD void bc6_phase_entries(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    for (int t = lane; t < W.nvalid * 10; t += 32) {
+        const int slot = t / 10, i = t - slot * 10;
+        W.tmp_fits[slot][i] = bc6_make_entry(W.tmp[slot][i], W, slot, bc6_base_mode(i), bc6_margin(P, i)) ? 1 : 0;
+    }
+}
+// the list of modes each block is encoded with; K:3069-3107
+ITW_HD void bc6_phase_select(int lane, Bc6Warp& W, const Bc6Params& P)
+{
+    for (int slot = lane; slot < W.nvalid; slot += 32) {
         int ntwo = 0, none = 0;
-        if (P.slow_mode) {                                       // every mode, margin 0; K:3073-3085
-            const int m2[6] = {0, 1, 2, 5, 6, 9};
+        if (P.slow_mode) {                                       // every mode whose (margin 0) test passes, in order
             for (int i = 0; i < 6; i++)
-                if (bc6_make_entry(W.two[slot][ntwo], W, slot, m2[i], 0.0f)) ntwo++;
-            for (int m = 10; m <= 13; m++)
-                if (bc6_make_entry(W.one[slot][none], W, slot, m, 0.0f)) none++;
-        } else {                                                 // the last mode whose span test passes; K:3086-3106
-            if (P.fast_skip > 0) {
-                const float m12 = 1.0f / 1.2f;
-                bc6_make_entry(W.two[slot][0], W, slot, 9, 0.0f);
-                if (P.fast_mode) bc6_make_entry(W.two[slot][0], W, slot, 1, 1.0f);
-                bc6_make_entry(W.two[slot][0], W, slot, 6, m12);
-                bc6_make_entry(W.two[slot][0], W, slot, 5, m12);
-                bc6_make_entry(W.two[slot][0], W, slot, 0, m12);
-                bc6_make_entry(W.two[slot][0], W, slot, 2, 1.0f);
+                if (W.tmp_fits[slot][i]) W.two[slot][ntwo++] = W.tmp[slot][i];
+            for (int i = 6; i < 10; i++)
+                if (W.tmp_fits[slot][i]) W.one[slot][none++] = W.tmp[slot][i];
+        } else {
+            if (P.fast_skip > 0) {                               // the LAST passing test of 9, [1], 6, 5, 0, 2 wins; K:3090-3095
+                int pick = 5;                                    // mode 9 (margin 0) always passes
+                if (P.fast_mode && W.tmp_fits[slot][1]) pick = 1;
+                if (W.tmp_fits[slot][4]) pick = 4;
+                if (W.tmp_fits[slot][3]) pick = 3;
+                if (W.tmp_fits[slot][0]) pick = 0;
+                if (W.tmp_fits[slot][2]) pick = 2;
+                W.two[slot][0] = W.tmp[slot][pick];
                 ntwo = 1;
-                if (!P.fast_mode && bc6_make_entry(W.two[slot][1], W, slot, 1, 0.0f)) ntwo = 2;
+                if (!P.fast_mode) { W.two[slot][1] = W.tmp[slot][1]; ntwo = 2; }     // mode 1 with margin 0; K:3098
             }
-            bc6_make_entry(W.one[slot][0], W, slot, 10, 0.0f);
-            bc6_make_entry(W.one[slot][0], W, slot, 11, 1.0f);
-            bc6_make_entry(W.one[slot][0], W, slot, 12, 1.0f);
-            bc6_make_entry(W.one[slot][0], W, slot, 13, 1.0f);
+            int pick = 6;                                        // 10, then 11, 12, 13 if they fit; K:3101-3105
+            for (int i = 7; i < 10; i++)
+                if (W.tmp_fits[slot][i]) pick = i;
+            W.one[slot][0] = W.tmp[slot][pick];
             none = 1;
         }
         W.ntwo[slot] = ntwo;
@@ -393,9 +485,7 @@ ITW_HD void bc6_phase_candidates(int lane, Bc6Warp& W, const Bc6Params& P)
         const int slot = t / per, r = t - slot * per;
         const int e = r / count, n = r - e * count;
         if (e >= W.ntwo[slot]) continue;
-        int q[16];
-        u32 i0, i1;
-        W.cand_err[slot][e][n] = bc6_eval_two_region(W.px[slot], W.two[slot][e], W.order[slot][n] & 31, W.fit[slot][n], q, i0, i1);
+        W.cand_err[slot][e][n] = bc6_eval_two_region(W.px[slot], W.two[slot][e], W.order[slot][n] & 31, W.fit[slot][n]);
     }
 }
 ITW_HD void bc6_phase_winners(int lane, Bc6Warp& W, const Bc6Params& P)
@@ -412,18 +502,12 @@ ITW_HD void bc6_phase_winners(int lane, Bc6Warp& W, const Bc6Params& P)
         W.win_pos[slot][e] = best;
     }
 }
-ITW_HD void bc6_phase_chain_two(int lane, Bc6Warp& W, const Bc6Params& P)
+ITW_HD void bc6_phase_chains(int lane, Bc6Warp& W, const Bc6Params& P)
 {
-    for (int t = lane; t < W.nvalid * kBc6MaxTwo; t += 32) {
-        const int slot = t / kBc6MaxTwo, e = t - slot * kBc6MaxTwo;
-        if (e < W.ntwo[slot]) bc6_chain_two_region(W, P, slot, e);
-    }
-}
-ITW_HD void bc6_phase_chain_one(int lane, Bc6Warp& W, const Bc6Params& P)
-{
-    for (int t = lane; t < W.nvalid * kBc6MaxOne; t += 32) {
-        const int slot = t / kBc6MaxOne, e = t - slot * kBc6MaxOne;
-        if (e < W.none[slot]) bc6_chain_one_region(W, P, slot, e);
+    const int per = kBc6MaxTwo + kBc6MaxOne;
+    for (int t = lane; t < W.nvalid * per; t += 32) {
+        const int slot = t / per, r = t - slot * per;
+        if (r < W.ntwo[slot] + W.none[slot]) bc6_chain(W, P, slot, r);
     }
 }
 ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_block)
@@ -448,16 +532,18 @@ ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_
 
 #define ITW_BC6_PROGRAM(PHASE)                                             \
     PHASE(bc6_phase_load(lane, W, surf, first_block, nvalid));             \
-    PHASE(bc6_phase_setup(lane, W, P));                                    \
-    if (P.slow_mode || P.fast_skip > 0) {                                  \
+    PHASE(bc6_phase_range(lane, W));                                       \
+    PHASE(bc6_phase_span(lane, W));                                        \
+    PHASE(bc6_phase_entries(lane, W, P));                                  \
+    PHASE(bc6_phase_select(lane, W, P));                                   \
+    if (P.fast_skip > 0) {                                                 \
         PHASE(bc6_phase_keys(lane, W));                                    \
         PHASE(bc6_phase_rank(lane, W));                                    \
         PHASE(bc6_phase_fits(lane, W, P));                                 \
         PHASE(bc6_phase_candidates(lane, W, P));                           \
-        PHASE(bc6_phase_winners(lane, W, P));                              \
-        PHASE(bc6_phase_chain_two(lane, W, P));                            \
     }                                                                      \
-    PHASE(bc6_phase_chain_one(lane, W, P));                                \
+    PHASE(bc6_phase_winners(lane, W, P));                                  \
+    PHASE(bc6_phase_chains(lane, W, P));                                   \
     PHASE(bc6_phase_store(lane, W, dst, first_block));
 
 #if defined(__CUDACC__)
