@@ -324,6 +324,9 @@ ITW_HD_NOINLINE void bc7_quantise(u32* out, const float* ep, int mode, int chann
     // so the x86 overflow rule of cvt_x86() can never trigger and a plain truncation is identical.
     // t*0.5 and (t-1)*0.5 are exact (power-of-two scaling), so fusing the +0.5 rounds once, exactly like
     // the reference's separate multiply and add.
+    // Modes 0-3 never emit a 4th component and their index search ignores it; it only matters when it votes
+    // (alpha profiles refining modes 0/3, quirk Q1).  Otherwise it is skipped (its byte stays 0).
+    const int ncomp = (mode <= 3 && votes <= 3) ? 3 : 4;
     u32 cand0[2] = {0u, 0u}, cand1[2] = {0u, 0u};
     bool pick1[2] = {false, false};
     float e0 = 0.0f, e1 = 0.0f;
@@ -333,6 +336,7 @@ ITW_HD_NOINLINE void bc7_quantise(u32* out, const float* ep, int mode, int chann
         u32 c0 = 0u, c1 = 0u;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
+            if (c >= ncomp) continue;
             const float x = ep[4 * i + c];
             const float t = div255(x) * ftop;
             int v0, v1;
@@ -572,53 +576,59 @@ ITW_HD void bc7_write_mode6(u32* out, u32 qa, u32 qb, u32 i0, u32 i1)
 // ---------------------------------------------------------------------------------------------
 // scalar channel of modes 4/5; K:1437-1563.  `a` = byte `shift/8` of the ORIGINAL texels.
 // ---------------------------------------------------------------------------------------------
-ITW_HD float scalar_texel(const Bc7Block* blk, int k, int shift) { return (float)((blk->tex[k] >> shift) & 255u); }
-ITW_HD void scalar_quantise(int (&q)[2], float (&ep)[2], int epbits)
+// After quantisation the two endpoints are integers, the texels are integers and the weights are
+// integers, so the index search and the least-squares sums are exact integer arithmetic; the projection
+// (x - e0)/(e1 - e0 + 0.001f) keeps the reference's float expression (K:1510) with the exact quotient
+// (domain proved in tests/test_exact_division.py).
+ITW_HD int scalar_texel(const Bc7Block* blk, int k, int shift) { return (int)((blk->tex[k] >> shift) & 255u); }
+ITW_HD void scalar_quantise(int (&q)[2], int (&e)[2], const float (&ep)[2], int epbits)
 {
     const int top = (1 << epbits) - 1;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        q[i] = clampi(cvt_x86(ep[i] / 255.0f * (float)top + 0.5f), 0, top);
-        ep[i] = (float)expand_bits(q[i], epbits);
+        q[i] = clampi(trunc_i(div255(ep[i]) * (float)top + 0.5f), 0, top);   // ep in [0,255]: no overflow
+        e[i] = expand_bits(q[i], epbits);
     }
 }
-ITW_HD float scalar_assign(u32& idx0, u32& idx1, const Bc7Block* blk, int shift, int bits, const float (&ep)[2])
+ITW_HD int scalar_assign(u32& idx0, u32& idx1, const Bc7Block* blk, int shift, int bits, const int (&e)[2])
 {
     const int levels = 1 << bits;
-    u32 out[2] = {0u, 0u};
-    float total = 0.0f;
+    const float flevels = (float)levels;
+    const float den = (float)(e[1] - e[0]) + 0.001f, rden = 1.0f / den;
+    u32 out0 = 0u, out1 = 0u;
+    int total = 0;
 #pragma unroll 1
     for (int k = 0; k < 16; k++) {
-        const float a = scalar_texel(blk, k, shift);
-        float proj = (a - ep[0]) / (ep[1] - ep[0] + 0.001f);
-        int q1 = clampi(cvt_x86(proj * (float)levels + 0.5f), 1, levels - 1);
-        float fw0 = (float)bc7_weight(bits, q1 - 1), fw1 = (float)bc7_weight(bits, q1);
-        float d0 = (float)cvt_x86(((64.0f - fw0) * ep[0] + fw0 * ep[1] + 32.0f) / 64.0f);
-        float d1 = (float)cvt_x86(((64.0f - fw1) * ep[0] + fw1 * ep[1] + 32.0f) / 64.0f);
-        float err0 = sq(d0 - a), err1 = sq(d1 - a);
-        int best_err = cvt_x86(err1), best_q = q1;
-        if (err0 < err1) { best_err = cvt_x86(err0); best_q = q1 - 1; }
-        out[k >> 3] += (u32)best_q << (4 * (k & 7));
-        total += (float)best_err;
+        const int a = scalar_texel(blk, k, shift);
+        const float proj = div_by_rcp((float)(a - e[0]), den, rden);
+        const int q1 = clampi(trunc_i(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);
+        const int w0 = bc7_weight(bits, q1 - 1), w1 = bc7_weight(bits, q1);
+        const int d0 = (((64 - w0) * e[0] + w0 * e[1] + 32) >> 6) - a;
+        const int d1 = (((64 - w1) * e[0] + w1 * e[1] + 32) >> 6) - a;
+        const int err0 = d0 * d0, err1 = d1 * d1;
+        const bool first = err0 < err1;
+        total += first ? err0 : err1;
+        const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
+        if (k < 8) out0 += bq; else out1 += bq;
     }
-    idx0 = out[0];
-    idx1 = out[1];
+    idx0 = out0;
+    idx1 = out1;
     return total;
 }
 ITW_HD void scalar_solve(float (&ep)[2], const Bc7Block* blk, int shift, int bits, u32 idx0, u32 idx1)
 {
-    const float top = (float)((1 << bits) - 1);
-    float atb1 = 0.0f, sq1 = 0.0f, sqq = 0.0f, sum = 0.0f;
+    const int itop = (1 << bits) - 1;
+    int iatb1 = 0, isq1 = 0, isqq = 0, isum = 0;
 #pragma unroll 1
     for (int k = 0; k < 16; k++) {
-        const float a = scalar_texel(blk, k, shift);
-        float q = (float)(((k < 8 ? idx0 : idx1) >> (4 * (k & 7))) & 15u);
-        float x = (float)cvt_x86(top - q);
-        sq1 += q;
-        sqq += q * q;
-        sum += a;
-        atb1 += x * a;
+        const int a = scalar_texel(blk, k, shift);
+        const int q = (int)(((k < 8 ? idx0 : idx1) >> (4 * (k & 7))) & 15u);
+        isq1 += q;
+        isqq += q * q;
+        isum += a;
+        iatb1 += (itop - q) * a;
     }
+    const float top = (float)itop, atb1 = (float)iatb1, sq1 = (float)isq1, sqq = (float)isqq, sum = (float)isum;
     float atb2 = top * sum - atb1;
     float cxx = 16.0f * sq(top) - (2.0f * top) * sq1 + sqq;
     float cyy = sqq;
@@ -635,26 +645,27 @@ ITW_HD void scalar_solve(float (&ep)[2], const Bc7Block* blk, int shift, int bit
 ITW_HD_NOINLINE int bc7_scalar_channel(int* aq, u32* aidx, const Bc7Block* blk, int rotation, int abits, int aepbits, int rch)
 {
     const int shift = 8 * rotation;
-    float ep[2] = {255.0f, 0.0f};
+    int lo = 255, hi = 0;                                        // K:1542-1548
 #pragma unroll 1
     for (int k = 0; k < 16; k++) {
-        const float a = scalar_texel(blk, k, shift);
-        ep[0] = min_sse(ep[0], a);
-        ep[1] = max_sse(ep[1], a);
+        const int a = scalar_texel(blk, k, shift);
+        lo = mini(lo, a);
+        hi = maxi(hi, a);
     }
-    int q[2];
+    float ep[2] = {(float)lo, (float)hi};
+    int q[2], e[2];
     u32 a0, a1;
-    scalar_quantise(q, ep, aepbits);
-    float err = scalar_assign(a0, a1, blk, shift, abits, ep);
+    scalar_quantise(q, e, ep, aepbits);
+    int err = scalar_assign(a0, a1, blk, shift, abits, e);
 #pragma unroll 1
     for (int it = 0; it < rch; it++) {
         scalar_solve(ep, blk, shift, abits, a0, a1);
-        scalar_quantise(q, ep, aepbits);
-        err = scalar_assign(a0, a1, blk, shift, abits, ep);
+        scalar_quantise(q, e, ep, aepbits);
+        err = scalar_assign(a0, a1, blk, shift, abits, e);
     }
     aq[0] = q[0]; aq[1] = q[1];
     aidx[0] = a0; aidx[1] = a1;
-    return (int)err;                                            // exact: a sum of 16 truncated integers
+    return err;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -842,9 +853,14 @@ ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, i
 ITW_HD void bc7_phase_shapes(int lane, Bc7Warp& W, const Bc7Params& P, int ma, int mb)
 {
     const int ca = bc7_slot_count(P, ma), cb = (mb != ma) ? bc7_slot_count(P, mb) : 0;
-    const int count = maxi(ca, cb);
-    for (int t = lane; t < W.nvalid * count; t += 32) {
-        const int slot = t / count, n = t - slot * count;
+    const int both = mini(ca, cb), count = maxi(ca, cb);
+    // list positions [0, both) run both modes, [both, count) only the longer list's mode; tasks are ordered
+    // so that the "both" positions of all blocks come first and a warp never mixes the two kinds
+    const int nboth = W.nvalid * both, nall = W.nvalid * count;
+    for (int t = lane; t < nall; t += 32) {
+        int slot, n;
+        if (t < nboth) { slot = t / both; n = t - slot * both; }
+        else { const int u = t - nboth, rest = count - both; slot = u / rest; n = both + (u - slot * rest); }
         bc7_eval_shape(W, lane, slot, bc7_slot_shape(W, slot, ma, n), n, ma, n < ca, mb, n < cb);
     }
 }

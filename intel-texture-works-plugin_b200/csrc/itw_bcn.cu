@@ -183,8 +183,11 @@ int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* se
     SurfaceView v{src->ptr, src->width, src->height, src->stride};
     if (!src_dev) {                      // H2D of the tightly packed rows (pinned sources copy at PCIe rate)
         if (grow(c.d_in, c.d_in_cap, row_bytes * src->height)) return -1;
-        ITW_CUDA(cudaMemcpy2DAsync(c.d_in, row_bytes, src->ptr, (size_t)src->stride, row_bytes, (size_t)src->height,
-                                   cudaMemcpyHostToDevice, c.stream));
+        if ((size_t)src->stride == row_bytes)   // tightly packed rows: one linear copy (full PCIe rate from pinned memory)
+            ITW_CUDA(cudaMemcpyAsync(c.d_in, src->ptr, row_bytes * src->height, cudaMemcpyHostToDevice, c.stream));
+        else
+            ITW_CUDA(cudaMemcpy2DAsync(c.d_in, row_bytes, src->ptr, (size_t)src->stride, row_bytes, (size_t)src->height,
+                                       cudaMemcpyHostToDevice, c.stream));
         v.ptr = c.d_in;
         v.stride = (int)row_bytes;
     }

@@ -42,6 +42,13 @@ int main(void) {
         bad += b2;
     }
     printf("proj %lld\n", bad);
+    /* (4) scalar channel of BC7 modes 4/5: integer x in [-255,255] by (n + 0.001f), n in [-255,255] */
+    bad = 0;
+    for (int n = -255; n <= 255; n++) {
+        float d = (float)n + 0.001f, r = 1.0f / d;
+        for (int x = -255; x <= 255; x++) bad += ((float)x / d != dq((float)x, d, r));
+    }
+    printf("scalar %lld\n", bad);
     return 0;
 }
 """
@@ -54,4 +61,4 @@ def test_fma_corrected_quotient_is_exact_on_every_domain_it_is_used_on():
         open(c, "w").write(SRC)
         subprocess.check_call(["gcc", "-O3", "-fopenmp", "-mavx2", "-mfma", "-ffp-contract=off", c, "-o", exe, "-lm"])
         out = subprocess.check_output([exe], text=True).split()
-    assert out == ["div255", "0", "count", "0", "proj", "0"], out
+    assert out == ["div255", "0", "count", "0", "proj", "0", "scalar", "0"], out
