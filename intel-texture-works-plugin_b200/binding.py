@@ -136,6 +136,18 @@ class ItwBcn(EncoderApi):
     def last_kernel_ms(self):
         return float(self.lib.itw_last_kernel_ms())
 
+    def encode_batch(self, fmt, surfaces, dst_ptrs, settings=None):
+        """itw_encode_batch: `surfaces` = list of (ptr, width, height, stride), `dst_ptrs` = list of addresses."""
+        n = len(surfaces)
+        arr = (RgbaSurface * n)(*[RgbaSurface(*s) for s in surfaces])
+        dst = (ctypes.c_void_p * n)(*dst_ptrs)
+        sp = ctypes.cast(ctypes.byref(settings), ctypes.c_void_p) if settings is not None else None
+        self.lib.itw_encode_batch.argtypes = [ctypes.c_int, ctypes.POINTER(RgbaSurface), ctypes.POINTER(ctypes.c_void_p),
+                                              ctypes.c_int, ctypes.c_void_p]
+        if self.lib.itw_encode_batch(FORMATS[fmt][0], arr, dst, n, sp) != 0:
+            self.check()
+            raise RuntimeError("itw_encode_batch failed")
+
     def encode_device(self, fmt, ptr, width, height, stride, dst_ptr, settings=None, stream=0):
         """Enqueue the encode of a device-resident surface on a CUDA stream (no copies, no sync)."""
         surf = RgbaSurface(ptr, width, height, stride)

@@ -53,7 +53,7 @@ struct Bc7Warp {
     Bc7Block blk[kBc7Slots];
     int cand_err[kBc7Slots][2][64];            // errors of the mode-slot pair being evaluated: [first/second][list position]
     int keys[kBc7Slots][64];                   // split-bound keys of the set being ranked (scratch)
-    int order[kBc7Slots][2][64];               // keys in ascending order: [0] RGB (modes 1,3), [1] profile channels (mode 7)
+    uint8_t order[kBc7Slots][2][64];           // shapes in ascending key order: [0] RGB (modes 1,3), [1] profile channels (mode 7)
     int win_pos[kBc7Slots][5];                 // winning list position per mode slot, -1 = none
     int res_err[kBc7Slots][kBc7MaxRoles];
     u32 res_code[kBc7Slots][kBc7MaxRoles][4];
@@ -882,7 +882,7 @@ ITW_HD void bc7_phase_rank(int lane, Bc7Warp& W, int set)
 {
     for (int t = lane; t < W.nvalid * 64; t += 32) {
         const int slot = t >> 6, i = t & 63;
-        W.order[slot][set][rank_of(W.keys[slot], 64, i)] = W.keys[slot][i];
+        W.order[slot][set][rank_of(W.keys[slot], 64, i)] = (uint8_t)(W.keys[slot][i] & 63);
     }
 }
 // first minimum of the candidate lists just evaluated for mode slots (ma, mb); K:1320 (strict <)

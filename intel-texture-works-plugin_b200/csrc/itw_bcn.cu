@@ -35,6 +35,14 @@ struct ThreadCtx {
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     int sm_count = 0;
     std::string err;
+    // itw_encode_batch: three copy/compute lanes so that H2D of tile i+1, the kernel of tile i and
+    // D2H of tile i-1 overlap (tile streaming)
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        uint8_t* d_in = nullptr;  size_t d_in_cap = 0;
+        uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+        bool busy = false;
+    } lanes[3];
 };
 thread_local ThreadCtx tls;
 
@@ -66,6 +74,7 @@ int ensure_ctx()
     if (c.stream) {                       // device changed: drop the old resources
         cudaStreamDestroy(c.stream); cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
         cudaFree(c.d_in); cudaFree(c.d_out);
+        for (auto& l : c.lanes) { if (l.stream) cudaStreamDestroy(l.stream); cudaFree(l.d_in); cudaFree(l.d_out); }
         c = ThreadCtx();
         c.wanted_device = dev;
     }
@@ -260,9 +269,60 @@ int itw_encode_device(int format, const rgba_surface* src, uint8_t* dst, const v
 
 int itw_encode_batch(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings)
 {
-    for (int i = 0; i < count; i++)
-        if (encode_any(format, &srcs[i], dsts[i], settings)) return -1;
-    return 0;
+    tls.err.clear();
+    FormatInfo f;
+    if (!format_info(format, f)) return fail("unknown format");
+    if (count < 0 || (count > 0 && (!srcs || !dsts))) return fail("itw_encode_batch: bad arguments");
+    if (ensure_ctx()) return -1;
+    ThreadCtx& c = tls;
+    int rc = 0;
+    for (int i = 0; i < count && rc == 0; i++) {
+        const rgba_surface* src = &srcs[i];
+        uint8_t* dst = dsts[i];
+        if (check_surface(src, f)) { rc = -1; break; }
+        if (!dst) { rc = fail("null dst"); break; }
+        ThreadCtx::Lane& L = c.lanes[i % 3];
+        if (!L.stream && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate"); break; }
+        if (L.busy) {                                  // its buffers are still in flight from tile i-3
+            if (cudaStreamSynchronize(L.stream) != cudaSuccess) { rc = fail("cudaStreamSynchronize"); break; }
+            L.busy = false;
+        }
+        const size_t row_bytes = (size_t)src->width * f.texel_bytes;
+        const size_t out_bytes = (size_t)(src->width >> 2) * (src->height >> 2) * f.bpb;
+        const bool src_dev = is_device_pointer(src->ptr), dst_dev = is_device_pointer(dst);
+        SurfaceView v{src->ptr, src->width, src->height, src->stride};
+        cudaError_t e = cudaSuccess;
+        if (!src_dev) {
+            if (grow(L.d_in, L.d_in_cap, row_bytes * src->height)) { rc = -1; break; }
+            if ((size_t)src->stride == row_bytes)
+                e = cudaMemcpyAsync(L.d_in, src->ptr, row_bytes * src->height, cudaMemcpyHostToDevice, L.stream);
+            else
+                e = cudaMemcpy2DAsync(L.d_in, row_bytes, src->ptr, (size_t)src->stride, row_bytes, (size_t)src->height,
+                                      cudaMemcpyHostToDevice, L.stream);
+            if (e != cudaSuccess) { rc = fail("itw_encode_batch H2D", e); break; }
+            v.ptr = L.d_in;
+            v.stride = (int)row_bytes;
+        }
+        uint8_t* d_dst = dst;
+        const bool dst_ok = dst_dev && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+        if (!dst_ok) {
+            if (grow(L.d_out, L.d_out_cap, out_bytes)) { rc = -1; break; }
+            d_dst = L.d_out;
+        }
+        if (launch(format, v, d_dst, settings, L.stream)) { rc = -1; break; }
+        if (!dst_ok) {
+            e = cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, L.stream);
+            if (e != cudaSuccess) { rc = fail("itw_encode_batch D2H", e); break; }
+        }
+        L.busy = true;
+    }
+    for (auto& L : c.lanes)                           // always drain, also on error
+        if (L.busy) {
+            if (cudaStreamSynchronize(L.stream) != cudaSuccess && rc == 0) rc = fail("cudaStreamSynchronize");
+            L.busy = false;
+        }
+    tls.timed = false;
+    return rc;
 }
 
 int itw_set_device(int device)

@@ -153,3 +153,32 @@ def test_full_size_properties():
         want = T.run(oracle, fmt, np.ascontiguousarray(img[1000:1000 + rows]), prof)
         off = (1000 // 4) * (4096 // 4) * bpb
         assert np.array_equal(a[off:off + want.size], want)
+
+
+def test_batch_entry_streams_independent_tiles():
+    """itw_encode_batch (config C5's tile stream): results equal the one-at-a-time encodes, for pageable,
+    pinned and device-resident tiles, with tiles of different sizes in one batch."""
+    import torch
+    lib = T.product()
+    fmt, prof = "BC7", "veryfast"
+    settings = lib.profile(prof)
+    sizes = [(64, 64), (32, 128), (64, 64), (128, 32), (4, 4), (64, 64), (64, 64)]
+    tiles = [_rand_img(fmt, h, w, seed=200 + i) for i, (h, w) in enumerate(sizes)]
+    want = [lib.encode(fmt, t, settings) for t in tiles]
+    # pageable host memory
+    outs = [np.zeros_like(w) for w in want]
+    lib.encode_batch(fmt, [(t.ctypes.data, t.shape[1], t.shape[0], t.strides[0]) for t in tiles], [o.ctypes.data for o in outs], settings)
+    assert all(np.array_equal(o, w) for o, w in zip(outs, want))
+    # pinned host memory
+    pins = [torch.from_numpy(t.copy().reshape(-1)).pin_memory() for t in tiles]
+    pouts = [torch.zeros(w.size, dtype=torch.uint8).pin_memory() for w in want]
+    lib.encode_batch(fmt, [(p.data_ptr(), t.shape[1], t.shape[0], t.shape[1] * 4) for p, t in zip(pins, tiles)],
+                     [o.data_ptr() for o in pouts], settings)
+    assert all(np.array_equal(o.numpy(), w) for o, w in zip(pouts, want))
+    # device-resident
+    devs = [p.cuda() for p in pins]
+    douts = [torch.zeros(w.size, dtype=torch.uint8, device="cuda") for w in want]
+    lib.encode_batch(fmt, [(d.data_ptr(), t.shape[1], t.shape[0], t.shape[1] * 4) for d, t in zip(devs, tiles)],
+                     [o.data_ptr() for o in douts], settings)
+    torch.cuda.synchronize()
+    assert all(np.array_equal(o.cpu().numpy(), w) for o, w in zip(douts, want))

@@ -63,3 +63,40 @@ def test_row_sharded_mip_chain_equals_single_process(fmt, prof):
     ret = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), fmt, prof, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _gpu_worker(rank, world, port, ret):
+    import importlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        lib = T.product()
+        lib.set_device(rank)
+        fmt, bpb = "BC3", 16
+        chain = T.synth.mip_chain(T.synth.mixed_rgba8(256, 256))
+        dev = [torch.from_numpy(np.ascontiguousarray(l).reshape(-1)).cuda() for l in chain]
+
+        def encode_band(li, y0, y1):
+            h, w = chain[li].shape[:2]
+            out = torch.empty((w // 4) * ((y1 - y0) // 4) * bpb, dtype=torch.uint8, device="cuda")
+            lib.encode_device(fmt, dev[li].data_ptr() + y0 * w * 4, w, y1 - y0, w * 4, out.data_ptr(), None,
+                              torch.cuda.current_stream().cuda_stream)
+            return out
+
+        got = sharding.encode_levels_sharded([(l.shape[1], l.shape[0]) for l in chain], bpb, encode_band, device="cuda")
+        torch.cuda.synchronize()
+        want = [lib.encode(fmt, np.ascontiguousarray(l)) for l in chain]
+        ret[rank] = all(np.array_equal(g.cpu().numpy(), w) for g, w in zip(got, want))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_row_sharded_mip_chain_on_two_gpus_nccl():
+    """Config C4 in small: BC3 + full mip chain, row-sharded over 2 GPUs, one NCCL all-gather."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_gpu_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert all(ret.get(r) for r in range(2)), dict(ret)
