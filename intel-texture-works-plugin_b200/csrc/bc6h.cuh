@@ -532,6 +532,8 @@ ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_
 
 #define ITW_BC6_PROGRAM(PHASE)                                             \
     PHASE(bc6_phase_load(lane, W, surf, first_block, nvalid));             \
+    ITW_BC6_PROGRAM_AFTER_LOAD(PHASE)
+#define ITW_BC6_PROGRAM_AFTER_LOAD(PHASE)                                  \
     PHASE(bc6_phase_range(lane, W));                                       \
     PHASE(bc6_phase_span(lane, W));                                        \
     PHASE(bc6_phase_entries(lane, W, P));                                  \
@@ -547,27 +549,58 @@ ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_
     PHASE(bc6_phase_store(lane, W, dst, first_block));
 
 #if defined(__CUDACC__)
-// Lock-step phases over one 16-warp CTA per SM, for instruction-cache locality (see bc7.cuh).
+// Lock-step phases over one 16-warp CTA per SM, for instruction-cache locality, and (kTma) the round's 48
+// blocks fetched by the TMA engine into a double-buffered shared-memory tile -- see bc7.cuh.
 constexpr int kBc6WarpsPerCta = 16;
 constexpr size_t kBc6SmemBytes = sizeof(Bc6Warp) * kBc6WarpsPerCta;
+constexpr int kBc6TileBlocks = kBc6WarpsPerCta * kBc6Slots;              // 48
+constexpr int kBc6TileRowBytes = kBc6TileBlocks * 32;                     // 1536
 
+template <bool kTma>
 __global__ void __launch_bounds__(kBc6WarpsPerCta * 32, 1)
-bc6h_kernel(SurfaceView surf, uint8_t* __restrict__ dst, Bc6Params P, long long nblocks)
+bc6h_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc6Params P, long long nblocks)
 {
     extern __shared__ __align__(16) unsigned char bc6_smem[];
+    __shared__ __align__(128) unsigned char stage[kTma ? 2 : 1][kTma ? 4 * kBc6TileRowBytes : 16];
+    __shared__ __align__(8) unsigned long long full[2];
     Bc6Warp& W = reinterpret_cast<Bc6Warp*>(bc6_smem)[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nbatches = (nblocks + kBc6Slots - 1) / kBc6Slots;
-    const long long warp0 = (long long)blockIdx.x * kBc6WarpsPerCta + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kBc6WarpsPerCta;
     const long long rounds = (nbatches + nwarps - 1) / nwarps;
+
+    auto tile_first = [&](long long round) { return ((long long)blockIdx.x * kBc6WarpsPerCta + round * nwarps) * kBc6Slots; };
+    auto prefetch = [&](long long round) {
+        const long long fb = tile_first(round);
+        if (round >= rounds || fb >= nblocks) return;
+        const long long left = nblocks - fb;
+        tma_prefetch_tile(stage[round & 1], kBc6TileRowBytes, &full[round & 1], gsurf, fb,
+                          (int)(left < kBc6TileBlocks ? left : kBc6TileBlocks), 32);
+    };
+    if (kTma) {
+        if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+        __syncthreads();
+        if (threadIdx.x == 0) prefetch(0);
+    }
     for (long long round = 0; round < rounds; round++) {
-        const long long batch = warp0 + round * nwarps;
-        const long long first_block = batch * kBc6Slots;
+        const long long batch = (long long)blockIdx.x * kBc6WarpsPerCta + warp + round * nwarps;
+        long long first_block = batch * kBc6Slots;
         const long long left = nblocks - first_block;
         const int nvalid = (int)(left <= 0 ? 0 : (left < kBc6Slots ? left : kBc6Slots));
+        SurfaceView surf = gsurf;
+        const long long out_block = first_block;
+        if (kTma) {
+            if (threadIdx.x == 0) prefetch(round + 1);
+            if (tile_first(round) < nblocks) mbar_wait(&full[round & 1], (unsigned)((round >> 1) & 1));
+            surf = SurfaceView{stage[round & 1], kBc6TileBlocks * 4, 4, kBc6TileRowBytes};
+            first_block = (long long)warp * kBc6Slots;
+        }
 #define ITW_PHASE_DEVICE(call) call; __syncthreads()
-        ITW_BC6_PROGRAM(ITW_PHASE_DEVICE)
+        {
+            ITW_PHASE_DEVICE(bc6_phase_load(lane, W, surf, first_block, nvalid));
+            first_block = out_block;
+            ITW_BC6_PROGRAM_AFTER_LOAD(ITW_PHASE_DEVICE)
+        }
 #undef ITW_PHASE_DEVICE
     }
 }

@@ -930,6 +930,8 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
 // The whole program for one batch, as a list of (phase, barrier) pairs.
 #define ITW_BC7_PROGRAM(PHASE)                                                         \
     PHASE(bc7_phase_load(lane, W, surf, first_block, nvalid));                         \
+    ITW_BC7_PROGRAM_AFTER_LOAD(PHASE)
+#define ITW_BC7_PROGRAM_AFTER_LOAD(PHASE)                                              \
     PHASE(bc7_phase_planes(lane, W));                                                  \
     if (P.sel[0]) {                                                                    \
         PHASE(bc7_phase_shapes(lane, W, P, 0, 1));                                     \
@@ -959,23 +961,58 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
 constexpr int kBc7WarpsPerCta = 16;
 constexpr size_t kBc7SmemBytes = sizeof(Bc7Warp) * kBc7WarpsPerCta;
 
+// kTma: the 64 consecutive blocks a CTA works on in one round are fetched by the TMA engine
+// (cp.async.bulk, SASS UBLKCP) into a double-buffered 4-row shared-memory tile while the previous round is
+// being encoded, signalled through an mbarrier; the load phase then reads the tile from shared memory.
+// Needs 16-byte aligned surface rows; other surfaces use the plain global-load variant.
+constexpr int kBc7TileBlocks = kBc7WarpsPerCta * kBc7Slots;              // 64
+constexpr int kBc7TileRowBytes = kBc7TileBlocks * 16;                     // 1024
+
+template <bool kTma>
 __global__ void __launch_bounds__(kBc7WarpsPerCta * 32, 1)
-bc7_kernel(SurfaceView surf, uint8_t* __restrict__ dst, Bc7Params P, long long nblocks)
+bc7_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc7Params P, long long nblocks)
 {
     extern __shared__ __align__(16) unsigned char bc7_smem[];
+    __shared__ __align__(128) unsigned char stage[kTma ? 2 : 1][kTma ? 4 * kBc7TileRowBytes : 16];
+    __shared__ __align__(8) unsigned long long full[2];
     Bc7Warp& W = reinterpret_cast<Bc7Warp*>(bc7_smem)[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nbatches = (nblocks + kBc7Slots - 1) / kBc7Slots;
-    const long long warp0 = (long long)blockIdx.x * kBc7WarpsPerCta + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kBc7WarpsPerCta;
     const long long rounds = (nbatches + nwarps - 1) / nwarps;            // same trip count for every warp of the CTA
+
+    auto tile_first = [&](long long round) { return ((long long)blockIdx.x * kBc7WarpsPerCta + round * nwarps) * kBc7Slots; };
+    auto prefetch = [&](long long round) {                                // one thread feeds the TMA engine
+        const long long fb = tile_first(round);
+        if (round >= rounds || fb >= nblocks) return;
+        const long long left = nblocks - fb;
+        tma_prefetch_tile(stage[round & 1], kBc7TileRowBytes, &full[round & 1], gsurf, fb,
+                          (int)(left < kBc7TileBlocks ? left : kBc7TileBlocks), 16);
+    };
+    if (kTma) {
+        if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+        __syncthreads();
+        if (threadIdx.x == 0) prefetch(0);
+    }
     for (long long round = 0; round < rounds; round++) {
-        const long long batch = warp0 + round * nwarps;
-        const long long first_block = batch * kBc7Slots;
+        const long long batch = (long long)blockIdx.x * kBc7WarpsPerCta + warp + round * nwarps;
+        long long first_block = batch * kBc7Slots;
         const long long left = nblocks - first_block;
         const int nvalid = (int)(left <= 0 ? 0 : (left < kBc7Slots ? left : kBc7Slots));
+        SurfaceView surf = gsurf;
+        const long long out_block = first_block;
+        if (kTma) {
+            if (threadIdx.x == 0) prefetch(round + 1);                   // next tile streams in behind this round's math
+            if (tile_first(round) < nblocks) mbar_wait(&full[round & 1], (unsigned)((round >> 1) & 1));
+            surf = SurfaceView{stage[round & 1], kBc7TileBlocks * 4, 4, kBc7TileRowBytes};
+            first_block = (long long)warp * kBc7Slots;                   // block index inside the staged tile
+        }
 #define ITW_PHASE_DEVICE(call) call; __syncthreads()
-        ITW_BC7_PROGRAM(ITW_PHASE_DEVICE)
+        {
+            ITW_PHASE_DEVICE(bc7_phase_load(lane, W, surf, first_block, nvalid));
+            first_block = out_block;
+            ITW_BC7_PROGRAM_AFTER_LOAD(ITW_PHASE_DEVICE)
+        }
 #undef ITW_PHASE_DEVICE
     }
 }

@@ -150,22 +150,35 @@ int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* setting
             if (!settings) return fail("CompressBlocksBC7: null settings");
             const Bc7Params P = bc7_params_from(*static_cast<const bc7_enc_settings*>(settings));
             if (const char* why = bc7_params_check(P)) return fail(why);
-            // per-device attribute; cheap enough to set on every (millisecond-scale) launch
-            ITW_CUDA(cudaFuncSetAttribute(bc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc7SmemBytes));
-            // one 16-warp CTA per SM, persistent over the batches
-            const long long want = (nblocks + kBc7Slots * kBc7WarpsPerCta - 1) / (kBc7Slots * kBc7WarpsPerCta);
+            // one 16-warp CTA per SM, persistent over the batches; TMA-staged variant when the surface allows it
+            const bool tma = vec16;                                       // 16-byte aligned rows
+            const long long want = (nblocks + kBc7TileBlocks - 1) / kBc7TileBlocks;
             const long long cap = (long long)tls.sm_count;
-            bc7_kernel<<<(unsigned)(want < cap ? want : cap), kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks);
+            const unsigned grid = (unsigned)(want < cap ? want : cap);
+            // per-device attribute; cheap enough to set on every (millisecond-scale) launch
+            if (tma) {
+                ITW_CUDA(cudaFuncSetAttribute(bc7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc7SmemBytes));
+                bc7_kernel<true><<<grid, kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks);
+            } else {
+                ITW_CUDA(cudaFuncSetAttribute(bc7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc7SmemBytes));
+                bc7_kernel<false><<<grid, kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks);
+            }
             break;
         }
         case ITW_FORMAT_BC6H: {
             if (!settings) return fail("CompressBlocksBC6H: null settings");
             const Bc6Params P = bc6_params_from(*static_cast<const bc6h_enc_settings*>(settings));
             if (const char* why = bc6_params_check(P)) return fail(why);
-            ITW_CUDA(cudaFuncSetAttribute(bc6h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc6SmemBytes));
-            const long long want = (nblocks + kBc6Slots * kBc6WarpsPerCta - 1) / (kBc6Slots * kBc6WarpsPerCta);
+            const long long want = (nblocks + kBc6TileBlocks - 1) / kBc6TileBlocks;
             const long long cap = (long long)tls.sm_count;
-            bc6h_kernel<<<(unsigned)(want < cap ? want : cap), kBc6WarpsPerCta * 32, kBc6SmemBytes, stream>>>(v, d_dst, P, nblocks);
+            const unsigned grid = (unsigned)(want < cap ? want : cap);
+            if (vec16) {
+                ITW_CUDA(cudaFuncSetAttribute(bc6h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc6SmemBytes));
+                bc6h_kernel<true><<<grid, kBc6WarpsPerCta * 32, kBc6SmemBytes, stream>>>(v, d_dst, P, nblocks);
+            } else {
+                ITW_CUDA(cudaFuncSetAttribute(bc6h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc6SmemBytes));
+                bc6h_kernel<false><<<grid, kBc6WarpsPerCta * 32, kBc6SmemBytes, stream>>>(v, d_dst, P, nblocks);
+            }
             break;
         }
         default: return fail("unknown format");

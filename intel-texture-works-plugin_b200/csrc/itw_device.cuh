@@ -175,10 +175,72 @@ struct BitSink {
     }
 };
 
+#if defined(__CUDACC__)
+// ---- TMA (bulk async copy engine, SASS UBLKCP) + mbarrier helpers: global -> shared staging of texel rows ----
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ITW_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ITW_MBAR_DONE;\n"
+        "bra ITW_MBAR_WAIT;\n"
+        "ITW_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// one contiguous run of `bytes` (multiple of 16, both addresses 16-byte aligned) into shared memory
+__device__ __forceinline__ void tma_load_row(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 struct SurfaceView {
     const uint8_t* ptr;  // pointer to texel (0,0) (device memory for the kernels)
     int width, height;   // texels, multiples of 4
     int stride;          // bytes between rows
 };
+
+#if defined(__CUDACC__)
+// Stage `count` consecutive blocks (raster block order, starting at block `first`) of a surface into shared
+// memory as a 4-row tile: stage row y holds texel row y of every block, `block_row_bytes` bytes per block
+// (16 for RGBA8, 32 for RGBA16F), `stage_row_bytes` between stage rows.  The run may wrap over several block
+// rows of the surface; each contiguous piece is one TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on
+// `bar`.  Called by ONE thread.  Requires 16-byte aligned surface rows (ptr and stride multiples of 16).
+__device__ __forceinline__ void tma_prefetch_tile(unsigned char* stage, unsigned stage_row_bytes, unsigned long long* bar,
+                                                  const SurfaceView& s, long long first, int count, unsigned block_row_bytes)
+{
+    const int bw = s.width >> 2;
+    fence_proxy_async();                                  // earlier generic-proxy reads of this stage buffer are complete
+    mbar_expect_tx(bar, 4u * (unsigned)count * block_row_bytes);
+    int pos = 0;
+    long long id = first;
+    while (count > 0) {
+        const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
+        const int n = (count < bw - bx) ? count : (bw - bx);
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+            tma_load_row(stage + y * stage_row_bytes + pos * block_row_bytes,
+                         s.ptr + (size_t)(by * 4 + y) * (size_t)s.stride + (size_t)bx * block_row_bytes, (unsigned)n * block_row_bytes, bar);
+        pos += n;
+        id += n;
+        count -= n;
+    }
+}
+#endif
 
 }  // namespace itw
