@@ -139,6 +139,40 @@ uint64_t itw_kernel_launch_count(void);
  * has completed (the CompressBlocks* entry points are synchronous for host buffers). */
 float itw_last_kernel_ms(void);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 3 -- DDS container: what IntelPlugin.cpp:2171 obtains from
+ * DirectX::SaveToDDSMemory (DirectXTex/DirectXTexDDS.cpp:1611-1815) with header rules of
+ * _EncodeDDSHeader (:441-675) and the structures of DirectXTex/DDS.h:40-235.  2-D textures and
+ * cube maps of block-compressed formats only.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct itw_dds_desc {
+    uint32_t width, height;   /* top level, texels (need not be multiples of 4) */
+    uint32_t mip_levels;      /* >= 1 */
+    uint32_t array_size;      /* images per mip level: 1, or 6*n for cube maps */
+    uint32_t dxgi_format;     /* DXGI_FORMAT value, e.g. 71 BC1_UNORM, 72 BC1_UNORM_SRGB, 77/78 BC3, 80 BC4_UNORM,
+                                 83 BC5_UNORM, 95 BC6H_UF16, 96 BC6H_SF16, 98/99 BC7 */
+    uint32_t is_cubemap;      /* 0 / 1 */
+} itw_dds_desc;
+
+/* 128 (legacy FourCC header: BC1/BC3/BC4U/BC5U, single image or one cube map) or 148 (with the
+ * 'DX10' extension: sRGB variants, BC6H, BC7, arrays); 0 if the description is not supported. */
+size_t itw_dds_header_bytes(const itw_dds_desc* desc);
+/* Bytes of one image (array item `item`, mip `mip`) and its offset from the start of the file;
+ * images are stored item-major, mip-minor, each tightly packed (DirectXTexDDS.cpp:1676-1720). */
+size_t itw_dds_image_bytes(const itw_dds_desc* desc, uint32_t mip);
+size_t itw_dds_image_offset(const itw_dds_desc* desc, uint32_t item, uint32_t mip);
+size_t itw_dds_file_bytes(const itw_dds_desc* desc);
+/* Write magic + DDS_HEADER (+ DDS_HEADER_DXT10).  Returns the header size, 0 on error. */
+size_t itw_dds_write_header(const itw_dds_desc* desc, uint8_t* dst, size_t capacity);
+/* Parse a header written by this library or by DirectXTex.  Returns the payload offset, 0 on error. */
+size_t itw_dds_read_header(const uint8_t* src, size_t size, itw_dds_desc* desc);
+/* The whole save path for one texture: encode array_size*mip_levels surfaces (item-major, mip-minor,
+ * each already padded to multiples of 4 as IntelPlugin.cpp:893-928 does) straight into `file`
+ * (capacity >= itw_dds_file_bytes) behind the header.  `settings` as for itw_encode_device.
+ * Returns the file size, 0 on error. */
+size_t itw_dds_encode_file(const itw_dds_desc* desc, const rgba_surface* images, const void* settings,
+                           uint8_t* file, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ from .binding import (  # noqa: F401
     FORMATS,
     Bc6hSettings,
     Bc7Settings,
+    DdsDesc,
     ItwBcn,
     RgbaSurface,
     library_path,

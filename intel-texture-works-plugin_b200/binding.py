@@ -43,8 +43,14 @@ FORMATS = {
 EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "CompressBlocksBC5",
             "CompressBlocksBC6H", "CompressBlocksBC7", "itw_bytes_per_block", "itw_encode_device",
             "itw_encode_batch", "itw_set_device", "itw_get_last_error", "itw_kernel_launch_count",
-            "itw_last_kernel_ms"]
+            "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
+            "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file"]
            + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
+
+
+class DdsDesc(ctypes.Structure):              # include/itw_bcn.h section 3
+    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("mip_levels", ctypes.c_uint32),
+                ("array_size", ctypes.c_uint32), ("dxgi_format", ctypes.c_uint32), ("is_cubemap", ctypes.c_uint32)]
 
 
 class EncoderApi:
@@ -118,8 +124,32 @@ class ItwBcn(EncoderApi):
         L.itw_bytes_per_block.restype = ctypes.c_int
         L.itw_set_device.restype = ctypes.c_int
 
+        for n in ("itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset", "itw_dds_file_bytes",
+                  "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file"):
+            getattr(L, n).restype = ctypes.c_size_t
+        L.itw_dds_image_bytes.argtypes = [ctypes.POINTER(DdsDesc), ctypes.c_uint32]
+        L.itw_dds_image_offset.argtypes = [ctypes.POINTER(DdsDesc), ctypes.c_uint32, ctypes.c_uint32]
+        L.itw_dds_write_header.argtypes = [ctypes.POINTER(DdsDesc), ctypes.c_void_p, ctypes.c_size_t]
+        L.itw_dds_read_header.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(DdsDesc)]
+        L.itw_dds_encode_file.argtypes = [ctypes.POINTER(DdsDesc), ctypes.POINTER(RgbaSurface), ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_size_t]
+
     def last_error(self):
         return self.lib.itw_get_last_error().decode()
+
+    def dds_encode_file(self, desc, images, settings=None):
+        """itw_dds_encode_file: `images` = host numpy arrays, item-major / mip-minor, padded to multiples of 4."""
+        n = self.lib.itw_dds_file_bytes(ctypes.byref(desc))
+        if not n:
+            raise ValueError("unsupported DDS description")
+        surf = (RgbaSurface * len(images))(*[RgbaSurface(im.ctypes.data, im.shape[1], im.shape[0], im.strides[0]) for im in images])
+        out = np.zeros(n, np.uint8)
+        sp = ctypes.cast(ctypes.byref(settings), ctypes.c_void_p) if settings is not None else None
+        got = self.lib.itw_dds_encode_file(ctypes.byref(desc), surf, sp, out.ctypes.data, n)
+        if got != n:
+            self.check()
+            raise RuntimeError("itw_dds_encode_file failed")
+        return out
 
     def check(self):
         e = self.last_error()

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/itw_bcn.h"
 #include "bc4_bc5.cuh"
@@ -373,3 +374,5 @@ float itw_last_kernel_ms(void)
 }
 
 }  // extern "C"
+
+#include "itw_dds.inc"
