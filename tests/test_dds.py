@@ -100,7 +100,7 @@ def test_encode_file_equals_per_level_encodes():
             off = lib.lib.itw_dds_image_offset(ctypes.byref(d), item, mip)
             want = lib.encode("BC3", np.ascontiguousarray(faces[item][mip]))
             assert np.array_equal(blob[off:off + want.size], want), (item, mip)
-    chain = T.synth.mip_chain(T.synth.random_rgba8(128, 64, seed=9))
+    chain = T.synth.mip_chain(T.synth.random_rgba8(64, 128, seed=9))    # 128 wide, 64 high
     d = D(128, 64, 8, 1, 99, 0)
     s = lib.profile("veryfast")
     blob = lib.dds_encode_file(d, chain, s)
