@@ -173,6 +173,26 @@ size_t itw_dds_read_header(const uint8_t* src, size_t size, itw_dds_desc* desc);
 size_t itw_dds_encode_file(const itw_dds_desc* desc, const rgba_surface* images, const void* settings,
                            uint8_t* file, size_t capacity);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 4 -- on-GPU pre-pass: mip chain + pad-to-4, RGBA8 only.
+ * Level l has max(1,w>>l) x max(1,h>>l) texels, filtered from level l-1 with the 2x2 box
+ * (a+b+c+d+2)>>2, and is STORED padded to multiples of 4 by edge replication
+ * (IntelPlugin.cpp:893-928), rows tightly packed -- ready to be handed to CompressBlocks*.
+ * ------------------------------------------------------------------------------------------- */
+/* Bytes of device scratch for the padded levels first_level..levels-1 of a w x h RGBA8 texture. */
+size_t itw_mip_scratch_bytes(int width, int height, int levels, int first_level);
+/* Build padded levels 1..levels-1 (and a padded copy of level 0 if its size is not a multiple of 4) in
+ * `scratch` (device, >= itw_mip_scratch_bytes(w, h, levels, pad0 ? 0 : 1)) from the device surface
+ * `level0` (width/height = the true texture size, any stride).  out[l] receives the padded surface of
+ * level l (out[0] = *level0 when no padding is needed).  Enqueued on `cuda_stream`; returns 0 on success. */
+int itw_generate_mips_device(const rgba_surface* level0, int levels, rgba_surface* out, uint8_t* scratch,
+                             void* cuda_stream);
+/* The complete save path of one LDR texture (IntelPlugin.cpp:2117-2171): `tops` = array_size HOST or
+ * device RGBA8 surfaces holding level 0 only; mips are generated on the GPU, every level is encoded, and
+ * the DDS file is written to `file` (host).  Returns the file size, 0 on error. */
+size_t itw_dds_encode_texture(const itw_dds_desc* desc, const rgba_surface* tops, const void* settings,
+                              uint8_t* file, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,7 +44,8 @@ EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "Comp
             "CompressBlocksBC6H", "CompressBlocksBC7", "itw_bytes_per_block", "itw_encode_device",
             "itw_encode_batch", "itw_set_device", "itw_get_last_error", "itw_kernel_launch_count",
             "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
-            "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file"]
+            "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file",
+            "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture"]
            + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
 
 
@@ -134,8 +135,30 @@ class ItwBcn(EncoderApi):
         L.itw_dds_encode_file.argtypes = [ctypes.POINTER(DdsDesc), ctypes.POINTER(RgbaSurface), ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_size_t]
 
+        L.itw_mip_scratch_bytes.restype = ctypes.c_size_t
+        L.itw_generate_mips_device.restype = ctypes.c_int
+        L.itw_generate_mips_device.argtypes = [ctypes.POINTER(RgbaSurface), ctypes.c_int, ctypes.POINTER(RgbaSurface),
+                                               ctypes.c_void_p, ctypes.c_void_p]
+        L.itw_dds_encode_texture.restype = ctypes.c_size_t
+        L.itw_dds_encode_texture.argtypes = [ctypes.POINTER(DdsDesc), ctypes.POINTER(RgbaSurface), ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_size_t]
+
     def last_error(self):
         return self.lib.itw_get_last_error().decode()
+
+    def dds_encode_texture(self, desc, tops, settings=None):
+        """itw_dds_encode_texture: `tops` = host numpy level-0 images (one per array item); mips made on the GPU."""
+        n = self.lib.itw_dds_file_bytes(ctypes.byref(desc))
+        if not n:
+            raise ValueError("unsupported DDS description")
+        surf = (RgbaSurface * len(tops))(*[RgbaSurface(im.ctypes.data, im.shape[1], im.shape[0], im.strides[0]) for im in tops])
+        out = np.zeros(n, np.uint8)
+        sp = ctypes.cast(ctypes.byref(settings), ctypes.c_void_p) if settings is not None else None
+        got = self.lib.itw_dds_encode_texture(ctypes.byref(desc), surf, sp, out.ctypes.data, n)
+        if got != n:
+            self.check()
+            raise RuntimeError("itw_dds_encode_texture failed")
+        return out
 
     def dds_encode_file(self, desc, images, settings=None):
         """itw_dds_encode_file: `images` = host numpy arrays, item-major / mip-minor, padded to multiples of 4."""

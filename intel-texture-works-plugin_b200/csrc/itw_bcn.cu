@@ -18,6 +18,7 @@
 
 #include "../../include/itw_bcn.h"
 #include "bc4_bc5.cuh"
+#include "mips.cuh"
 #include "itw_params.h"
 
 using namespace itw;
@@ -376,3 +377,4 @@ float itw_last_kernel_ms(void)
 }  // extern "C"
 
 #include "itw_dds.inc"
+#include "itw_mips.inc"

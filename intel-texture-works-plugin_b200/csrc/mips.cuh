@@ -1,0 +1,58 @@
+// mips.cuh -- on-GPU pre-pass of the save path: mip-chain generation with a 2x2 box filter
+// and padding of every level to multiples of 4 by edge replication, so that the encoder never has to leave
+// the device between IntelPlugin.cpp:2117 (GenerateMipMaps) and :2171 (SaveToDDSMemory).
+//
+//   * filter: out = (a + b + c + d + 2) >> 2 per 8-bit channel (round to nearest), the integer form of the box
+//     filter of DirectXTex/DirectXTexMipmaps.cpp:715-805.  The plug-in itself asks for TEX_FILTER_DEFAULT, which
+//     on Windows goes through WIC (not vendored, not restatable): parity of the mip CONTENT with the plug-in is
+//     therefore unpinned; the contract here is the integer formula above (tests/test_mips.py, numpy restatement).
+//   * level l has max(1, w>>l) x max(1, h>>l) texels (floor, like DirectXTex); a 1-texel-wide/high source
+//     degenerates to the 2-tap average (a + b + 1) >> 1 through coordinate clamping.
+//   * padding: texel (x, y) of the padded level reads (min(x, w-1), min(y, h-1)) -- exactly the edge replication
+//     of DoPaddingToMultiplesOf4 (IntelPlugin.cpp:893-928) -- so box filter and padding are ONE bandwidth-bound
+//     pass: 16 B read + 4 B written per output texel.
+#pragma once
+#include "itw_device.cuh"
+
+namespace itw {
+
+// 8-bit x4 box filter on packed RGBA
+ITW_HD u32 box4_rgba8(u32 a, u32 b, u32 c, u32 d)
+{
+    const u32 m = 0x00FF00FFu;
+    const u32 rb = ((a & m) + (b & m) + (c & m) + (d & m) + 0x00020002u) >> 2;
+    const u32 ga = (((a >> 8) & m) + ((b >> 8) & m) + ((c >> 8) & m) + ((d >> 8) & m) + 0x00020002u) >> 2;
+    return (rb & m) | ((ga & m) << 8);
+}
+// one output texel of a padded mip level; src = previous level (valid region sw x sh, tight or padded storage)
+ITW_HD u32 mip_texel(const uint8_t* src, int sw, int sh, int sstride, int dw, int dh, int x, int y)
+{
+    const int cx = mini(x, dw - 1), cy = mini(y, dh - 1);
+    const int x0 = mini(2 * cx, sw - 1), x1 = mini(2 * cx + 1, sw - 1);
+    const int y0 = mini(2 * cy, sh - 1), y1 = mini(2 * cy + 1, sh - 1);
+    const u32* r0 = reinterpret_cast<const u32*>(src + (size_t)y0 * (size_t)sstride);
+    const u32* r1 = reinterpret_cast<const u32*>(src + (size_t)y1 * (size_t)sstride);
+    return box4_rgba8(r0[x0], r0[x1], r1[x0], r1[x1]);
+}
+
+#if defined(__CUDACC__)
+// grid: (ceil(pw/64), ph); block 64 threads: thread = one padded output texel
+__global__ void __launch_bounds__(64) mip_box_rgba8_kernel(const uint8_t* __restrict__ src, int sw, int sh, int sstride,
+                                                           uint8_t* __restrict__ dst, int dw, int dh, int pw, int dstride)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y;
+    if (x >= pw) return;
+    reinterpret_cast<u32*>(dst + (size_t)y * (size_t)dstride)[x] = mip_texel(src, sw, sh, sstride, dw, dh, x, y);
+}
+// edge-replicating copy of a (w x h) surface into its padded (pw x ph) storage (level 0 of an unpadded texture)
+__global__ void __launch_bounds__(64) pad_rgba8_kernel(const uint8_t* __restrict__ src, int sw, int sh, int sstride,
+                                                       uint8_t* __restrict__ dst, int pw, int dstride)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y;
+    if (x >= pw) return;
+    const u32* r = reinterpret_cast<const u32*>(src + (size_t)mini(y, sh - 1) * (size_t)sstride);
+    reinterpret_cast<u32*>(dst + (size_t)y * (size_t)dstride)[x] = r[mini(x, sw - 1)];
+}
+#endif
+
+}  // namespace itw

@@ -69,9 +69,14 @@ def mixed_rgba8(h, w, seed=0xB2000004):
 
 
 def box_mip(img):
-    """Next mip level by the 2x2 box filter with round-to-nearest ((a+b+c+d+2)>>2)."""
+    """Next mip level: max(1, w>>1) x max(1, h>>1), 2x2 box filter with round-to-nearest ((a+b+c+d+2)>>2);
+    a 1-texel-wide/high level degenerates to the 2-tap average; an odd trailing row/column is dropped (floor)."""
     h, w = img.shape[:2]
     a = img.astype(np.uint16)
+    if h > 1:
+        a = a[: h // 2 * 2]
+    if w > 1:
+        a = a[:, : w // 2 * 2]
     if h > 1 and w > 1:
         s = a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2]
         return ((s + 2) >> 2).astype(np.uint8)

@@ -3,7 +3,7 @@
 summary committed under profiles/: headline metrics, stall reasons per issued instruction, and executed
 instructions per device function (function boundaries from nvdisasm of the library that was profiled).
 
-usage: python profiles/summarise.py <report.ncu-rep> <kernel-name-substring> [libitw_bcn.so] > profiles/<name>.txt
+usage: python profiles/summarise.py <report.ncu-rep> <kernel-name-substring> [libitw_bcn.so [mangled-section-substring]] > profiles/<name>.txt
 """
 import csv
 import os
@@ -30,6 +30,7 @@ def ncu_csv(rep, *extra):
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     lib = sys.argv[3] if len(sys.argv) > 3 else None
+    section = sys.argv[4] if len(sys.argv) > 4 else kern
     rows = ncu_csv(rep, "--page", "raw")
     hdr, units = rows[0], rows[1]
     print(f"# {os.path.basename(rep)} -- kernel filter '{kern}'")
@@ -53,7 +54,7 @@ def main():
         dis = subprocess.run(["nvdisasm", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
     start = end = None
     for i, l in enumerate(dis):
-        if l.startswith(".text.") and kern in l and l.endswith(":"):
+        if l.startswith(".text.") and section in l and l.endswith(":"):
             start = i
         elif start is not None and l.startswith("//---------------------") and i > start:
             end = i

@@ -9,6 +9,7 @@
 #include <cstring>
 #include "../../intel-texture-works-plugin_b200/csrc/bc4_bc5.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/itw_params.h"
+#include "../../intel-texture-works-plugin_b200/csrc/mips.cuh"
 
 using namespace itw;
 
@@ -63,6 +64,12 @@ void emu_CompressBlocksBC6H(const rgba_surface* src, uint8_t* dst, bc6h_enc_sett
     }
 }
 
+// one padded mip level, texel by texel, through the kernel's own per-texel routine (csrc/mips.cuh)
+void emu_mip_level(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int pw, int ph)
+{
+    for (int y = 0; y < ph; y++)
+        for (int x = 0; x < pw; x++) reinterpret_cast<u32*>(dst + (size_t)y * pw * 4)[x] = mip_texel(src, sw, sh, sstride, dw, dh, x, y);
+}
 // the product's profile tables (csrc/itw_params.h), exported so the emulation is self-contained
 #define EMU_BC7(name, row) void emu_GetProfile_##name(bc7_enc_settings* s) { bc7_fill_profile(s, row); }
 EMU_BC7(ultrafast, 0) EMU_BC7(veryfast, 1) EMU_BC7(fast, 2) EMU_BC7(basic, 3) EMU_BC7(slow, 4)
