@@ -87,9 +87,23 @@ def _gpu_worker(rank, world, port, ret):
         got = sharding.encode_levels_sharded([(l.shape[1], l.shape[0]) for l in chain], bpb, encode_band, device="cuda")
         torch.cuda.synchronize()
         want = [lib.encode(fmt, np.ascontiguousarray(l)) for l in chain]
-        ret[rank] = all(np.array_equal(g.cpu().numpy(), w) for g, w in zip(got, want))
+        ok = all(np.array_equal(g.cpu().numpy(), w) for g, w in zip(got, want))
+        # config C4 proper: level 0 row-sharded, mips made on the GPUs, one small texel gather + one block gather
+        base = T.synth.mixed_rgba8(256, 256, seed=3)
+        y0, y1 = sharding.band_rows(256, world, rank)
+        band = torch.from_numpy(np.ascontiguousarray(base[y0:y1]).reshape(-1)).cuda()
+        got2 = sharding.encode_mip_chain_sharded(lib, fmt, band, 256, 256, 9)
+        ref_chain = T.synth.mip_chain(base)
+        want2 = [lib.encode(fmt, np.ascontiguousarray(l)) for l in ref_chain]
+        ok = ok and len(got2) == 9 and all(np.array_equal(g.cpu().numpy(), w) for g, w in zip(got2, want2))
+        ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
+
+
+def test_shardable_levels_rule():
+    assert [sharding.shardable_levels(8192, 14, n) for n in (1, 2, 4, 8)] == [12, 11, 10, 9]
+    assert sharding.shardable_levels(256, 9, 2) == 6 and sharding.shardable_levels(4, 3, 1) == 1
 
 
 @pytest.mark.gpu
