@@ -226,9 +226,11 @@ ITW_HD void bc7_fit_impl(float* ep, const View& v, u32 mask)
         float d = 0.0f;
 #pragma unroll
         for (int c = 0; c < CH; c++) d += axis[c] * ((float)((P[c][k >> 2] >> (8 * (k & 3))) & 255u) - mean[c]);
+        // d is finite here (8-bit texels, finite axis), so the reference's (a<b)?a:b equals fminf/fmaxf up to
+        // the sign of a zero, which the affine map below cannot observe: one FMNMX instead of FSETP+FSEL
         if ((mask >> k) & 1u) {
-            lo = min_sse(lo, d);
-            hi = max_sse(hi, d);
+            lo = fminf(lo, d);
+            hi = fmaxf(hi, d);
         }
     }
     if (hi - lo < 1.0f) { lo -= 0.5f; hi += 0.5f; }

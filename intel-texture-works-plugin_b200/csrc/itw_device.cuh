@@ -148,11 +148,14 @@ ITW_HD int shape_anchor(int shape, int subset)
     return (subset == 0) ? 0
                          : ((subset == 1) ? (int)ITW_TABLE(shape_anchor1)[shape] : (int)ITW_TABLE(shape_anchor2)[shape]);
 }
-// BC7 interpolation weight of index q at `bits` bits per index; K:675-686
+// BC7 interpolation weight of index q at `bits` bits per index; K:675-686.  The three tables
+// {0,21,43,64}, {0,9,...,64}, {0,4,...,64} are round(64 q / (2^bits - 1)) = (64 q + n/2) / n with n = 2^bits - 1,
+// computed with an exact multiply-shift division (checked against the tables in tests/test_tables.py).
 ITW_HD int bc7_weight(int bits, int q)
 {
-    int base = (bits == 2) ? 0 : ((bits == 3) ? 4 : 12);
-    return ITW_TABLE(weights)[base + q];
+    const int n = (1 << bits) - 1;
+    const int m = (bits == 2) ? 5462 : ((bits == 3) ? 2341 : 1093);      // ceil(2^14 / n)
+    return ((64 * q + (n >> 1)) * m) >> 14;
 }
 
 // LSB-first writer into one 128-bit block held in four registers

@@ -98,3 +98,14 @@ def test_tables_equal_reference_kernel_and_directxtex():
     for s in range(64):
         assert int(trip[64 + s][1]) == a1[s]                     # DirectXTex BC6HBC7.cpp:247
         assert (int(trip[128 + s][1]), int(trip[128 + s][2])) == (a1[64 + s], a2[64 + s])
+
+
+def test_weight_formula_equals_the_spec_tables():
+    """csrc/itw_device.cuh computes BC7 weights arithmetically; it must reproduce kernel.ispc:679-681."""
+    tables = {2: [0, 21, 43, 64], 3: [0, 9, 18, 27, 37, 46, 55, 64], 4: [0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64]}
+    mult = {2: 5462, 3: 2341, 4: 1093}
+    src = open(os.path.join(CSRC, "itw_device.cuh")).read()
+    assert "5462" in src and "2341" in src and "1093" in src
+    for bits, tab in tables.items():
+        n = (1 << bits) - 1
+        assert [((64 * q + (n >> 1)) * mult[bits]) >> 14 for q in range(n + 1)] == tab
