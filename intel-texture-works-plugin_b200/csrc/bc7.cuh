@@ -57,7 +57,8 @@ struct Bc7Warp {
     int win_pos[kBc7Slots][5];                 // winning list position per mode slot, -1 = none
     int res_err[kBc7Slots][kBc7MaxRoles];
     u32 res_code[kBc7Slots][kBc7MaxRoles][4];
-    u32 palette[24][32];                       // lane-private palette of the index search: [entry][lane]
+    u32 palette[40][32];                       // lane-private scratch of the index search, [entry][lane]: 24 palette
+                                               // entries, then 5 per-subset constants x 3 subsets
     int nvalid;
 };
 // mode slots m = 0..4 <-> BC7 modes {0, 2, 1, 3, 7}: the reference's evaluation order
@@ -153,7 +154,7 @@ template <int CH, int kIterations>
 ITW_HD void bc7_power_axis(float (&axis)[4], const float (&m)[10])
 {
     float v0 = 1.0f, v1 = 1.0f, v2 = 1.0f, v3 = 1.0f;
-#pragma unroll 1
+#pragma unroll 2
     for (int it = 0; it < kIterations; it++) {
         float a0, a1, a2, a3 = 0.0f;
         if (CH == 3) {
@@ -332,7 +333,7 @@ ITW_HD_NOINLINE void bc7_quantise(u32* out, const float* ep, int mode, int chann
     u32 cand0[2] = {0u, 0u}, cand1[2] = {0u, 0u};
     bool pick1[2] = {false, false};
     float e0 = 0.0f, e1 = 0.0f;
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 2; i++) {
         if (family == 0) { e0 = 0.0f; e1 = 0.0f; }
         u32 c0 = 0u, c1 = 0u;
@@ -391,34 +392,30 @@ ITW_HD_NOINLINE int bc7_assign(u32* idx, u32 (*pal)[32], int lane, const Bc7Bloc
 {
     const View v{blk, rot, alpha};
     const int levels = 1 << bits;
-    u32 EA[3], EB[3];
-    int cst[3];
-    float fdiv[3], frcp[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        EA[j] = EB[j] = 0u; cst[j] = 0; fdiv[j] = 1.0f; frcp[j] = 1.0f;
-        if (j < pairs) {
-            const u32 a = ends[2 * j] & chmask, b = ends[2 * j + 1] & chmask;
-            const u32 aa = dp4a_u8(a, a, 0u), ab = dp4a_u8(a, b, 0u), bb = dp4a_u8(b, b, 0u);
-            EA[j] = a; EB[j] = b;
-            cst[j] = (int)(ab - aa);
-            fdiv[j] = (float)(int)(bb - 2u * ab + aa);          // sum of squared differences, exact
-            frcp[j] = 1.0f / fdiv[j];                           // inf when the endpoints coincide (-> NaN below, as 0/0)
-            for (int q = 0; q < levels; q++) pal[j * levels + q][lane] = lerp_rgba(a, b, (u32)bc7_weight(bits, q));
-        }
+    // per-subset constants go to lane-private shared memory too and are fetched by subset id in the texel
+    // loop: the load/store pipe is nearly idle in this kernel while the ALU pipe (selects) is the busiest
+    for (int j = 0; j < pairs; j++) {
+        const u32 a = ends[2 * j] & chmask, b = ends[2 * j + 1] & chmask;
+        const u32 aa = dp4a_u8(a, a, 0u), ab = dp4a_u8(a, b, 0u), bb = dp4a_u8(b, b, 0u);
+        const float fdiv = (float)(int)(bb - 2u * ab + aa);      // sum of squared differences, exact
+        const float frcp = 1.0f / fdiv;                          // inf when the endpoints coincide (-> NaN below, as 0/0)
+        pal[24 + 5 * j + 0][lane] = a;
+        pal[24 + 5 * j + 1][lane] = b;
+        pal[24 + 5 * j + 2][lane] = ab - aa;
+        pal[24 + 5 * j + 3][lane] = float_bits(fdiv);
+        pal[24 + 5 * j + 4][lane] = float_bits(frcp);
+        for (int q = 0; q < levels; q++) pal[j * levels + q][lane] = lerp_rgba(a, b, (u32)bc7_weight(bits, q));
     }
     const float flevels = (float)levels;
     int total = 0;
     u32 out0 = 0u, out1 = 0u;
-#pragma unroll 2
+#pragma unroll 8
     for (int k = 0; k < 16; k++) {
         const u32 t = view_tex(v, k) & chmask;
         const int j = (int)((pattern >> (2 * k)) & 3u);
-        const u32 ea = (j == 0) ? EA[0] : ((j == 1) ? EA[1] : EA[2]);
-        const u32 eb = (j == 0) ? EB[0] : ((j == 1) ? EB[1] : EB[2]);
-        const int cj = (j == 0) ? cst[0] : ((j == 1) ? cst[1] : cst[2]);
-        const float dj = (j == 0) ? fdiv[0] : ((j == 1) ? fdiv[1] : fdiv[2]);
-        const float rj = (j == 0) ? frcp[0] : ((j == 1) ? frcp[1] : frcp[2]);
+        const u32 ea = pal[24 + 5 * j + 0][lane], eb = pal[24 + 5 * j + 1][lane];
+        const int cj = (int)pal[24 + 5 * j + 2][lane];
+        const float dj = bits_float(pal[24 + 5 * j + 3][lane]), rj = bits_float(pal[24 + 5 * j + 4][lane]);
         // sum_c (t_c - a_c)(b_c - a_c): integer, |value| < 2^18, so the float it converts to is the
         // reference's float sum; the division of K:1158 is the exact FMA-corrected quotient (proved
         // equal to IEEE num/div on this integer domain, tests/test_exact_division.py)

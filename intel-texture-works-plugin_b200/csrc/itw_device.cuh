@@ -17,6 +17,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
@@ -61,6 +62,22 @@ ITW_HD int mini(int a, int b) { return (a < b) ? a : b; }
 ITW_HD int maxi(int a, int b) { return (a > b) ? a : b; }
 ITW_HD int clampi(int v, int lo, int hi) { return mini(maxi(v, lo), hi); }
 ITW_HD float sq(float v) { return v * v; }
+ITW_HD u32 float_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    u32 u; memcpy(&u, &f, 4); return u;
+#endif
+}
+ITW_HD float bits_float(u32 u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
 ITW_HD float inf_f()
 {
 #if defined(__CUDA_ARCH__)
