@@ -17,7 +17,8 @@ namespace itw {
 ITW_HD int scale8(int a, int b) { int t = a * b + 128; return (t + (t >> 8)) >> 8; }
 ITW_HD int pack565(float r, float g, float b)
 {
-    int v = (scale8(cvt_x86(r), 31) << 11) + (scale8(cvt_x86(g), 63) << 5) + scale8(cvt_x86(b), 31);
+    // callers clamp r,g,b to [0,255], so plain truncation equals the x86 conversion
+    int v = (scale8(trunc_i(r), 31) << 11) + (scale8(trunc_i(g), 63) << 5) + scale8(trunc_i(b), 31);
     return v & 0xFFFF;
 }
 ITW_HD void unpack565(float c[3], int p)
@@ -51,7 +52,8 @@ ITW_HD u32 bc1_linear_indices(const float (&px)[3][16], int p0, int p1)
         float d = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) d += px[c][k] * dir[c];
-        int q = clampi(cvt_x86(d + bias), 0, 3);
+        // |d + bias| < 2^31; the only special value is NaN (p0 == p1), INT_MIN on x86 and 0 here: both clamp to 0
+        int q = clampi(trunc_i(d + bias), 0, 3);
         bits |= (u32)q << (2 * k);      // == K's bits += q*4^k: the fields never overlap
     }
     return bits;
@@ -103,8 +105,8 @@ ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
         float d = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) d += (px[c][k] - mean[c]) * axis[c];
-        dmin = min_sse(dmin, d);
-        dmax = max_sse(dmax, d);
+        dmin = fminf(dmin, d);            // d is finite: identical to the reference's (a<b)?a:b, one FMNMX
+        dmax = fmaxf(dmax, d);
     }
     if (dmax - dmin < 1.0f) { dmin -= 0.5f; dmax += 0.5f; }
     float n2 = 0.0f;
@@ -127,16 +129,18 @@ ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
 #pragma unroll
         for (int c = 0; c < 3; c++) ea[c] = eb[c] = mean[c];
     } else {
+        // sums of q and q^2 over the sixteen 2-bit indices are exact small integers: count bits instead of
+        // adding floats (q = 2*hi + lo, q^2 = 4*hi + 4*hi*lo + lo).  x*px and its running sum (<= 12240) are
+        // exact too, so the fused multiply-add gives the reference's value.
+        const u32 lo_b = bits & 0x55555555u, hi_b = (bits >> 1) & 0x55555555u;
+        const float sq1 = (float)(popcount32(lo_b) + 2 * popcount32(hi_b));
+        const float sqq = (float)(popcount32(lo_b) + 4 * popcount32(hi_b) + 4 * popcount32(lo_b & hi_b));
         float atb1[3] = {0.0f, 0.0f, 0.0f};
-        float sq1 = 0.0f, sqq = 0.0f;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            float q = (float)((bits >> (2 * k)) & 3u);
-            float x = 3.0f - q;
-            sq1 += q;
-            sqq += q * q;
+            const float x = (float)(3 - (int)((bits >> (2 * k)) & 3u));
 #pragma unroll
-            for (int c = 0; c < 3; c++) atb1[c] += x * px[c][k];
+            for (int c = 0; c < 3; c++) atb1[c] = fma_rn(x, px[c][k], atb1[c]);
         }
         float cxx = 16.0f * 9.0f - 6.0f * sq1 + sqq;
         float cyy = sqq;
@@ -168,21 +172,21 @@ ITW_HD void bc3_alpha_block(const float (&a)[16], u32& w0, u32& w1)
 {
     float lo = 255.0f, hi = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 16; k++) { lo = min_sse(lo, a[k]); hi = max_sse(hi, a[k]); }
+    for (int k = 0; k < 16; k++) { lo = fminf(lo, a[k]); hi = fmaxf(hi, a[k]); }
     if (lo == hi) hi = lo + 0.1f;
     unsigned long long idx = 0;
     float scale = 7.0f / (hi - lo);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         float proj = (a[k] - lo) * scale + 0.5f;
-        int q = clampi(cvt_x86(proj), 0, 7);
+        int q = clampi(trunc_i(proj), 0, 7);                 // 0.5 <= proj <= 255*70 + 0.5
         q = 7 - q;
         if (q > 0) q++;
         if (q == 8) q = 1;
         idx |= (unsigned long long)q << (3 * k);
     }
     // bytes: alpha0 = max, alpha1 = min, then 48 index bits
-    u32 head = (u32)(clampi(cvt_x86(lo), 0, 255) * 256 + clampi(cvt_x86(hi), 0, 255));
+    u32 head = (u32)(clampi(trunc_i(lo), 0, 255) * 256 + clampi(trunc_i(hi), 0, 255));
     w0 = head | ((u32)idx << 16);
     w1 = (u32)(idx >> 16);
 }

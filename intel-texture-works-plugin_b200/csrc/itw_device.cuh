@@ -143,6 +143,14 @@ ITW_HD u32 byte_perm(u32 a, u32 b, u32 sel)      // PRMT: result byte i = byte (
     return r;
 #endif
 }
+ITW_HD int popcount32(u32 v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
 ITW_HD int popcount16(u32 v)
 {
 #if defined(__CUDA_ARCH__)
