@@ -241,7 +241,7 @@ ITW_HD void bc1_bc3_encode_block(const u32 (&tex)[16], u32 (&out)[4])
 
 #if defined(__CUDACC__)
 template <bool kAlpha, bool kVec16>
-__global__ void __launch_bounds__(128) bc1_bc3_kernel(SurfaceView s, uint8_t* __restrict__ dst)
+__global__ void __launch_bounds__(128, 5) bc1_bc3_kernel(SurfaceView s, uint8_t* __restrict__ dst)
 {
     const int bw = s.width >> 2, bh = s.height >> 2;
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;

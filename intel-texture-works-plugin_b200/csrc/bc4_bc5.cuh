@@ -11,70 +11,12 @@
 
 namespace itw {
 
-// Endpoint optimisation over a ramp of 6 or 8 steps (BC.h:727-856).  kSteps is a template
-// parameter so that the ramp coefficient tables fold into immediates.
-template <int kSteps>
-ITW_HD void bc4_fit_ramp(float& out_lo, float& out_hi, const float (&t)[16])
-{
-    const float last = (float)(kSteps - 1);
-    float coef_lo[8], coef_hi[8];
-#pragma unroll
-    for (int s = 0; s < kSteps; s++) {
-        coef_lo[s] = (float)(kSteps - 1 - s) / last;
-        coef_hi[s] = (float)s / last;
-    }
-    float lo = 1.0f, hi = 0.0f;
-    if (kSteps == 8) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            if (t[i] < lo) lo = t[i];
-            if (t[i] > hi) hi = t[i];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            if (t[i] < lo && t[i] > 0.0f) lo = t[i];
-            if (t[i] > hi && t[i] < 1.0f) hi = t[i];
-        }
-        if (lo == hi) hi = 1.0f;
-    }
-    for (int iter = 0; iter < 8; iter++) {
-        if ((hi - lo) < (1.0f / 256.0f)) break;
-        const float scale = last / (hi - lo);
-        float ramp[8];
-#pragma unroll
-        for (int s = 0; s < kSteps; s++) ramp[s] = coef_lo[s] * lo + coef_hi[s] * hi;
-        float dlo = 0.0f, dhi = 0.0f, d2lo = 0.0f, d2hi = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const float dot = (t[i] - lo) * scale;
-            int step;
-            if (dot <= 0.0f) step = ((kSteps == 6) && (t[i] <= lo * 0.5f)) ? 6 : 0;
-            else if (dot >= last) step = ((kSteps == 6) && (t[i] >= (hi + 1.0f) * 0.5f)) ? 7 : (kSteps - 1);
-            else step = (int)(dot + 0.5f);
-            if (step < kSteps) {
-                // select the step's ramp value / coefficients without dynamic register indexing
-                float r = ramp[0], cl = coef_lo[0], ch = coef_hi[0];
-#pragma unroll
-                for (int s = 1; s < kSteps; s++)
-                    if (step == s) { r = ramp[s]; cl = coef_lo[s]; ch = coef_hi[s]; }
-                const float diff = r - t[i];
-                dlo += cl * diff;
-                d2lo += cl * cl;
-                dhi += ch * diff;
-                d2hi += ch * ch;
-            }
-        }
-        if (d2lo > 0.0f) lo -= dlo / d2lo;
-        if (d2hi > 0.0f) hi -= dhi / d2hi;
-        if (lo > hi) { float f = lo; lo = hi; hi = f; }
-        if ((dlo * dlo < (1.0f / 64.0f)) && (dhi * dhi < (1.0f / 64.0f))) break;
-    }
-    out_lo = (lo < 0.0f) ? 0.0f : ((lo > 1.0f) ? 1.0f : lo);
-    out_hi = (hi < 0.0f) ? 0.0f : ((hi > 1.0f) ? 1.0f : hi);
-}
-
-// 16 byte values of one channel -> one 8-byte BC4U block (two words)
+// 16 byte values of one channel -> one 8-byte BC4U block (two words).
+// FindEndPointsBC4U (BC4BC5.cpp:186-238) + OptimizeAlpha<false> (BC.h:727-856) + FindClosestUNORM (:314-337).
+// The reference has two code paths (6- and 8-step ramps); here the ramp length is DATA (`steps`), so the
+// threads of a warp never diverge on it: blocks that touch 0 or 255 and blocks that do not run the same
+// instruction stream.  The ramp coefficients (steps-1-s)/(steps-1) and s/(steps-1), compile-time constants
+// in the reference (BC.h:730-733), are the same correctly rounded quotients computed at run time.
 ITW_HD void bc4_encode_channel(const int (&v)[16], u32& w0, u32& w1)
 {
     float t[16];
@@ -88,30 +30,66 @@ ITW_HD void bc4_encode_channel(const int (&v)[16], u32& w0, u32& w1)
     }
     // blocks touching 0 or 1 use the 6-step ramp with explicit 0/1 codes; BC4BC5.cpp:206-237
     const bool six = (0.0f == bmin || 1.0f == bmax);
-    float fs, fe;
-    int e0, e1;
-    if (!six) {
-        bc4_fit_ramp<8>(fs, fe, t);
-        e1 = (int)(fs * 255.0f) & 255;          // (uint8_t) truncation; values are in [0,255]
-        e0 = (int)(fe * 255.0f) & 255;
-    } else {
-        bc4_fit_ramp<6>(fs, fe, t);
-        e0 = (int)(fs * 255.0f) & 255;
-        e1 = (int)(fe * 255.0f) & 255;
+    const int steps = six ? 6 : 8;
+    const float last = (float)(steps - 1), rlast = 1.0f / last;
+
+    // starting interval; BC.h:748-776
+    float lo = 1.0f, hi = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (t[i] < lo && (!six || t[i] > 0.0f)) lo = t[i];
+        if (t[i] > hi && (!six || t[i] < 1.0f)) hi = t[i];
     }
-    // palette; BC4BC5.cpp:48-71
+    if (six && lo == hi) hi = 1.0f;
+
+    // Newton iterations on the two endpoints; BC.h:778-851
+#pragma unroll 1
+    for (int iter = 0; iter < 8; iter++) {
+        if ((hi - lo) < (1.0f / 256.0f)) break;
+        const float scale = last / (hi - lo);
+        float dlo = 0.0f, dhi = 0.0f, d2lo = 0.0f, d2hi = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float dot = (t[i] - lo) * scale;
+            int step;
+            if (dot <= 0.0f) step = (six && (t[i] <= lo * 0.5f)) ? 6 : 0;
+            else if (dot >= last) step = (six && (t[i] >= (hi + 1.0f) * 0.5f)) ? 7 : (steps - 1);
+            else step = (int)(dot + 0.5f);
+            if (step < steps) {
+                // integer / {5,7}: the exact quotient (tests/test_exact_division.py covers this domain)
+                const float cl = div_by_rcp((float)(steps - 1 - step), last, rlast);
+                const float ch = div_by_rcp((float)step, last, rlast);
+                const float diff = (cl * lo + ch * hi) - t[i];
+                dlo += cl * diff;
+                d2lo += cl * cl;
+                dhi += ch * diff;
+                d2hi += ch * ch;
+            }
+        }
+        if (d2lo > 0.0f) lo -= dlo / d2lo;
+        if (d2hi > 0.0f) hi -= dhi / d2hi;
+        if (lo > hi) { float f = lo; lo = hi; hi = f; }
+        if ((dlo * dlo < (1.0f / 64.0f)) && (dhi * dhi < (1.0f / 64.0f))) break;
+    }
+    const float fs = (lo < 0.0f) ? 0.0f : ((lo > 1.0f) ? 1.0f : lo);
+    const float fe = (hi < 0.0f) ? 0.0f : ((hi > 1.0f) ? 1.0f : hi);
+    const int is = (int)(fs * 255.0f) & 255, ie = (int)(fe * 255.0f) & 255;      // (uint8_t) truncation
+    const int e0 = six ? is : ie, e1 = six ? ie : is;                             // BC4BC5.cpp:222-236
+
+    // palette; BC4BC5.cpp:48-71 (decode mode follows the stored endpoint order, not the encoder's intent)
     float pal[8];
     const float f0 = (float)e0 / 255.0f, f1 = (float)e1 / 255.0f;
+    const bool eight = e0 > e1;
+    const float n = eight ? 7.0f : 5.0f;
     pal[0] = f0;
     pal[1] = f1;
-    if (e0 > e1) {
 #pragma unroll
-        for (int i = 2; i < 8; i++) pal[i] = (f0 * (float)(8 - i) + f1 * (float)(i - 1)) / 7.0f;
-    } else {
-#pragma unroll
-        for (int i = 2; i < 6; i++) pal[i] = (f0 * (float)(6 - i) + f1 * (float)(i - 1)) / 5.0f;
-        pal[6] = 0.0f;
-        pal[7] = 1.0f;
+    for (int i = 2; i < 8; i++) {
+        const float k = (float)(i - 1);
+        float p = (f0 * (n - k) + f1 * k) / n;
+        if (!eight && i == 6) p = 0.0f;
+        if (!eight && i == 7) p = 1.0f;
+        pal[i] = p;
     }
     unsigned long long data = (unsigned long long)e0 | ((unsigned long long)e1 << 8);
 #pragma unroll

@@ -49,6 +49,11 @@ int main(void) {
         for (int x = -255; x <= 255; x++) bad += ((float)x / d != dq((float)x, d, r));
     }
     printf("scalar %lld\n", bad);
+    /* (5) BC4/BC5 ramp coefficients: integer 0..7 by 5 or 7 */
+    bad = 0;
+    for (int d = 5; d <= 7; d += 2)
+        for (int x = 0; x <= 7; x++) bad += ((float)x / (float)d != dq((float)x, (float)d, 1.0f / (float)d));
+    printf("ramp %lld\n", bad);
     return 0;
 }
 """
@@ -61,4 +66,4 @@ def test_fma_corrected_quotient_is_exact_on_every_domain_it_is_used_on():
         open(c, "w").write(SRC)
         subprocess.check_call(["gcc", "-O3", "-fopenmp", "-mavx2", "-mfma", "-ffp-contract=off", c, "-o", exe, "-lm"])
         out = subprocess.check_output([exe], text=True).split()
-    assert out == ["div255", "0", "count", "0", "proj", "0", "scalar", "0"], out
+    assert out == ["div255", "0", "count", "0", "proj", "0", "scalar", "0", "ramp", "0"], out
