@@ -107,6 +107,11 @@ def corpus16(size=64, seed=11):
     nar = (0x3800 + rng.integers(0, 40, (n, n, 4))).astype(np.uint16)          # tiny spans -> modes 2-4, 13
     nar[..., 0] += rng.integers(0, 200, (n, n)).astype(np.uint16)
     out["narrow"] = nar
+    for c, tag in ((1, "narrow_g"), (2, "narrow_b")):                          # wide channel G / B -> modes 3,7 / 4,8
+        v = (0x3800 + rng.integers(0, 40, (n, n, 4))).astype(np.uint16)
+        v[..., c] += rng.integers(0, 200, (n, n)).astype(np.uint16)
+        v[: n // 2, :, c] += rng.integers(0, 1500, (n // 2, n)).astype(np.uint16)
+        out[tag] = v
     return out
 
 
