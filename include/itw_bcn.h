@@ -79,7 +79,10 @@ void GetProfile_bc6h_veryslow(bc6h_enc_settings* settings);
 /* ispc_texcomp.h:104-107; ispc_texcomp.cpp:417-435 -> kernel.ispc:598/607/3132/2030.
  * dst receives (width/4)*(height/4) blocks, tightly packed in raster block order
  * (8 bytes/block for BC1, 16 for BC3/BC6H/BC7).  `src->ptr` and `dst` may each be host or
- * device memory (detected per call); host buffers are staged through pinned memory.
+ * device memory (detected per call).  The call is synchronous.  With a device operand the work is
+ * issued on the legacy default stream, i.e. it is ordered after work already enqueued on blocking
+ * streams; producers on NON-blocking streams must be synchronised by the caller (or use
+ * itw_encode_device, which is stream-ordered).
  * void return as in the reference: failures are reported through itw_get_last_error(). */
 void CompressBlocksBC1(const rgba_surface* src, uint8_t* dst);
 void CompressBlocksBC3(const rgba_surface* src, uint8_t* dst);

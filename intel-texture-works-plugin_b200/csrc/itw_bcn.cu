@@ -45,6 +45,18 @@ struct ThreadCtx {
         uint8_t* d_out = nullptr; size_t d_out_cap = 0;
         bool busy = false;
     } lanes[3];
+    void release()
+    {
+        // best effort: at process exit the runtime may already be unloading, errors are ignored
+        if (stream) cudaStreamDestroy(stream);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        cudaFree(d_in); cudaFree(d_out);
+        for (auto& l : lanes) { if (l.stream) cudaStreamDestroy(l.stream); cudaFree(l.d_in); cudaFree(l.d_out); l = Lane(); }
+        stream = nullptr; ev0 = ev1 = nullptr; d_in = d_out = nullptr; d_in_cap = d_out_cap = 0;
+        cudaGetLastError();
+    }
+    ~ThreadCtx() { release(); }            // pool threads come and go (win32Threads.cpp:98-190)
 };
 thread_local ThreadCtx tls;
 
@@ -74,11 +86,9 @@ int ensure_ctx()
     }
     if (c.device == dev && c.stream) return 0;
     if (c.stream) {                       // device changed: drop the old resources
-        cudaStreamDestroy(c.stream); cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
-        cudaFree(c.d_in); cudaFree(c.d_out);
-        for (auto& l : c.lanes) { if (l.stream) cudaStreamDestroy(l.stream); cudaFree(l.d_in); cudaFree(l.d_out); }
-        c = ThreadCtx();
-        c.wanted_device = dev;
+        c.release();
+        c.device = -1;
+        c.timed = false;
     }
     cudaDeviceProp prop;
     ITW_CUDA(cudaGetDeviceProperties(&prop, dev));
@@ -208,14 +218,18 @@ int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* se
     const size_t out_bytes = (size_t)(src->width >> 2) * (src->height >> 2) * f.bpb;
     const bool src_dev = is_device_pointer(src->ptr), dst_dev = is_device_pointer(dst);
 
+    // Device-resident operands were produced by the caller's own streams.  The legacy default stream orders
+    // after every blocking stream (torch's default stream included), which gives the synchronous call the
+    // semantics a caller expects; pure host calls use this thread's private non-blocking stream.
+    cudaStream_t s = (src_dev || dst_dev) ? cudaStreamLegacy : c.stream;
     SurfaceView v{src->ptr, src->width, src->height, src->stride};
     if (!src_dev) {                      // H2D of the tightly packed rows (pinned sources copy at PCIe rate)
         if (grow(c.d_in, c.d_in_cap, row_bytes * src->height)) return -1;
         if ((size_t)src->stride == row_bytes)   // tightly packed rows: one linear copy (full PCIe rate from pinned memory)
-            ITW_CUDA(cudaMemcpyAsync(c.d_in, src->ptr, row_bytes * src->height, cudaMemcpyHostToDevice, c.stream));
+            ITW_CUDA(cudaMemcpyAsync(c.d_in, src->ptr, row_bytes * src->height, cudaMemcpyHostToDevice, s));
         else
             ITW_CUDA(cudaMemcpy2DAsync(c.d_in, row_bytes, src->ptr, (size_t)src->stride, row_bytes, (size_t)src->height,
-                                       cudaMemcpyHostToDevice, c.stream));
+                                       cudaMemcpyHostToDevice, s));
         v.ptr = c.d_in;
         v.stride = (int)row_bytes;
     }
@@ -225,13 +239,13 @@ int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* se
         if (grow(c.d_out, c.d_out_cap, out_bytes)) return -1;
         d_dst = c.d_out;
     }
-    ITW_CUDA(cudaEventRecord(c.ev0, c.stream));
-    if (launch(format, v, d_dst, settings, c.stream)) return -1;
-    ITW_CUDA(cudaEventRecord(c.ev1, c.stream));
+    ITW_CUDA(cudaEventRecord(c.ev0, s));
+    if (launch(format, v, d_dst, settings, s)) return -1;
+    ITW_CUDA(cudaEventRecord(c.ev1, s));
     c.timed = true;
     if (!dst_ok)
-        ITW_CUDA(cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
-    ITW_CUDA(cudaStreamSynchronize(c.stream));
+        ITW_CUDA(cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    ITW_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
 
