@@ -196,6 +196,18 @@ int itw_generate_mips_device(const rgba_surface* level0, int levels, rgba_surfac
 size_t itw_dds_encode_texture(const itw_dds_desc* desc, const rgba_surface* tops, const void* settings,
                               uint8_t* file, size_t capacity);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 5 -- decoders: what the plug-in's preview obtains from
+ * DirectX::Decompress (IntelPlugin.cpp:1051-1066; DirectXTex/DirectXTexCompress.cpp:358-468 ->
+ * D3DXDecodeBC1/3/4U/5U/6HU/7, BC.cpp:897, BC4BC5.cpp:369-400, BC6HBC7.cpp:2879-2900).
+ * `blocks` holds (width/4)*(height/4) blocks in raster order; dst->ptr is WRITTEN: RGBA8 texels
+ * (4 B) for BC1/BC3/BC4/BC5/BC7 (BC4: r,0,0,255; BC5: r,g,0,255), RGBA16F texels (8 B, half bit
+ * patterns, alpha = 1.0) for BC6H_UF16.  width/height multiples of 4; either side may be host or
+ * device memory; synchronous.  BC7 and BC6H are exact by the format definition; the BC1-BC5 palettes
+ * use the integer formulas stated in csrc/decode.cuh.  Returns 0 on success.
+ * ------------------------------------------------------------------------------------------- */
+int itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,7 +45,7 @@ EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "Comp
             "itw_encode_batch", "itw_set_device", "itw_get_last_error", "itw_kernel_launch_count",
             "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
             "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file",
-            "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture"]
+            "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture", "itw_decode"]
            + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
 
 
@@ -99,6 +99,26 @@ class EncoderApi:
         self._call(fmt, surf, out.ctypes.data, settings)
         self.check()
         return out
+
+    def decode(self, fmt, blocks, width, height):
+        """itw_decode: host blocks -> H x W x 4 image (uint8; uint16 half bit patterns for BC6H)."""
+        _, bpb, texel, _ = FORMATS[fmt]
+        blocks = np.ascontiguousarray(np.frombuffer(bytes(blocks), np.uint8))
+        assert blocks.size == (width // 4) * (height // 4) * bpb
+        img = np.zeros((height, width, 4), np.uint16 if texel == 8 else np.uint8)
+        self.decode_raw(fmt, blocks.ctypes.data, img.ctypes.data, width, height, img.strides[0])
+        return img
+
+    def decode_raw(self, fmt, blocks_ptr, dst_ptr, width, height, stride):
+        """itw_decode on raw addresses (host or device)."""
+        f = self.fn("itw_decode")
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(RgbaSurface)]
+        surf = RgbaSurface(dst_ptr, width, height, stride)
+        rc = f(FORMATS[fmt][0], ctypes.c_void_p(blocks_ptr), ctypes.byref(surf))
+        self.check()
+        if rc != 0:
+            raise RuntimeError("itw_decode failed")
 
     def encode_raw(self, fmt, ptr, width, height, stride, dst_ptr, settings=None):
         """CompressBlocks<fmt> on raw addresses (host or device)."""

@@ -1,0 +1,363 @@
+// decode.cuh -- BCn DECODERS: the step after the hot path in the plug-in's preview
+// (IntelPlugin.cpp:1051-1066 -> DirectX::Decompress -> D3DXDecodeBC*, DirectXTex/DirectXTexCompress.cpp:358-468).
+//
+// One thread decodes one 4x4 block and writes its 16 texels (4 x 128-bit row stores for RGBA8; a warp covers 32
+// adjacent blocks, so every row store is a contiguous 512-byte request).  Bandwidth-bound: 8/16 B in, 64/128 B out.
+//
+// Contract.  BC7 and BC6H are integer-exact by the format definition (interpolation ((64-w)a + wb + 32) >> 6,
+// BC6H un-quantisation and the final (x*31)>>6 to half bits; DirectXTex/BC6HBC7.cpp:1077-1236, :1937-2144), so the
+// result is THE decode.  BC1/BC3/BC4/BC5 palettes are defined here with the usual integer formulas (bit-replicated
+// 565, (2a+b+1)/3, ((7-i)a + ib + 3)/7 ...); DirectXTex computes them in float (BC.cpp:322-370, BC4BC5.cpp:42-95)
+// and may differ by one LSB -- parity with the plug-in's preview is unpinned for those four formats.
+// The numpy restatement of exactly these rules is tests/bcn_decode.py.
+#pragma once
+#include "bc6h.cuh"
+
+namespace itw {
+
+// LSB-first reader over one 128-bit block
+struct BitReader {
+    unsigned long long lo, hi;
+    int pos;
+    ITW_HD void init(const u32 (&w)[4])
+    {
+        lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+        hi = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
+        pos = 0;
+    }
+    ITW_HD u32 get(int n)                     // 0 <= n <= 16
+    {
+        unsigned long long v;
+        if (pos >= 64) v = hi >> (pos - 64);
+        else v = (lo >> pos) | ((pos == 0) ? 0ull : (hi << (64 - pos)));
+        pos += n;
+        return (u32)v & ((1u << n) - 1u);
+    }
+};
+
+// ---- BC1 colour block -> packed RGBA (alpha 255, or 0 for the transparent code of 3-colour mode) ----
+ITW_HD u32 expand565(u32 c)
+{
+    const u32 r = (c >> 11) & 31u, g = (c >> 5) & 63u, b = c & 31u;
+    return ((r << 3) | (r >> 2)) | (((g << 2) | (g >> 4)) << 8) | (((b << 3) | (b >> 2)) << 16);
+}
+ITW_HD u32 mix_rgb(u32 a, u32 b, u32 wa, u32 wb, u32 add, u32 div)     // per channel (wa*a + wb*b + add) / div
+{
+    u32 out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const u32 x = (a >> (8 * c)) & 255u, y = (b >> (8 * c)) & 255u;
+        out |= ((wa * x + wb * y + add) / div) << (8 * c);
+    }
+    return out;
+}
+ITW_HD void decode_bc1_colour(u32 (&px)[16], u32 w0, u32 w1, bool force4)
+{
+    const u32 c0 = w0 & 0xFFFFu, c1 = w0 >> 16;
+    const u32 a = expand565(c0), b = expand565(c1);
+    const bool four = (c0 > c1) || force4;
+    const u32 p0 = a | 0xFF000000u, p1 = b | 0xFF000000u;
+    const u32 p2 = (four ? mix_rgb(a, b, 2, 1, 1, 3) : mix_rgb(a, b, 1, 1, 0, 2)) | 0xFF000000u;
+    const u32 p3 = four ? (mix_rgb(a, b, 1, 2, 1, 3) | 0xFF000000u) : 0u;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 q = (w1 >> (2 * k)) & 3u;
+        px[k] = (q == 0) ? p0 : ((q == 1) ? p1 : ((q == 2) ? p2 : p3));
+    }
+}
+// ---- BC3 alpha / BC4 / BC5 channel block -> 16 values ----
+ITW_HD void decode_alpha(u32 (&val)[16], u32 w0, u32 w1)
+{
+    const u32 a0 = w0 & 255u, a1 = (w0 >> 8) & 255u;
+    const unsigned long long idx = ((unsigned long long)w1 << 16) | (w0 >> 16);
+    const bool eight = a0 > a1;
+    // the eight palette entries packed one per byte, then a 64-bit shift per texel instead of a select chain
+    unsigned long long pal = (unsigned long long)a0 | ((unsigned long long)a1 << 8);
+#pragma unroll
+    for (u32 q = 2; q < 8; q++) {
+        u32 v;
+        if (eight) v = ((8u - q) * a0 + (q - 1u) * a1 + 3u) / 7u;
+        else if (q == 6) v = 0u;
+        else if (q == 7) v = 255u;
+        else v = ((6u - q) * a0 + (q - 1u) * a1 + 2u) / 5u;
+        pal |= (unsigned long long)v << (8 * q);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 q = (u32)(idx >> (3 * k)) & 7u;
+        val[k] = (u32)(pal >> (8 * q)) & 255u;
+    }
+}
+
+// ---- BC7; format definition as implemented by DirectXTex/BC6HBC7.cpp:1937-2144 ----
+// subsets, partition bits, rotation bits, index-selection bits, colour bits, alpha bits, endpoint p-bits,
+// shared p-bits, index bits, second index bits
+struct Bc7ModeDesc { int ns, pb, rb, isb, cb, ab, epb, spb, ib, ib2; };
+ITW_HD Bc7ModeDesc bc7_mode_desc(int m)
+{
+    switch (m) {
+        case 0: return Bc7ModeDesc{3, 4, 0, 0, 4, 0, 1, 0, 3, 0};
+        case 1: return Bc7ModeDesc{2, 6, 0, 0, 6, 0, 0, 1, 3, 0};
+        case 2: return Bc7ModeDesc{3, 6, 0, 0, 5, 0, 0, 0, 2, 0};
+        case 3: return Bc7ModeDesc{2, 6, 0, 0, 7, 0, 1, 0, 2, 0};
+        case 4: return Bc7ModeDesc{1, 0, 2, 1, 5, 6, 0, 0, 2, 3};
+        case 5: return Bc7ModeDesc{1, 0, 2, 0, 7, 8, 0, 0, 2, 2};
+        case 6: return Bc7ModeDesc{1, 0, 0, 0, 7, 7, 1, 0, 4, 0};
+        default: return Bc7ModeDesc{2, 6, 0, 0, 5, 5, 1, 0, 2, 0};
+    }
+}
+ITW_HD int lowest_set_bit(u32 v)              // v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+ITW_HD u32 widen8(u32 v, int bits) { return ((v << (8 - bits)) | (v >> (2 * bits - 8))) & 255u; }
+
+// Returns false for the reserved mode (mode byte 0): the block decodes to transparent black, as in DirectXTex
+// (BC6HBC7.cpp:2135-2143).  All endpoint arrays are indexed by fully unrolled loops so that they live in registers.
+ITW_HD bool decode_bc7(u32 (&px)[16], const u32 (&w)[4])
+{
+    if ((w[0] & 255u) == 0u) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = 0u;
+        return false;
+    }
+    BitReader b;
+    b.init(w);
+    const int mode = lowest_set_bit(w[0] & 255u);
+    b.pos = mode + 1;
+    const Bc7ModeDesc d = bc7_mode_desc(mode);
+    const int shape = (int)b.get(d.pb), rot = (int)b.get(d.rb), isel = (int)b.get(d.isb);
+    const int ne = 2 * d.ns;
+    u32 ep[6][4];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int e = 0; e < 6; e++) ep[e][c] = (e < ne) ? b.get(d.cb) : 0u;
+#pragma unroll
+    for (int e = 0; e < 6; e++) ep[e][3] = (d.ab && e < ne) ? b.get(d.ab) : 255u;
+    int cbits = d.cb, abits = d.ab;
+    if (d.epb) {
+#pragma unroll
+        for (int e = 0; e < 6; e++) {
+            if (e < ne) {
+                const u32 p = b.get(1);
+#pragma unroll
+                for (int c = 0; c < 3; c++) ep[e][c] = (ep[e][c] << 1) | p;
+                if (d.ab) ep[e][3] = (ep[e][3] << 1) | p;
+            }
+        }
+        cbits++;
+        if (d.ab) abits++;
+    }
+    if (d.spb) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {            // mode 1 only: two subsets
+            const u32 p = b.get(1);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                ep[2 * s][c] = (ep[2 * s][c] << 1) | p;
+                ep[2 * s + 1][c] = (ep[2 * s + 1][c] << 1) | p;
+            }
+        }
+        cbits++;
+    }
+    u32 pk[6];                                   // packed r | g<<8 | b<<16 | a<<24
+#pragma unroll
+    for (int e = 0; e < 6; e++) {
+        const u32 a = d.ab ? widen8(ep[e][3], abits) : 255u;
+        pk[e] = widen8(ep[e][0], cbits) | (widen8(ep[e][1], cbits) << 8) | (widen8(ep[e][2], cbits) << 16) | (a << 24);
+    }
+    const u32 pattern = (d.ns == 1) ? 0u : shape_pattern(d.ns == 2 ? shape : 64 + shape);
+    const int anchor1 = (d.ns == 1) ? -1 : shape_anchor(d.ns == 2 ? shape : 64 + shape, 1);
+    const int anchor2 = (d.ns == 3) ? shape_anchor(64 + shape, 2) : -1;
+    unsigned long long i1 = 0, i2 = 0;           // 4 bits per texel
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const bool anchor = (k == 0) || (k == anchor1) || (k == anchor2);
+        i1 |= (unsigned long long)b.get(anchor ? d.ib - 1 : d.ib) << (4 * k);
+    }
+    if (d.ib2) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) i2 |= (unsigned long long)b.get(k == 0 ? d.ib2 - 1 : d.ib2) << (4 * k);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 s = (pattern >> (2 * k)) & 3u;
+        const u32 e0 = (s == 0) ? pk[0] : ((s == 1) ? pk[2] : pk[4]);
+        const u32 e1 = (s == 0) ? pk[1] : ((s == 1) ? pk[3] : pk[5]);
+        const int q1 = (int)((i1 >> (4 * k)) & 15ull), q2 = (int)((i2 >> (4 * k)) & 15ull);
+        u32 cw, aw;
+        if (!d.ib2) cw = aw = (u32)bc7_weight(d.ib, q1);
+        else if (!isel) { cw = (u32)bc7_weight(d.ib, q1); aw = (u32)bc7_weight(d.ib2, q2); }
+        else { cw = (u32)bc7_weight(d.ib2, q2); aw = (u32)bc7_weight(d.ib, q1); }
+        // two 16-bit lanes per word: every lane is at most 64*255 + 32 < 2^16
+        const u32 rb = (((64u - cw) * (e0 & 0x00FF00FFu) + cw * (e1 & 0x00FF00FFu) + 0x00200020u) >> 6) & 0x00FF00FFu;
+        const u32 g = (((64u - cw) * ((e0 >> 8) & 255u) + cw * ((e1 >> 8) & 255u) + 32u) >> 6);
+        const u32 a = (((64u - aw) * (e0 >> 24) + aw * (e1 >> 24) + 32u) >> 6);
+        u32 v = rb | (g << 8) | (a << 24);
+        if (rot) {                               // swap alpha with channel rot-1
+            const int sh = 8 * (rot - 1);
+            const u32 ch = (v >> sh) & 255u;
+            v = (v & ~((255u << sh) | 0xFF000000u)) | (a << sh) | (ch << 24);
+        }
+        px[k] = v;
+    }
+    return true;
+}
+
+// ---- BC6H, unsigned; format definition as implemented by DirectXTex/BC6HBC7.cpp:1077-1236 ----
+ITW_HD int bc6_mode_epb(int mode)
+{
+    // {10,7,11,11,11,9,8,8,8,6,10,11,12,16} packed 5 bits each
+    const unsigned long long t = 10ull | (7ull << 5) | (11ull << 10) | (11ull << 15) | (11ull << 20) | (9ull << 25) | (8ull << 30) |
+                                 (8ull << 35) | (8ull << 40) | (6ull << 45) | (10ull << 50) | (11ull << 55);
+    if (mode < 12) return (int)((t >> (5 * mode)) & 31ull);
+    return (mode == 12) ? 12 : 16;
+}
+// out[k][0] = r | g << 16, out[k][1] = b | 0x3C00 << 16 (half bit patterns, alpha = 1.0).  Returns false for the
+// reserved mode fields (decoded as opaque black, BC6HBC7.cpp:1088-1106).
+ITW_HD_NOINLINE bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
+{
+    const u32 m2 = w[0] & 3u;
+    const u32 field = (m2 < 2u) ? m2 : (w[0] & 31u);
+    int mode = -1;
+    for (int m = 0; m < 14; m++)
+        if ((u32)bc6_prefix(m) == field) mode = m;
+    if (mode < 0) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) { px[k][0] = 0u; px[k][1] = 0x3C000000u; }
+        return false;
+    }
+    BitReader b;
+    b.init(w);
+#if defined(__CUDA_ARCH__)
+    const Bc6Step* steps = d_bc6_layout[mode];
+#else
+    const Bc6Step* steps = h_bc6_layout[mode];
+#endif
+    int fld[13], nbits[13];
+    for (int i = 0; i < 13; i++) fld[i] = nbits[i] = 0;
+    for (int i = 0; i < kBc6MaxSteps; i++) {
+        const int f = steps[i].f, bit = steps[i].b, n = steps[i].n;
+        if (n == 0) break;
+        if (n > 0) {
+            fld[f] |= (int)(b.get(n) << bit);
+            if (bit + n > nbits[f]) nbits[f] = bit + n;
+        } else {
+            for (int j = 0; j < -n; j++) fld[f] |= (int)(b.get(1) << (bit - j));
+            if (bit + 1 > nbits[f]) nbits[f] = bit + 1;
+        }
+    }
+    const int regions = (mode < 10) ? 2 : 1;
+    const int epb = bc6_mode_epb(mode);
+    const bool delta = !(mode == 9 || mode == 10);
+    int e[4][3];
+    for (int i = 0; i < 4; i++)
+        for (int c = 0; c < 3; c++) {
+            int v = fld[1 + 3 * i + c];
+            if (delta && i > 0) {
+                const int nb = nbits[1 + 3 * i + c];
+                if (nb > 0 && (v & (1 << (nb - 1)))) v -= 1 << nb;
+                v = (fld[1 + c] + v) & ((1 << epb) - 1);
+            }
+            e[i][c] = bc6_dequant(v, epb);
+        }
+    const int shape = (regions == 2) ? (int)b.get(5) : 0;
+    const u32 pattern = (regions == 2) ? shape_pattern(shape) : 0u;
+    const int anchor1 = (regions == 2) ? shape_anchor(shape, 1) : -1;
+    const int ib = (regions == 2) ? 3 : 4;
+    for (int k = 0; k < 16; k++) {
+        const int s = (int)((pattern >> (2 * k)) & 3u);
+        const bool anchor = (k == 0) || (k == anchor1);
+        const int q = (int)b.get(anchor ? ib - 1 : ib);
+        const int wt = bc7_weight(ib, q);
+        u32 h[3];
+        for (int c = 0; c < 3; c++) h[c] = (u32)(((((64 - wt) * e[2 * s][c] + wt * e[2 * s + 1][c] + 32) >> 6) * 31) >> 6);
+        px[k][0] = h[0] | (h[1] << 16);
+        px[k][1] = h[2] | 0x3C000000u;
+    }
+    return true;
+}
+
+// ---- one block of any format -> 16 packed texels (RGBA8: one word, RGBA16F: two words) ----
+// kFormat: ITW_FORMAT_* ids (DXGI numbers 71/77/80/83/95/98)
+template <int kFormat>
+ITW_HD void decode_block_rgba8(u32 (&px)[16], const u32 (&w)[4])
+{
+    if (kFormat == 71) decode_bc1_colour(px, w[0], w[1], false);
+    else if (kFormat == 77) {
+        u32 a[16];
+        decode_bc1_colour(px, w[2], w[3], true);
+        decode_alpha(a, w[0], w[1]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = (px[k] & 0x00FFFFFFu) | (a[k] << 24);
+    } else if (kFormat == 80) {
+        u32 r[16];
+        decode_alpha(r, w[0], w[1]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = r[k] | 0xFF000000u;
+    } else if (kFormat == 83) {
+        u32 r[16], g[16];
+        decode_alpha(r, w[0], w[1]);
+        decode_alpha(g, w[2], w[3]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = r[k] | (g[k] << 8) | 0xFF000000u;
+    } else decode_bc7(px, w);
+}
+
+#if defined(__CUDACC__)
+// dst rows: `stride` bytes apart, texel (x, y) at dst + y*stride + x*texel_bytes
+template <int kFormat, bool kVec16>
+__global__ void __launch_bounds__(128) decode_kernel(const uint8_t* __restrict__ blocks, uint8_t* __restrict__ dst, int width,
+                                                     int height, long long stride)
+{
+    const int bw = width >> 2, bh = height >> 2;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)bw * bh) return;
+    const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
+    u32 w[4];
+    if (kFormat == 71 || kFormat == 80) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(blocks) + id);
+        w[0] = v.x; w[1] = v.y; w[2] = w[3] = 0u;
+    } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(blocks) + id);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    if (kFormat == 95) {
+        u32 px[16][2];
+        decode_bc6h(px, w);
+        uint8_t* row = dst + (long long)(4 * by) * stride + (long long)bx * 32;
+#pragma unroll
+        for (int y = 0; y < 4; y++, row += stride) {
+            if (kVec16) {
+                reinterpret_cast<uint4*>(row)[0] = make_uint4(px[4 * y][0], px[4 * y][1], px[4 * y + 1][0], px[4 * y + 1][1]);
+                reinterpret_cast<uint4*>(row)[1] = make_uint4(px[4 * y + 2][0], px[4 * y + 2][1], px[4 * y + 3][0], px[4 * y + 3][1]);
+            } else {
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    reinterpret_cast<u32*>(row)[2 * x] = px[4 * y + x][0];
+                    reinterpret_cast<u32*>(row)[2 * x + 1] = px[4 * y + x][1];
+                }
+            }
+        }
+    } else {
+        u32 px[16];
+        decode_block_rgba8<kFormat>(px, w);
+        uint8_t* row = dst + (long long)(4 * by) * stride + (long long)bx * 16;
+#pragma unroll
+        for (int y = 0; y < 4; y++, row += stride) {
+            if (kVec16) *reinterpret_cast<uint4*>(row) = make_uint4(px[4 * y], px[4 * y + 1], px[4 * y + 2], px[4 * y + 3]);
+            else {
+#pragma unroll
+                for (int x = 0; x < 4; x++) reinterpret_cast<u32*>(row)[x] = px[4 * y + x];
+            }
+        }
+    }
+}
+#endif
+
+}  // namespace itw

@@ -19,6 +19,7 @@
 #include "../../include/itw_bcn.h"
 #include "bc4_bc5.cuh"
 #include "mips.cuh"
+#include "decode.cuh"
 #include "itw_params.h"
 
 using namespace itw;
@@ -249,6 +250,70 @@ int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* se
     return 0;
 }
 
+
+// ---- decoders (decode.cuh): blocks -> RGBA8 (BC1/3/4/5/7) or RGBA16F (BC6H) surface; either side host or device ----
+template <int kFormat>
+void launch_decode_as(bool vec16, unsigned grid, cudaStream_t s, const uint8_t* blocks, uint8_t* dst, int w, int h, long long stride)
+{
+    if (vec16) decode_kernel<kFormat, true><<<grid, 128, 0, s>>>(blocks, dst, w, h, stride);
+    else       decode_kernel<kFormat, false><<<grid, 128, 0, s>>>(blocks, dst, w, h, stride);
+}
+int launch_decode(int format, const uint8_t* d_blocks, uint8_t* d_dst, int w, int h, long long stride, cudaStream_t s)
+{
+    const long long nblocks = (long long)(w >> 2) * (h >> 2);
+    const unsigned grid = (unsigned)((nblocks + 127) / 128);
+    const bool vec16 = ((reinterpret_cast<uintptr_t>(d_dst) | (uintptr_t)stride) & 15u) == 0;
+    switch (format) {
+        case ITW_FORMAT_BC1: launch_decode_as<ITW_FORMAT_BC1>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
+        case ITW_FORMAT_BC3: launch_decode_as<ITW_FORMAT_BC3>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
+        case ITW_FORMAT_BC4: launch_decode_as<ITW_FORMAT_BC4>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
+        case ITW_FORMAT_BC5: launch_decode_as<ITW_FORMAT_BC5>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
+        case ITW_FORMAT_BC6H: launch_decode_as<ITW_FORMAT_BC6H>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
+        case ITW_FORMAT_BC7: launch_decode_as<ITW_FORMAT_BC7>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
+        default: return fail("unknown format");
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    ITW_CUDA(cudaGetLastError());
+    return 0;
+}
+int decode_any(int format, const uint8_t* blocks, const rgba_surface* dst)
+{
+    tls.err.clear();
+    FormatInfo f;
+    if (!format_info(format, f)) return fail("unknown format");
+    if (check_surface(dst, f)) return -1;
+    if (!blocks) return fail("null blocks");
+    if (ensure_ctx()) return -1;
+    ThreadCtx& c = tls;
+    const size_t row_bytes = (size_t)dst->width * f.texel_bytes;
+    const size_t in_bytes = (size_t)(dst->width >> 2) * (dst->height >> 2) * f.bpb;
+    const bool src_dev = is_device_pointer(blocks), dst_dev = is_device_pointer(dst->ptr);
+    cudaStream_t s = (src_dev || dst_dev) ? cudaStreamLegacy : c.stream;       // same ordering rule as encode_any
+    const uint8_t* d_blocks = blocks;
+    if (!src_dev || (reinterpret_cast<uintptr_t>(blocks) & 15u)) {
+        if (grow(c.d_in, c.d_in_cap, in_bytes)) return -1;
+        ITW_CUDA(cudaMemcpyAsync(c.d_in, blocks, in_bytes, src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        d_blocks = c.d_in;
+    }
+    uint8_t* d_dst = dst->ptr;
+    long long stride = dst->stride;
+    const bool dst_ok = dst_dev && (((uintptr_t)dst->ptr | (uintptr_t)dst->stride) & 3u) == 0;
+    if (!dst_ok) {
+        if (grow(c.d_out, c.d_out_cap, row_bytes * dst->height)) return -1;
+        d_dst = c.d_out;
+        stride = (long long)row_bytes;
+    }
+    ITW_CUDA(cudaEventRecord(c.ev0, s));
+    if (launch_decode(format, d_blocks, d_dst, dst->width, dst->height, stride, s)) return -1;
+    ITW_CUDA(cudaEventRecord(c.ev1, s));
+    c.timed = true;
+    if (!dst_ok)
+        ITW_CUDA(cudaMemcpy2DAsync(dst->ptr, (size_t)dst->stride, d_dst, row_bytes, row_bytes, (size_t)dst->height,
+                                   dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    ITW_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -299,6 +364,8 @@ int itw_encode_device(int format, const rgba_surface* src, uint8_t* dst, const v
     SurfaceView v{src->ptr, src->width, src->height, src->stride};
     return launch(format, v, dst, settings, static_cast<cudaStream_t>(cuda_stream));
 }
+
+int itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst) { return decode_any(format, blocks, dst); }
 
 int itw_encode_batch(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings)
 {

@@ -10,6 +10,7 @@
 #include "../../intel-texture-works-plugin_b200/csrc/bc4_bc5.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/itw_params.h"
 #include "../../intel-texture-works-plugin_b200/csrc/mips.cuh"
+#include "../../intel-texture-works-plugin_b200/csrc/decode.cuh"
 
 using namespace itw;
 
@@ -26,6 +27,27 @@ static void per_block(const rgba_surface* src, uint8_t* dst, int bpb, F f)
             fetch_rows_rgba8<false>(tex, s, bx, by);
             f(tex, out);
             memcpy(dst + ((size_t)by * bw + bx) * bpb, out, bpb);
+        }
+}
+
+// block decoders (csrc/decode.cuh), block by block through the kernel's own per-block routines
+template <int kFormat>
+static void emu_decode_as(const uint8_t* blocks, uint8_t* dst, int w, int h, int stride, int bpb)
+{
+    const int bw = w / 4, bh = h / 4;
+    for (int by = 0; by < bh; by++)
+        for (int bx = 0; bx < bw; bx++) {
+            u32 wd[4] = {0, 0, 0, 0};
+            memcpy(wd, blocks + ((size_t)by * bw + bx) * bpb, bpb);
+            if (kFormat == 95) {
+                u32 px[16][2];
+                decode_bc6h(px, wd);
+                for (int k = 0; k < 16; k++) memcpy(dst + (size_t)(4 * by + k / 4) * stride + (size_t)(4 * bx + k % 4) * 8, px[k], 8);
+            } else {
+                u32 px[16];
+                decode_block_rgba8<kFormat>(px, wd);
+                for (int k = 0; k < 16; k++) memcpy(dst + (size_t)(4 * by + k / 4) * stride + (size_t)(4 * bx + k % 4) * 4, &px[k], 4);
+            }
         }
 }
 
@@ -69,6 +91,18 @@ void emu_mip_level(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst
 {
     for (int y = 0; y < ph; y++)
         for (int x = 0; x < pw; x++) reinterpret_cast<u32*>(dst + (size_t)y * pw * 4)[x] = mip_texel(src, sw, sh, sstride, dw, dh, x, y);
+}
+int emu_itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst)
+{
+    switch (format) {
+        case 71: emu_decode_as<71>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 8); return 0;
+        case 77: emu_decode_as<77>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
+        case 80: emu_decode_as<80>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 8); return 0;
+        case 83: emu_decode_as<83>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
+        case 95: emu_decode_as<95>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
+        case 98: emu_decode_as<98>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
+        default: return -1;
+    }
 }
 // the product's profile tables (csrc/itw_params.h), exported so the emulation is self-contained
 #define EMU_BC7(name, row) void emu_GetProfile_##name(bc7_enc_settings* s) { bc7_fill_profile(s, row); }
