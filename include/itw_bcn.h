@@ -208,6 +208,40 @@ size_t itw_dds_encode_texture(const itw_dds_desc* desc, const rgba_surface* tops
  * ------------------------------------------------------------------------------------------- */
 int itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 6 -- pixel-format front end and the image-level entry: what the plug-in
+ * does between Photoshop's buffer and CompressBlocks*:
+ *   CopyDataForEncoding (IntelPlugin.cpp:85-181) -> ConvertToBC{,4or5,6}From{8,16,32}Bit (:291-433,
+ *   :741-810) with the scalar rules of IntelPlugin.h:41-96; FlipXYChannelNormalMap (:1504-1546);
+ *   NormalizeNormalMapChain (:1551-1612); DoPaddingToMultiplesOf4 (:892-928).
+ * All of it is per-texel work, fused here into ONE bandwidth-bound pass (the padding is a
+ * coordinate clamp), optionally followed by the encoder without leaving the GPU.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct itw_pixel_source {  /* Photoshop's FormatRecord as the converters read it */
+    const void* data;              /* interleaved: element (x, y, c) at row y, index x*planes + c   */
+    int32_t width, height;         /* texels; need NOT be multiples of 4                            */
+    int32_t planes;                /* channels per texel in `data`, 1..4 (hiPlane - loPlane + 1)    */
+    int32_t depth;                 /* 8; 16 = Photoshop's 0..32768 integers; 32 = float, gamma 1.0   */
+    int64_t row_bytes;             /* bytes between rows; 0 = tightly packed (the plug-in's case)    */
+} itw_pixel_source;
+enum {
+    ITW_FRONT_HAS_ALPHA = 1,   /* plane 3 is alpha (else alpha = 255 / 1.0); needs planes == 4          */
+    ITW_FRONT_GAMMA = 2,       /* 32-bit LDR only: v^(1/2.2) before the byte conversion (IntelPlugin.h:71) */
+    ITW_FRONT_FLIP_X = 4,      /* normal maps: r = 255 - r   /  half(1 - r)                              */
+    ITW_FRONT_FLIP_Y = 8,      /* normal maps: g = 255 - g   /  half(1 - g)                              */
+    ITW_FRONT_NORMALIZE = 16   /* normal maps: rgb re-normalised around 128 (LDR) / to unit length (HDR) */
+};
+/* Convert `src` for encoding to `format` (ITW_FORMAT_*): BC6H -> RGBA16F texels, everything else ->
+ * RGBA8; missing planes are 0 (BC4/BC5: a copy of plane 0).  dst->width/height must be the source
+ * size or that size rounded up to multiples of 4 (edge texels are replicated).  Either side may be
+ * host or device memory; synchronous.  Returns 0 on success. */
+int itw_convert_pixels(int format, const itw_pixel_source* src, uint32_t flags, const rgba_surface* dst);
+/* The image-level entry (the seam of CompressImageST, win32Threads.h:57-58, moved above the
+ * conversion): convert + pad + encode in one call; `dst_blocks` receives ((w+3)/4)*((h+3)/4)
+ * blocks.  `settings` as for itw_encode_device.  Returns 0 on success. */
+int itw_encode_pixels(int format, const itw_pixel_source* src, uint32_t flags, const void* settings,
+                      uint8_t* dst_blocks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,8 +45,16 @@ EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "Comp
             "itw_encode_batch", "itw_set_device", "itw_get_last_error", "itw_kernel_launch_count",
             "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
             "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file",
-            "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture", "itw_decode"]
+            "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture", "itw_decode", "itw_convert_pixels", "itw_encode_pixels"]
            + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
+
+
+class PixelSource(ctypes.Structure):          # include/itw_bcn.h section 6
+    _fields_ = [("data", ctypes.c_void_p), ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("planes", ctypes.c_int32),
+                ("depth", ctypes.c_int32), ("row_bytes", ctypes.c_int64)]
+
+
+FRONT_HAS_ALPHA, FRONT_GAMMA, FRONT_FLIP_X, FRONT_FLIP_Y, FRONT_NORMALIZE = 1, 2, 4, 8, 16
 
 
 class DdsDesc(ctypes.Structure):              # include/itw_bcn.h section 3
@@ -120,6 +128,27 @@ class EncoderApi:
         if rc != 0:
             raise RuntimeError("itw_decode failed")
 
+    def convert_pixels(self, fmt, pixels, flags=0, pad=True):
+        """itw_convert_pixels: host numpy H x W x planes array (uint8 / uint16 / float32) -> RGBA8 / RGBA16F image."""
+        h, w, planes = pixels.shape
+        pixels = np.ascontiguousarray(pixels)
+        texel = FORMATS[fmt][2]
+        dw, dh = ((w + 3) & ~3, (h + 3) & ~3) if pad else (w, h)
+        img = np.zeros((dh, dw, 4), np.uint16 if texel == 8 else np.uint8)
+        src = PixelSource(pixels.ctypes.data, w, h, planes, pixels.itemsize * 8, 0)
+        self.convert_pixels_raw(fmt, src, flags, img.ctypes.data, dw, dh, img.strides[0])
+        return img
+
+    def convert_pixels_raw(self, fmt, src, flags, dst_ptr, width, height, stride):
+        f = self.fn("itw_convert_pixels")
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.POINTER(PixelSource), ctypes.c_uint32, ctypes.POINTER(RgbaSurface)]
+        surf = RgbaSurface(dst_ptr, width, height, stride)
+        rc = f(FORMATS[fmt][0], ctypes.byref(src), flags, ctypes.byref(surf))
+        self.check()
+        if rc != 0:
+            raise RuntimeError("itw_convert_pixels failed")
+
     def encode_raw(self, fmt, ptr, width, height, stride, dst_ptr, settings=None):
         """CompressBlocks<fmt> on raw addresses (host or device)."""
         self._call(fmt, RgbaSurface(ptr, width, height, stride), dst_ptr, settings)
@@ -162,6 +191,25 @@ class ItwBcn(EncoderApi):
         L.itw_dds_encode_texture.restype = ctypes.c_size_t
         L.itw_dds_encode_texture.argtypes = [ctypes.POINTER(DdsDesc), ctypes.POINTER(RgbaSurface), ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_size_t]
+
+    def encode_pixels(self, fmt, pixels, flags=0, settings=None):
+        """itw_encode_pixels: host numpy H x W x planes array -> blocks of the padded image."""
+        h, w, planes = pixels.shape
+        pixels = np.ascontiguousarray(pixels)
+        out = np.zeros(((w + 3) // 4) * ((h + 3) // 4) * FORMATS[fmt][1], np.uint8)
+        src = PixelSource(pixels.ctypes.data, w, h, planes, pixels.itemsize * 8, 0)
+        self.encode_pixels_raw(fmt, src, flags, out.ctypes.data, settings)
+        return out
+
+    def encode_pixels_raw(self, fmt, src, flags, dst_ptr, settings=None):
+        f = self.lib.itw_encode_pixels
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.POINTER(PixelSource), ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+        sp = ctypes.cast(ctypes.byref(settings), ctypes.c_void_p) if settings is not None else None
+        rc = f(FORMATS[fmt][0], ctypes.byref(src), flags, sp, ctypes.c_void_p(dst_ptr))
+        self.check()
+        if rc != 0:
+            raise RuntimeError("itw_encode_pixels failed")
 
     def last_error(self):
         return self.lib.itw_get_last_error().decode()

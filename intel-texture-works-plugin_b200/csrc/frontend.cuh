@@ -1,0 +1,152 @@
+// frontend.cuh -- pixel-format front end: Photoshop's interleaved 8/16/32-bit planes -> the
+// RGBA8 / RGBA16F surface the encoders read, in ONE pass per destination texel.  Restates, per texel,
+//   IntelPlugin.h:41-96          FloatToByte, ConvertTo8Bit x3, ConvertTo16Bit x3                     (cited IPh:line)
+//   IntelPlugin.cpp:291-433, :741-810   ConvertToBC{,4or5,6}From{8,16,32}Bit                          (cited IP:line)
+//   IntelPlugin.cpp:1504-1546    FlipXYChannelNormalMap
+//   IntelPlugin.cpp:1551-1612    NormalizeNormalMapChain
+//   IntelPlugin.cpp:892-928      DoPaddingToMultiplesOf4 -- here a coordinate clamp (replicated edge texels)
+// The reference runs these as four whole-image passes on the host; every one of them is per-texel, so the order
+// convert -> flip -> normalise -> pad collapses into a single bandwidth-bound kernel.
+//
+// Half conversion: the plug-in calls DirectXMath's XMConvertFloatToHalf / XMConvertHalfToFloat (IPh:31-39), which
+// is Windows SDK code and not in the reference tree.  front_half_from_float / front_float_from_half restate the
+// published DirectXMath 3.06 scalar algorithm (the SDK generation of the reference's toolset): RNE on the rebiased
+// pattern, |x| > 0x47FFEFFF -> 0x7FFF, truncating denormal shift, exponent 31 decoded as an ordinary binade.
+// Outside the normal-half range other DirectXMath versions differ: unpinned there.
+#pragma once
+#include "itw_device.cuh"
+
+namespace itw {
+
+struct FrontParams {
+    const uint8_t* data;
+    int width, height;        // source texels
+    int planes, depth;        // 1..4; 8 / 16 / 32
+    long long row_bytes;
+    int family;               // 0 colour (BC1/3/7), 1 BC4/BC5 (missing planes copy plane 0), 2 HDR (BC6H -> RGBA16F)
+    u32 flags;                // ITW_FRONT_*
+};
+constexpr u32 kFrontAlpha = 1, kFrontGamma = 2, kFrontFlipX = 4, kFrontFlipY = 8, kFrontNormalize = 16;
+
+ITW_HD u32 front_half_from_float(float value)
+{
+    u32 bits = float_bits(value);
+    const u32 sign = (bits & 0x80000000u) >> 16;
+    bits &= 0x7FFFFFFFu;
+    if (bits > 0x47FFEFFFu) return 0x7FFFu | sign;
+    if (bits < 0x38800000u) {
+        const u32 shift = 113u - (bits >> 23);
+        bits = (shift < 32u) ? ((0x800000u | (bits & 0x7FFFFFu)) >> shift) : 0u;
+    } else bits += 0xC8000000u;
+    return (((bits + 0x0FFFu + ((bits >> 13) & 1u)) >> 13) & 0x7FFFu) | sign;
+}
+ITW_HD float front_float_from_half(u32 h)
+{
+    u32 mant = h & 0x3FFu, exp;
+    if (h & 0x7C00u) exp = (h >> 10) & 31u;
+    else if (mant) {
+        exp = 1u;
+        do { exp--; mant <<= 1; } while (!(mant & 0x400u));
+        mant &= 0x3FFu;
+    } else exp = (u32)-112;
+    return bits_float(((h & 0x8000u) << 16) | ((exp + 112u) << 23) | (mant << 13));
+}
+// FloatToByte, IPh:41-48; the (unsigned char) of an out-of-range double is x86's cvttsd2si low byte: NaN -> 0
+ITW_HD u32 front_byte(double v)
+{
+    if (v > 1.0) return 255u;
+    if (v < 0.0) return 0u;
+    if (!(v == v)) return 0u;
+    return (u32)(int)(v * 255.0) & 255u;
+}
+// one source element -> byte; IPh:56-76.  16-bit: FloatToByte(v / 32768.0) = floor(v * 255 / 32768) exactly
+ITW_HD u32 front_ldr_element(const uint8_t* p, int depth, bool gamma)
+{
+    if (depth == 8) return *p;
+    if (depth == 16) {
+        const u32 v = *reinterpret_cast<const uint16_t*>(p);
+        return (v > 32768u) ? 255u : ((v * 255u) >> 15);
+    }
+    double v = (double)*reinterpret_cast<const float*>(p);
+    if (gamma) v = pow(v, 1 / 2.2);
+    return front_byte(v);
+}
+// one source element -> half bits; IPh:79-96
+ITW_HD u32 front_hdr_element(const uint8_t* p, int depth)
+{
+    if (depth == 8) return front_half_from_float((float)*p / 255.0f);
+    if (depth == 16) return front_half_from_float((float)((double)*reinterpret_cast<const uint16_t*>(p) / 32768.0));
+    return front_half_from_float(*reinterpret_cast<const float*>(p));
+}
+
+// Destination texel (x, y) -> out[0] (RGBA8) or out[0..1] (RGBA16F: r | g << 16, b | a << 16)
+ITW_HD void front_texel(u32 (&out)[2], const FrontParams& P, int x, int y)
+{
+    const int sx = (x < P.width) ? x : P.width - 1, sy = (y < P.height) ? y : P.height - 1;      // IP:892-928
+    const int esize = P.depth >> 3;
+    const uint8_t* px = P.data + (long long)sy * P.row_bytes + (long long)sx * P.planes * esize;
+    const bool alpha = (P.flags & kFrontAlpha) != 0;
+    if (P.family == 2) {
+        // IP:291-366.  The 32-bit variant reads alpha from plane 2 (IP:361) -- reference behaviour, kept.
+        u32 r = front_hdr_element(px, P.depth);
+        u32 g = (P.planes > 1) ? front_hdr_element(px + esize, P.depth) : 0u;
+        u32 b = (P.planes > 2) ? front_hdr_element(px + 2 * esize, P.depth) : 0u;
+        const u32 a = alpha ? front_hdr_element(px + ((P.depth == 32) ? 2 : 3) * esize, P.depth) : 0x3C00u;
+        if (P.flags & (kFrontFlipX | kFrontFlipY)) {                                              // IP:1531-1542
+            const float fr = front_float_from_half(r), fg = front_float_from_half(g);
+            if (P.flags & kFrontFlipX) r = front_half_from_float(1.0f - fr);
+            if (P.flags & kFrontFlipY) g = front_half_from_float(1.0f - fg);
+        }
+        if (P.flags & kFrontNormalize) {                                                          // IP:1586-1607
+            const float fr = front_float_from_half(r), fg = front_float_from_half(g), fb = front_float_from_half(b);
+            float m = sqrtf(fr * fr + fg * fg + fb * fb);
+            if (m > 0.0f) {
+                m = 1.0f / m;
+                r = front_half_from_float(fr * m);
+                g = front_half_from_float(fg * m);
+                b = front_half_from_float(fb * m);
+            } else { r = 0u; g = 0u; b = 0x3C00u; }
+        }
+        out[0] = r | (g << 16);
+        out[1] = b | (a << 16);
+        return;
+    }
+    // IP:741-810 (colour: missing planes are 0) and IP:368-433 (BC4/BC5: missing planes copy plane 0)
+    const bool gamma = (P.flags & kFrontGamma) != 0;
+    u32 r = front_ldr_element(px, P.depth, gamma);
+    const u32 missing = (P.family == 1) ? r : 0u;
+    u32 g = (P.planes > 1) ? front_ldr_element(px + esize, P.depth, gamma) : missing;
+    u32 b = (P.planes > 2) ? front_ldr_element(px + 2 * esize, P.depth, gamma) : missing;
+    const u32 a = alpha ? front_ldr_element(px + 3 * esize, P.depth, gamma) : 255u;
+    if (P.flags & kFrontFlipX) r = 255u - r;                                                       // IP:1519-1527
+    if (P.flags & kFrontFlipY) g = 255u - g;
+    if (P.flags & kFrontNormalize) {                                                               // IP:1565-1584
+        const float fr = (float)((int)r - 128), fg = (float)((int)g - 128), fb = (float)((int)b - 128);
+        float m = sqrtf(fr * fr + fg * fg + fb * fb);
+        if (m > 0.0f) {
+            m = 127.0f / m;
+            r = (u32)(int)(fr * m + 128.0f) & 255u;
+            g = (u32)(int)(fg * m + 128.0f) & 255u;
+            b = (u32)(int)(fb * m + 128.0f) & 255u;
+        } else { r = 128u; g = 128u; b = 255u; }
+    }
+    out[0] = r | (g << 8) | (b << 16) | (a << 24);
+    out[1] = 0u;
+}
+
+#if defined(__CUDACC__)
+// One thread per destination texel: a warp writes 128 (RGBA8) or 256 (RGBA16F) contiguous bytes and reads
+// 32 * planes * depth/8 contiguous source bytes.  Algorithmic traffic per texel: planes*depth/8 B in, 4 / 8 B out.
+__global__ void __launch_bounds__(256) front_kernel(FrontParams P, uint8_t* __restrict__ dst, int dst_w, int dst_h, long long dst_stride)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst_w || y >= dst_h) return;
+    u32 out[2];
+    front_texel(out, P, x, y);
+    uint8_t* row = dst + (long long)y * dst_stride;
+    if (P.family == 2) *reinterpret_cast<uint2*>(row + (long long)x * 8) = make_uint2(out[0], out[1]);
+    else *reinterpret_cast<u32*>(row + (long long)x * 4) = out[0];
+}
+#endif
+
+}  // namespace itw

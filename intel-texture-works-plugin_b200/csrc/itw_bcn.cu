@@ -20,6 +20,7 @@
 #include "bc4_bc5.cuh"
 #include "mips.cuh"
 #include "decode.cuh"
+#include "frontend.cuh"
 #include "itw_params.h"
 
 using namespace itw;
@@ -36,6 +37,7 @@ struct ThreadCtx {
     bool timed = false;
     uint8_t* d_in = nullptr;  size_t d_in_cap = 0;
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+    uint8_t* d_mid = nullptr; size_t d_mid_cap = 0;      // itw_encode_pixels: the converted surface between the two kernels
     int sm_count = 0;
     std::string err;
     // itw_encode_batch: three copy/compute lanes so that H2D of tile i+1, the kernel of tile i and
@@ -52,7 +54,8 @@ struct ThreadCtx {
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        cudaFree(d_in); cudaFree(d_out);
+        cudaFree(d_in); cudaFree(d_out); cudaFree(d_mid);
+        d_mid = nullptr; d_mid_cap = 0;
         for (auto& l : lanes) { if (l.stream) cudaStreamDestroy(l.stream); cudaFree(l.d_in); cudaFree(l.d_out); l = Lane(); }
         stream = nullptr; ev0 = ev1 = nullptr; d_in = d_out = nullptr; d_in_cap = d_out_cap = 0;
         cudaGetLastError();
@@ -314,6 +317,120 @@ int decode_any(int format, const uint8_t* blocks, const rgba_surface* dst)
     return 0;
 }
 
+
+// ---- pixel-format front end (frontend.cuh) ----
+int front_params(FrontParams& P, int format, const itw_pixel_source* src, uint32_t flags)
+{
+    FormatInfo f;
+    if (!format_info(format, f)) return fail("unknown format");
+    if (!src || !src->data) return fail("null pixel source");
+    if (src->width <= 0 || src->height <= 0) return fail("pixel source: width/height must be positive");
+    if (src->planes < 1 || src->planes > 4) return fail("pixel source: planes must be 1..4");
+    if (src->depth != 8 && src->depth != 16 && src->depth != 32) return fail("pixel source: depth must be 8, 16 or 32");
+    if (flags & ~31u) return fail("unknown front-end flag");
+    const int esize = src->depth / 8;
+    const long long tight = (long long)src->width * src->planes * esize;
+    const long long row_bytes = src->row_bytes ? src->row_bytes : tight;
+    if (row_bytes < tight) return fail("pixel source: row_bytes smaller than a texel row");
+    if ((reinterpret_cast<uintptr_t>(src->data) | (uintptr_t)row_bytes) & (uintptr_t)(esize - 1)) return fail("pixel source: misaligned elements");
+    const int family = (format == ITW_FORMAT_BC6H) ? 2 : ((format == ITW_FORMAT_BC4 || format == ITW_FORMAT_BC5) ? 1 : 0);
+    if (flags & ITW_FRONT_HAS_ALPHA) {
+        // the converters read plane 3 (IntelPlugin.cpp:310, :758 ...); the 32-bit HDR one reads plane 2 (:361)
+        const int need = (family == 2 && src->depth == 32) ? 3 : 4;
+        if (src->planes < need) return fail("ITW_FRONT_HAS_ALPHA needs an alpha plane in the source");
+    }
+    P = FrontParams{static_cast<const uint8_t*>(src->data), src->width, src->height, src->planes, src->depth, row_bytes, family, flags};
+    return 0;
+}
+int launch_front(const FrontParams& P, uint8_t* d_dst, int dw, int dh, long long dstride, cudaStream_t s)
+{
+    dim3 grid((unsigned)((dw + 255) / 256), (unsigned)dh);
+    if (dh > 65535) return fail("front end: height above 65535");
+    front_kernel<<<grid, 256, 0, s>>>(P, d_dst, dw, dh, dstride);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    ITW_CUDA(cudaGetLastError());
+    return 0;
+}
+// Stage a host pixel source in d_in (tight rows); P.data / P.row_bytes are redirected.
+int stage_pixels(ThreadCtx& c, FrontParams& P, cudaStream_t s)
+{
+    const size_t tight = (size_t)P.width * P.planes * (P.depth / 8);
+    if (grow(c.d_in, c.d_in_cap, tight * P.height)) return -1;
+    ITW_CUDA(cudaMemcpy2DAsync(c.d_in, tight, P.data, (size_t)P.row_bytes, tight, (size_t)P.height, cudaMemcpyHostToDevice, s));
+    P.data = c.d_in;
+    P.row_bytes = (long long)tight;
+    return 0;
+}
+int convert_any(int format, const itw_pixel_source* src, uint32_t flags, const rgba_surface* dst)
+{
+    tls.err.clear();
+    FrontParams P;
+    if (front_params(P, format, src, flags)) return -1;
+    if (!dst || !dst->ptr) return fail("null surface");
+    const int texel = (P.family == 2) ? 8 : 4;
+    const int pw = (P.width + 3) & ~3, ph = (P.height + 3) & ~3;
+    if (!((dst->width == P.width && dst->height == P.height) || (dst->width == pw && dst->height == ph)))
+        return fail("itw_convert_pixels: dst must have the source size or that size rounded up to multiples of 4");
+    if ((long long)dst->stride < (long long)dst->width * texel) return fail("surface stride smaller than a texel row");
+    if (ensure_ctx()) return -1;
+    ThreadCtx& c = tls;
+    const bool src_dev = is_device_pointer(P.data), dst_dev = is_device_pointer(dst->ptr);
+    cudaStream_t s = (src_dev || dst_dev) ? cudaStreamLegacy : c.stream;
+    if (!src_dev && stage_pixels(c, P, s)) return -1;
+    uint8_t* d_dst = dst->ptr;
+    long long stride = dst->stride;
+    const bool dst_ok = dst_dev && (((uintptr_t)dst->ptr | (uintptr_t)dst->stride) & (uintptr_t)(texel - 1)) == 0;
+    const size_t row_bytes = (size_t)dst->width * texel;
+    if (!dst_ok) {
+        if (grow(c.d_out, c.d_out_cap, row_bytes * dst->height)) return -1;
+        d_dst = c.d_out;
+        stride = (long long)row_bytes;
+    }
+    ITW_CUDA(cudaEventRecord(c.ev0, s));
+    if (launch_front(P, d_dst, dst->width, dst->height, stride, s)) return -1;
+    ITW_CUDA(cudaEventRecord(c.ev1, s));
+    c.timed = true;
+    if (!dst_ok)
+        ITW_CUDA(cudaMemcpy2DAsync(dst->ptr, (size_t)dst->stride, d_dst, row_bytes, row_bytes, (size_t)dst->height,
+                                   dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    ITW_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+// convert + pad + encode; the intermediate surface never leaves the GPU
+int encode_pixels_any(int format, const itw_pixel_source* src, uint32_t flags, const void* settings, uint8_t* dst)
+{
+    tls.err.clear();
+    FrontParams P;
+    if (front_params(P, format, src, flags)) return -1;
+    if (!dst) return fail("null dst");
+    FormatInfo f;
+    format_info(format, f);
+    if (ensure_ctx()) return -1;
+    ThreadCtx& c = tls;
+    const int pw = (P.width + 3) & ~3, ph = (P.height + 3) & ~3;
+    const size_t mid_row = (size_t)pw * f.texel_bytes, out_bytes = (size_t)(pw >> 2) * (ph >> 2) * f.bpb;
+    const bool src_dev = is_device_pointer(P.data), dst_dev = is_device_pointer(dst);
+    cudaStream_t s = (src_dev || dst_dev) ? cudaStreamLegacy : c.stream;
+    if (!src_dev && stage_pixels(c, P, s)) return -1;
+    if (grow(c.d_mid, c.d_mid_cap, mid_row * ph)) return -1;
+    uint8_t* d_dst = dst;
+    const bool dst_ok = dst_dev && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    if (!dst_ok) {
+        if (grow(c.d_out, c.d_out_cap, out_bytes)) return -1;
+        d_dst = c.d_out;
+    }
+    ITW_CUDA(cudaEventRecord(c.ev0, s));
+    if (launch_front(P, c.d_mid, pw, ph, (long long)mid_row, s)) return -1;
+    const SurfaceView v{c.d_mid, pw, ph, (int)mid_row};
+    if (launch(format, v, d_dst, settings, s)) return -1;
+    ITW_CUDA(cudaEventRecord(c.ev1, s));
+    c.timed = true;
+    if (!dst_ok)
+        ITW_CUDA(cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    ITW_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -366,6 +483,11 @@ int itw_encode_device(int format, const rgba_surface* src, uint8_t* dst, const v
 }
 
 int itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst) { return decode_any(format, blocks, dst); }
+int itw_convert_pixels(int format, const itw_pixel_source* src, uint32_t flags, const rgba_surface* dst) { return convert_any(format, src, flags, dst); }
+int itw_encode_pixels(int format, const itw_pixel_source* src, uint32_t flags, const void* settings, uint8_t* dst_blocks)
+{
+    return encode_pixels_any(format, src, flags, settings, dst_blocks);
+}
 
 int itw_encode_batch(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings)
 {

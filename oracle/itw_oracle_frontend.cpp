@@ -1,0 +1,170 @@
+/*
+ * itw_oracle_frontend.cpp -- CPU ORACLE for the pixel-format front end.  TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * Restates, as the whole-image passes the plug-in runs on the host,
+ *   IntelPlugin.h:41-96                  FloatToByte, ConvertTo8Bit x3, ConvertTo16Bit x3     (cited IPh:line)
+ *   IntelPlugin.cpp:85-181               CopyDataForEncoding (dispatch on format / depth)      (cited IP:line)
+ *   IntelPlugin.cpp:291-433, :741-810    ConvertToBC{,4or5,6}From{8,16,32}Bit
+ *   IntelPlugin.cpp:1504-1546            FlipXYChannelNormalMap
+ *   IntelPlugin.cpp:1551-1612            NormalizeNormalMapChain
+ *   IntelPlugin.cpp:892-928              DoPaddingToMultiplesOf4
+ * Built into libitw_oracle.so by oracle/Makefile.  Only tests/ and __graft_entry__.smoke() may load it.
+ *
+ * PINNING.  tests/test_frontend.py compares this restatement byte for byte with oracle/_ref/libitw_ref_frontend.so,
+ * i.e. with the reference's OWN function bodies cut from IntelPlugin.h / IntelPlugin.cpp by oracle/build_ref_frontend.py,
+ * over every depth x plane count x format family x flag combination.  Two ingredients are NOT in the reference tree
+ * and are therefore unpinned beyond that build: DirectXMath's half conversions (restated here from the published
+ * DirectXMath 3.06 scalar source, see build_ref_frontend.py) and the C library's pow().
+ */
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../include/itw_bcn.h"
+
+namespace {
+
+uint16_t half_from_float(float value)                  // XMConvertFloatToHalf, DirectXMath 3.06 scalar path
+{
+    uint32_t bits;
+    memcpy(&bits, &value, 4);
+    const uint32_t sign = (bits & 0x80000000u) >> 16;
+    bits &= 0x7FFFFFFFu;
+    uint32_t result;
+    if (bits > 0x47FFEFFFu) result = 0x7FFFu;
+    else {
+        if (bits < 0x38800000u) {
+            const uint32_t shift = 113u - (bits >> 23);
+            bits = (shift < 32u) ? ((0x800000u | (bits & 0x7FFFFFu)) >> shift) : 0u;
+        } else bits += 0xC8000000u;
+        result = ((bits + 0x0FFFu + ((bits >> 13) & 1u)) >> 13) & 0x7FFFu;
+    }
+    return (uint16_t)(result | sign);
+}
+float float_from_half(uint16_t h)                      // XMConvertHalfToFloat, DirectXMath 3.06 scalar path
+{
+    uint32_t mant = h & 0x3FFu, exp;
+    if (h & 0x7C00u) exp = (h >> 10) & 31u;
+    else if (mant) {
+        exp = 1;
+        do { exp--; mant <<= 1; } while (!(mant & 0x400u));
+        mant &= 0x3FFu;
+    } else exp = (uint32_t)-112;
+    const uint32_t bits = ((uint32_t)(h & 0x8000u) << 16) | ((exp + 112u) << 23) | (mant << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+uint8_t float_to_byte(double v)                        // IPh:41-48; out-of-range cast = cvttsd2si low byte (NaN -> 0)
+{
+    if (v > 1) return 255;
+    if (v < 0) return 0;
+    if (v != v) return 0;
+    return (uint8_t)(int)(v * 255);
+}
+uint8_t to8(uint8_t v) { return v; }                                           // IPh:56-59
+uint8_t to8(uint16_t v) { return float_to_byte(v / 32768.0); }                 // IPh:60-66
+uint8_t to8(float v, bool gamma)                                               // IPh:67-76
+{
+    double d = v;
+    if (gamma) d = pow(d, 1 / 2.2);
+    return float_to_byte(d);
+}
+uint16_t to16(uint8_t v) { return half_from_float(v / 255.f); }                // IPh:79-82
+uint16_t to16(uint16_t v) { return half_from_float((float)(v / 32768.0)); }   // IPh:83-89
+uint16_t to16(float v) { return half_from_float(v); }                          // IPh:90-98
+
+template <class T>
+const T* element(const itw_pixel_source* s, long long row_bytes, int x, int y)
+{
+    return reinterpret_cast<const T*>(static_cast<const uint8_t*>(s->data) + y * row_bytes) + (long long)x * s->planes;
+}
+
+}  // namespace
+
+extern "C" int oracle_itw_convert_pixels(int format, const itw_pixel_source* s, uint32_t flags, const rgba_surface* dst)
+{
+    const int w = s->width, h = s->height, planes = s->planes;
+    const bool alpha = flags & ITW_FRONT_HAS_ALPHA, gamma = flags & ITW_FRONT_GAMMA;
+    const bool hdr = format == ITW_FORMAT_BC6H, copy0 = (format == ITW_FORMAT_BC4 || format == ITW_FORMAT_BC5);
+    const long long row_bytes = s->row_bytes ? s->row_bytes : (long long)w * planes * (s->depth / 8);
+    const int texel = hdr ? 8 : 4;
+    std::vector<uint8_t> top((size_t)w * h * texel);
+
+    // pass 1: CopyDataForEncoding, IP:85-181
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            if (hdr) {                                                         // IP:291-366
+                uint16_t* t = reinterpret_cast<uint16_t*>(top.data()) + ((size_t)y * w + x) * 4;
+                for (int c = 0; c < 4; c++) {
+                    // alpha: plane 3, except the 32-bit converter, which reads plane 2 (IP:361)
+                    const int sc = (c == 3 && s->depth == 32) ? 2 : c;
+                    const bool present = (c == 3) ? alpha : (c < planes);
+                    uint16_t v = (c == 3) ? half_from_float(1.f) : 0;
+                    if (present) {
+                        if (s->depth == 8) v = to16(element<uint8_t>(s, row_bytes, x, y)[sc]);
+                        else if (s->depth == 16) v = to16(element<uint16_t>(s, row_bytes, x, y)[sc]);
+                        else v = to16(element<float>(s, row_bytes, x, y)[sc]);
+                    }
+                    t[c] = v;
+                }
+            } else {                                                           // IP:741-810, :368-433
+                uint8_t* t = top.data() + ((size_t)y * w + x) * 4;
+                for (int c = 0; c < 4; c++) {
+                    const bool present = (c == 3) ? alpha : (c < planes);
+                    uint8_t v = (c == 3) ? 255 : (copy0 ? t[0] : 0);
+                    if (present) {
+                        if (s->depth == 8) v = to8(element<uint8_t>(s, row_bytes, x, y)[c]);
+                        else if (s->depth == 16) v = to8(element<uint16_t>(s, row_bytes, x, y)[c]);
+                        else v = to8(element<float>(s, row_bytes, x, y)[c], gamma);
+                    }
+                    t[c] = v;
+                }
+            }
+        }
+    // pass 2: FlipXYChannelNormalMap, IP:1504-1546
+    if (flags & (ITW_FRONT_FLIP_X | ITW_FRONT_FLIP_Y))
+        for (size_t i = 0; i < (size_t)w * h; i++) {
+            if (hdr) {
+                uint16_t* t = reinterpret_cast<uint16_t*>(top.data()) + i * 4;
+                const float r = float_from_half(t[0]), g = float_from_half(t[1]);
+                if (flags & ITW_FRONT_FLIP_X) t[0] = half_from_float(1.f - r);
+                if (flags & ITW_FRONT_FLIP_Y) t[1] = half_from_float(1.f - g);
+            } else {
+                uint8_t* t = top.data() + i * 4;
+                if (flags & ITW_FRONT_FLIP_X) t[0] = 255 - t[0];
+                if (flags & ITW_FRONT_FLIP_Y) t[1] = 255 - t[1];
+            }
+        }
+    // pass 3: NormalizeNormalMapChain, IP:1551-1612
+    if (flags & ITW_FRONT_NORMALIZE)
+        for (size_t i = 0; i < (size_t)w * h; i++) {
+            if (hdr) {
+                uint16_t* t = reinterpret_cast<uint16_t*>(top.data()) + i * 4;
+                const float r = float_from_half(t[0]), g = float_from_half(t[1]), b = float_from_half(t[2]);
+                float m = sqrtf(r * r + g * g + b * b);
+                if (m > 0) {
+                    m = 1.0f / m;
+                    t[0] = half_from_float(r * m); t[1] = half_from_float(g * m); t[2] = half_from_float(b * m);
+                } else { t[0] = half_from_float(0); t[1] = half_from_float(0); t[2] = half_from_float(1); }
+            } else {
+                uint8_t* t = top.data() + i * 4;
+                const float r = (float)(t[0] - 128), g = (float)(t[1] - 128), b = (float)(t[2] - 128);
+                float m = sqrtf(r * r + g * g + b * b);
+                if (m > 0) {
+                    m = 127 / m;
+                    t[0] = (uint8_t)(int)(r * m + 128); t[1] = (uint8_t)(int)(g * m + 128); t[2] = (uint8_t)(int)(b * m + 128);
+                } else { t[0] = 128; t[1] = 128; t[2] = 255; }
+            }
+        }
+    // pass 4: DoPaddingToMultiplesOf4, IP:892-928 (or a plain copy when dst has the source size)
+    for (int y = 0; y < dst->height; y++) {
+        const int sy = y < h ? y : h - 1;
+        for (int x = 0; x < dst->width; x++) {
+            const int sx = x < w ? x : w - 1;
+            memcpy(dst->ptr + (size_t)y * dst->stride + (size_t)x * texel, top.data() + ((size_t)sy * w + sx) * texel, texel);
+        }
+    }
+    return 0;
+}

@@ -11,6 +11,7 @@
 #include "../../intel-texture-works-plugin_b200/csrc/itw_params.h"
 #include "../../intel-texture-works-plugin_b200/csrc/mips.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/decode.cuh"
+#include "../../intel-texture-works-plugin_b200/csrc/frontend.cuh"
 
 using namespace itw;
 
@@ -103,6 +104,21 @@ int emu_itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst)
         case 98: emu_decode_as<98>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
         default: return -1;
     }
+}
+// pixel-format front end (csrc/frontend.cuh), texel by texel through the kernel's own per-texel routine
+int emu_itw_convert_pixels(int format, const itw_pixel_source* src, uint32_t flags, const rgba_surface* dst)
+{
+    const int family = (format == 95) ? 2 : ((format == 80 || format == 83) ? 1 : 0);
+    const long long row_bytes = src->row_bytes ? src->row_bytes : (long long)src->width * src->planes * (src->depth / 8);
+    const FrontParams P{static_cast<const uint8_t*>(src->data), src->width, src->height, src->planes, src->depth, row_bytes, family, flags};
+    const int texel = (family == 2) ? 8 : 4;
+    for (int y = 0; y < dst->height; y++)
+        for (int x = 0; x < dst->width; x++) {
+            u32 out[2];
+            front_texel(out, P, x, y);
+            memcpy(dst->ptr + (size_t)y * dst->stride + (size_t)x * texel, out, texel);
+        }
+    return 0;
 }
 // the product's profile tables (csrc/itw_params.h), exported so the emulation is self-contained
 #define EMU_BC7(name, row) void emu_GetProfile_##name(bc7_enc_settings* s) { bc7_fill_profile(s, row); }

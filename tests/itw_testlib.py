@@ -44,6 +44,30 @@ def ref():
 
 
 @functools.lru_cache(None)
+def ref_frontend():
+    """The reference's own front-end function bodies (oracle/build_ref_frontend.py) as a ctypes library; None if unavailable."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import build_ref_frontend
+        try:
+            path = build_ref_frontend.build(verbose=False)
+        except FileNotFoundError:
+            return None
+    finally:
+        sys.path.pop(0)
+    lib = ctypes.CDLL(path)
+    lib.ref_convert_pixels.restype = ctypes.c_int
+    lib.ref_convert_pixels.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_uint, ctypes.c_void_p]
+    lib.ref_float_to_half.restype = ctypes.c_ushort
+    lib.ref_float_to_half.argtypes = [ctypes.c_float]
+    lib.ref_half_to_float.restype = ctypes.c_float
+    lib.ref_half_to_float.argtypes = [ctypes.c_ushort]
+    return lib
+
+
+@functools.lru_cache(None)
 def emu():
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     try:
