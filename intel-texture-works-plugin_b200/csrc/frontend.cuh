@@ -59,39 +59,40 @@ ITW_HD u32 front_byte(double v)
     if (!(v == v)) return 0u;
     return (u32)(int)(v * 255.0) & 255u;
 }
-// one source element -> byte; IPh:56-76.  16-bit: FloatToByte(v / 32768.0) = floor(v * 255 / 32768) exactly
-ITW_HD u32 front_ldr_element(const uint8_t* p, int depth, bool gamma)
+// one source element (raw bits: the 8/16-bit integer, or the float's bit pattern) -> byte; IPh:56-76.
+// 16-bit: FloatToByte(v / 32768.0) = floor(v * 255 / 32768) exactly
+ITW_HD u32 front_ldr_value(u32 raw, int depth, bool gamma)
 {
-    if (depth == 8) return *p;
-    if (depth == 16) {
-        const u32 v = *reinterpret_cast<const uint16_t*>(p);
-        return (v > 32768u) ? 255u : ((v * 255u) >> 15);
-    }
-    double v = (double)*reinterpret_cast<const float*>(p);
+    if (depth == 8) return raw;
+    if (depth == 16) return (raw > 32768u) ? 255u : ((raw * 255u) >> 15);
+    double v = (double)bits_float(raw);
     if (gamma) v = pow(v, 1 / 2.2);
     return front_byte(v);
 }
 // one source element -> half bits; IPh:79-96
-ITW_HD u32 front_hdr_element(const uint8_t* p, int depth)
+ITW_HD u32 front_hdr_value(u32 raw, int depth)
 {
-    if (depth == 8) return front_half_from_float((float)*p / 255.0f);
-    if (depth == 16) return front_half_from_float((float)((double)*reinterpret_cast<const uint16_t*>(p) / 32768.0));
-    return front_half_from_float(*reinterpret_cast<const float*>(p));
+    if (depth == 8) return front_half_from_float((float)raw / 255.0f);
+    if (depth == 16) return front_half_from_float((float)((double)raw / 32768.0));
+    return front_half_from_float(bits_float(raw));
+}
+ITW_HD u32 front_load_raw(const uint8_t* p, int depth)
+{
+    if (depth == 8) return *p;
+    if (depth == 16) return *reinterpret_cast<const uint16_t*>(p);
+    return *reinterpret_cast<const u32*>(p);
 }
 
-// Destination texel (x, y) -> out[0] (RGBA8) or out[0..1] (RGBA16F: r | g << 16, b | a << 16)
-ITW_HD void front_texel(u32 (&out)[2], const FrontParams& P, int x, int y)
+// raw[c] = element of plane c (valid for c < planes) -> out[0] (RGBA8) or out[0..1] (RGBA16F: r | g << 16, b | a << 16)
+ITW_HD void front_compose(u32 (&out)[2], const FrontParams& P, const u32 (&raw)[4])
 {
-    const int sx = (x < P.width) ? x : P.width - 1, sy = (y < P.height) ? y : P.height - 1;      // IP:892-928
-    const int esize = P.depth >> 3;
-    const uint8_t* px = P.data + (long long)sy * P.row_bytes + (long long)sx * P.planes * esize;
     const bool alpha = (P.flags & kFrontAlpha) != 0;
     if (P.family == 2) {
         // IP:291-366.  The 32-bit variant reads alpha from plane 2 (IP:361) -- reference behaviour, kept.
-        u32 r = front_hdr_element(px, P.depth);
-        u32 g = (P.planes > 1) ? front_hdr_element(px + esize, P.depth) : 0u;
-        u32 b = (P.planes > 2) ? front_hdr_element(px + 2 * esize, P.depth) : 0u;
-        const u32 a = alpha ? front_hdr_element(px + ((P.depth == 32) ? 2 : 3) * esize, P.depth) : 0x3C00u;
+        u32 r = front_hdr_value(raw[0], P.depth);
+        u32 g = (P.planes > 1) ? front_hdr_value(raw[1], P.depth) : 0u;
+        u32 b = (P.planes > 2) ? front_hdr_value(raw[2], P.depth) : 0u;
+        const u32 a = alpha ? front_hdr_value((P.depth == 32) ? raw[2] : raw[3], P.depth) : 0x3C00u;
         if (P.flags & (kFrontFlipX | kFrontFlipY)) {                                              // IP:1531-1542
             const float fr = front_float_from_half(r), fg = front_float_from_half(g);
             if (P.flags & kFrontFlipX) r = front_half_from_float(1.0f - fr);
@@ -113,11 +114,11 @@ ITW_HD void front_texel(u32 (&out)[2], const FrontParams& P, int x, int y)
     }
     // IP:741-810 (colour: missing planes are 0) and IP:368-433 (BC4/BC5: missing planes copy plane 0)
     const bool gamma = (P.flags & kFrontGamma) != 0;
-    u32 r = front_ldr_element(px, P.depth, gamma);
+    u32 r = front_ldr_value(raw[0], P.depth, gamma);
     const u32 missing = (P.family == 1) ? r : 0u;
-    u32 g = (P.planes > 1) ? front_ldr_element(px + esize, P.depth, gamma) : missing;
-    u32 b = (P.planes > 2) ? front_ldr_element(px + 2 * esize, P.depth, gamma) : missing;
-    const u32 a = alpha ? front_ldr_element(px + 3 * esize, P.depth, gamma) : 255u;
+    u32 g = (P.planes > 1) ? front_ldr_value(raw[1], P.depth, gamma) : missing;
+    u32 b = (P.planes > 2) ? front_ldr_value(raw[2], P.depth, gamma) : missing;
+    const u32 a = alpha ? front_ldr_value(raw[3], P.depth, gamma) : 255u;
     if (P.flags & kFrontFlipX) r = 255u - r;                                                       // IP:1519-1527
     if (P.flags & kFrontFlipY) g = 255u - g;
     if (P.flags & kFrontNormalize) {                                                               // IP:1565-1584
@@ -133,10 +134,21 @@ ITW_HD void front_texel(u32 (&out)[2], const FrontParams& P, int x, int y)
     out[0] = r | (g << 8) | (b << 16) | (a << 24);
     out[1] = 0u;
 }
+// Destination texel (x, y): clamp into the source (IP:892-928), load its planes, compose
+ITW_HD void front_texel(u32 (&out)[2], const FrontParams& P, int x, int y)
+{
+    const int sx = (x < P.width) ? x : P.width - 1, sy = (y < P.height) ? y : P.height - 1;
+    const int esize = P.depth >> 3;
+    const uint8_t* px = P.data + (long long)sy * P.row_bytes + (long long)sx * P.planes * esize;
+    u32 raw[4] = {0u, 0u, 0u, 0u};
+    for (int c = 0; c < P.planes; c++) raw[c] = front_load_raw(px + c * esize, P.depth);
+    front_compose(out, P, raw);
+}
 
 #if defined(__CUDACC__)
 // One thread per destination texel: a warp writes 128 (RGBA8) or 256 (RGBA16F) contiguous bytes and reads
 // 32 * planes * depth/8 contiguous source bytes.  Algorithmic traffic per texel: planes*depth/8 B in, 4 / 8 B out.
+// General path (any alignment, any width).
 __global__ void __launch_bounds__(256) front_kernel(FrontParams P, uint8_t* __restrict__ dst, int dst_w, int dst_h, long long dst_stride)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -146,6 +158,75 @@ __global__ void __launch_bounds__(256) front_kernel(FrontParams P, uint8_t* __re
     uint8_t* row = dst + (long long)y * dst_stride;
     if (P.family == 2) *reinterpret_cast<uint2*>(row + (long long)x * 8) = make_uint2(out[0], out[1]);
     else *reinterpret_cast<u32*>(row + (long long)x * 4) = out[0];
+}
+// Fast path: one thread per TWO quads of four destination texels -> 128-bit stores; the 4 * planes * depth/8 source
+// bytes of a quad are contiguous and 4-byte aligned, and are fetched as 32-bit words into registers (all indices are
+// compile-time constants; both quads' loads are issued before any conversion so that two requests per thread are in
+// flight).  Needs dst_w % 4 == 0, 16-byte aligned dst rows and 4-byte aligned source rows; quads that touch the
+// replicated edge fall back to the per-texel routine.
+template <int kDepth, int kPlanes>
+__global__ void __launch_bounds__(256) front_kernel_x4(FrontParams P, uint8_t* __restrict__ dst, int dst_w, int dst_h, long long dst_stride)
+{
+    constexpr int kWords = kPlanes * kDepth / 8;              // 32-bit words per quad
+    constexpr int kQuads = 2;
+    const int xbase = (blockIdx.x * blockDim.x + threadIdx.x) * 4 * kQuads, y = blockIdx.y;
+    if (xbase >= dst_w || y >= dst_h) return;
+    FrontParams Q = P;                                        // compile-time depth / planes for the conversion code
+    Q.depth = kDepth;
+    Q.planes = kPlanes;
+    const bool vec = (kWords % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.data) | (uintptr_t)P.row_bytes) & 15u) == 0;
+    u32 wv[kQuads][kWords];
+    bool inside[kQuads], live[kQuads];
+#pragma unroll
+    for (int q = 0; q < kQuads; q++) {
+        const int x0 = xbase + 4 * q;
+        live[q] = x0 < dst_w;
+        inside[q] = live[q] && (x0 + 3 < P.width) && (y < P.height);
+        if (inside[q]) {
+            const u32* src = reinterpret_cast<const u32*>(P.data + (long long)y * P.row_bytes) + (long long)(x0 >> 2) * kWords;
+            if (vec) {
+#pragma unroll
+                for (int i = 0; i < kWords / 4; i++) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+                    wv[q][4 * i] = v.x; wv[q][4 * i + 1] = v.y; wv[q][4 * i + 2] = v.z; wv[q][4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kWords; i++) wv[q][i] = __ldg(src + i);
+            }
+        }
+    }
+    uint8_t* row = dst + (long long)y * dst_stride;
+#pragma unroll
+    for (int q = 0; q < kQuads; q++) {
+        if (!live[q]) continue;
+        const int x0 = xbase + 4 * q;
+        u32 out[4][2];
+        if (inside[q]) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                u32 raw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int c = 0; c < kPlanes; c++) {
+                    const int e = t * kPlanes + c;            // element index inside the quad
+                    if (kDepth == 8) raw[c] = (wv[q][e >> 2] >> (8 * (e & 3))) & 255u;
+                    else if (kDepth == 16) raw[c] = (wv[q][e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+                    else raw[c] = wv[q][e];
+                }
+                front_compose(out[t], Q, raw);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) front_texel(out[t], Q, x0 + t, y);
+        }
+        if (P.family == 2) {
+            uint4* o = reinterpret_cast<uint4*>(row + (long long)x0 * 8);
+            o[0] = make_uint4(out[0][0], out[0][1], out[1][0], out[1][1]);
+            o[1] = make_uint4(out[2][0], out[2][1], out[3][0], out[3][1]);
+        } else {
+            *reinterpret_cast<uint4*>(row + (long long)x0 * 4) = make_uint4(out[0][0], out[1][0], out[2][0], out[3][0]);
+        }
+    }
 }
 #endif
 

@@ -342,11 +342,30 @@ int front_params(FrontParams& P, int format, const itw_pixel_source* src, uint32
     P = FrontParams{static_cast<const uint8_t*>(src->data), src->width, src->height, src->planes, src->depth, row_bytes, family, flags};
     return 0;
 }
+template <int kDepth>
+void launch_front_x4(const FrontParams& P, dim3 grid, cudaStream_t s, uint8_t* d_dst, int dw, int dh, long long dstride)
+{
+    switch (P.planes) {
+        case 1: front_kernel_x4<kDepth, 1><<<grid, 256, 0, s>>>(P, d_dst, dw, dh, dstride); break;
+        case 2: front_kernel_x4<kDepth, 2><<<grid, 256, 0, s>>>(P, d_dst, dw, dh, dstride); break;
+        case 3: front_kernel_x4<kDepth, 3><<<grid, 256, 0, s>>>(P, d_dst, dw, dh, dstride); break;
+        default: front_kernel_x4<kDepth, 4><<<grid, 256, 0, s>>>(P, d_dst, dw, dh, dstride); break;
+    }
+}
 int launch_front(const FrontParams& P, uint8_t* d_dst, int dw, int dh, long long dstride, cudaStream_t s)
 {
-    dim3 grid((unsigned)((dw + 255) / 256), (unsigned)dh);
     if (dh > 65535) return fail("front end: height above 65535");
-    front_kernel<<<grid, 256, 0, s>>>(P, d_dst, dw, dh, dstride);
+    const bool quads = (dw & 3) == 0 && ((reinterpret_cast<uintptr_t>(d_dst) | (uintptr_t)dstride) & 15u) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(P.data) | (uintptr_t)P.row_bytes) & 3u) == 0;
+    if (quads) {
+        dim3 grid((unsigned)(((dw + 7) / 8 + 255) / 256), (unsigned)dh);      // two quads per thread
+        if (P.depth == 8) launch_front_x4<8>(P, grid, s, d_dst, dw, dh, dstride);
+        else if (P.depth == 16) launch_front_x4<16>(P, grid, s, d_dst, dw, dh, dstride);
+        else launch_front_x4<32>(P, grid, s, d_dst, dw, dh, dstride);
+    } else {
+        dim3 grid((unsigned)((dw + 255) / 256), (unsigned)dh);
+        front_kernel<<<grid, 256, 0, s>>>(P, d_dst, dw, dh, dstride);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     ITW_CUDA(cudaGetLastError());
     return 0;

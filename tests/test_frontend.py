@@ -115,6 +115,11 @@ def test_gpu_convert_matches_oracle(fmt, depth, planes):
     for flags in flag_sets(fmt, depth, planes):
         assert np.array_equal(p.convert_pixels(fmt, px, flags), o.convert_pixels(fmt, px, flags)), flags
     assert np.array_equal(p.convert_pixels(fmt, px, 0, pad=False), o.convert_pixels(fmt, px, 0, pad=False))
+    # widths that are multiples of 4 take the four-texels-per-thread kernel; 62 -> 64 also crosses the replicated edge
+    for w in (64, 62, 256):
+        px = source(depth, planes, w, 10, seed=w + planes)
+        for flags in list(flag_sets(fmt, depth, planes))[::3]:
+            assert np.array_equal(p.convert_pixels(fmt, px, flags), o.convert_pixels(fmt, px, flags)), (w, flags)
 
 
 @pytest.mark.gpu
