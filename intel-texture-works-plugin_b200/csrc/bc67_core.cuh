@@ -97,7 +97,7 @@ ITW_HD void covariance_of(float (&cov)[10], const float (&st)[15], int channels)
 // PCA line through the masked texels, endpoints at the extreme projections; K:834-905.
 // clamp255 = K:896 block_segment (BC7); otherwise K:857 block_segment_core (BC6H).
 // Writes ep[0..channels) and ep[4..4+channels).
-ITW_HD_NOINLINE void fit_segment(float* ep, const float* px, int mask, int channels, bool clamp255)
+ITW_HD void fit_segment_inl(float (&ep)[8], const float* px, int mask, int channels, bool clamp255)
 {
     float st[15], cov[10], mean[4], axis[4];
     masked_moments(st, px, mask, channels);
@@ -222,7 +222,7 @@ ITW_HD_NOINLINE float assign_indices(u32& idx0, u32& idx1, const float* px, int 
 }
 
 // Least-squares endpoints of one subset from its current indices; K:1198-1262
-ITW_HD_NOINLINE void solve_endpoints(float* ep, const float* px, int bits, u32 idx0, u32 idx1, int mask, int channels)
+ITW_HD void solve_endpoints_inl(float (&ep)[8], const float* px, int bits, u32 idx0, u32 idx1, int mask, int channels)
 {
     const float top = (float)((1 << bits) - 1);
     float atb1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};

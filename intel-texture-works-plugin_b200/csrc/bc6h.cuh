@@ -29,7 +29,9 @@ struct Bc6Entry {
     int mode, epb;
     int qbounds[8];
 };
+struct Bc6Step;
 struct Bc6Warp {
+    const Bc6Step* layout;                        // the 14 header layouts: CTA-shared copy on the device (bc6h_kernel), host table in the emulation
     float px[kBc6Slots][64];
     float lo[kBc6Slots][3], hi[kBc6Slots][3];
     float max_span[kBc6Slots];
@@ -93,6 +95,9 @@ ITW_HD int bc6_dequant(int v, int bits)
 ITW_HD int bc6_quant1(float e, int bits)
 {
     const int top = (1 << bits) - 1;
+    // +-0 / 65535 * top + 0.5 = 0.5 -> 0.  The never-written fourth component is always zero here and a zero
+    // numerator sends the IEEE division to its slow path, so it is answered directly (same result).
+    if (e == 0.0f) return 0;
     return clampi(cvt_x86(e / (256.0f * 256.0f - 1.0f) * (float)top + 0.5f), 0, top);
 }
 // 8*pairs values: quantise, clamp RGB into the entry's window, decode in place
@@ -187,14 +192,26 @@ static const Bc6Step h_bc6_layout[14][kBc6MaxSteps] = {ITW_BC6_LAYOUT_INIT};
 #undef G3
 #undef B3
 
-ITW_HD_NOINLINE void bc6_put_header(BitSink& s, const int* q, int mode)
+// Register-resident working set of the refinement chain.  Everything below is passed BY VALUE between the
+// (non-inlined) routines: nvcc keeps small structs in registers across calls, while arrays handed over by pointer
+// live in local memory, and the chain's dependent loads from it were 80 % of this kernel's long-scoreboard stalls
+// (profiles/r1_bc6h_v4_ncu.txt).
+struct Bc6Seg { float a[3], b[3]; };                      // one subset's endpoints A, B (r, g, b)
+struct Bc6Quant {
+    unsigned long long ch[3];                             // per channel: quantised A0, B0, A1, B1, 16 bits each
+    u32 dec[2][3];                                        // per subset and channel: decoded A | decoded B << 16
+};
+struct Bc6Search { float err; u32 idx0, idx1; };
+ITW_HD u32 bc6_q(const Bc6Quant& Q, int endpoint, int c) { return (u32)(Q.ch[c] >> (16 * endpoint)) & 0xFFFFu; }
+
+// Header bits of `mode` from the quantised endpoints; one 32-bit shared-memory read per layout step.
+ITW_HD_NOINLINE BitSink bc6_put_header(unsigned long long ch0, unsigned long long ch1, unsigned long long ch2, int mode,
+                                       const Bc6Step* layout)
 {
+    BitSink s;
+    s.reset();
     const bool delta = !(mode == 9 || mode == 10);
-#if defined(__CUDA_ARCH__)
-    const Bc6Step* steps = d_bc6_layout[mode];
-#else
-    const Bc6Step* steps = h_bc6_layout[mode];
-#endif
+    const Bc6Step* steps = layout + mode * kBc6MaxSteps;
     for (int i = 0; i < kBc6MaxSteps; i++) {
         const int f = steps[i].f, b = steps[i].b, n = steps[i].n;
         if (n == 0) break;
@@ -202,33 +219,36 @@ ITW_HD_NOINLINE void bc6_put_header(BitSink& s, const int* q, int mode)
         if (f == 0) value = bc6_prefix(mode);
         else {
             const int e = (f - 1) / 3, c = (f - 1) % 3;
-            value = q[4 * e + c];
-            if (delta && e > 0) value -= q[c];
+            const unsigned long long sel = (c == 0) ? ch0 : ((c == 1) ? ch1 : ch2);
+            value = (int)((u32)(sel >> (16 * e)) & 0xFFFFu);
+            if (delta && e > 0) value -= (int)((u32)sel & 0xFFFFu);
         }
         if (n > 0) s.put(n, (u32)value >> b);
         else
             for (int j = 0; j < -n; j++) s.put(1, ((u32)value >> (b - j)) & 1u);
     }
+    return s;
 }
 
 // ---- index search, three channels, decoded endpoints are integers 0..65535; K:1133-1193 ----
-// dq = decoded endpoints [subset][A r,g,b,-, B r,g,b,-].  The two palette entries are computed with
+// D[j][c] = decoded endpoints A | B << 16 of subset j.  The two palette entries are computed with
 // integer arithmetic: (64-w)*a + w*b + 32 < 2^23 is exact in the reference's float evaluation and its
 // (int) cast is a floor, so the integer shift gives the same value.  Everything that involves the
 // (non-integer) texels stays in float, in the reference's order, with the x86 conversion rule.
-ITW_HD_NOINLINE float bc6_assign(u32* idx, const float* px, int bits, const int* dq, u32 pattern)
+ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32 d00, u32 d01, u32 d02, u32 d10, u32 d11, u32 d12)
 {
     const int levels = 1 << bits;
     const float flevels = (float)levels;
     int ea[2][3], eb[2][3];
     float div[2];
+    const u32 D[2][3] = {{d00, d01, d02}, {d10, d11, d12}};
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         float d2 = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            ea[j][c] = dq[8 * j + c];
-            eb[j][c] = dq[8 * j + 4 + c];
+            ea[j][c] = (int)(D[j][c] & 0xFFFFu);
+            eb[j][c] = (int)(D[j][c] >> 16);
             d2 += sq((float)(eb[j][c] - ea[j][c]));          // K:1155; the difference of two exact integers is exact
         }
         div[j] = d2;
@@ -264,30 +284,65 @@ ITW_HD_NOINLINE float bc6_assign(u32* idx, const float* px, int bits, const int*
         if (k < 8) out0 += bq; else out1 += bq;
         total += (float)best_err;
     }
-    idx[0] = out0;
-    idx[1] = out1;
-    return total;
+    return Bc6Search{total, out0, out1};
 }
-// Quantise 8*pairs float endpoints for entry E (K:2139-2169): q = quantised, dq = decoded integers
-ITW_HD void bc6_quantise(const Bc6Entry& E, int* q, int* dq, const float* ep, int pairs)
+ITW_HD Bc6Search bc6_assign(const float* px, int bits, u32 pattern, const Bc6Quant& Q)
 {
-    for (int i = 0; i < 2 * pairs; i++) {
+    return bc6_assign(px, bits, pattern, Q.dec[0][0], Q.dec[0][1], Q.dec[0][2], Q.dec[1][0], Q.dec[1][1], Q.dec[1][2]);
+}
+// Quantise the endpoints of `pairs` subsets for entry E (K:2139-2169).  The never-written fourth component of the
+// reference's arrays is not carried: nothing downstream reads it (K:2392-2980 packs r, g, b only).
+ITW_HD Bc6Quant bc6_quantise(const Bc6Entry& E, const Bc6Seg (&seg)[2], int pairs)
+{
+    Bc6Quant Q;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            int v = bc6_quant1(ep[4 * i + c], E.epb);
-            if (c < 3) v = clampi(v, E.qbounds[c], E.qbounds[4 + c]);
-            q[4 * i + c] = v;
-            dq[4 * i + c] = bc6_dequant(v, E.epb);
+    for (int c = 0; c < 3; c++) {
+        Q.ch[c] = 0ull;
+        const int lo = E.qbounds[c], hi = E.qbounds[4 + c];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            u32 qa = 0u, qb = 0u;
+            if (j < pairs) {
+                qa = (u32)clampi(bc6_quant1(seg[j].a[c], E.epb), lo, hi);
+                qb = (u32)clampi(bc6_quant1(seg[j].b[c], E.epb), lo, hi);
+            } else {                                         // one-region entries: the second pair quantises zeros
+                qa = qb = (u32)clampi(0, lo, hi);
+            }
+            Q.ch[c] |= ((unsigned long long)qa | ((unsigned long long)qb << 16)) << (32 * j);
+            Q.dec[j][c] = (u32)bc6_dequant((int)qa, E.epb) | ((u32)bc6_dequant((int)qb, E.epb) << 16);
         }
     }
+    return Q;
 }
 // One candidate of the two-region search: stored fit -> quantise for E -> index search; K:2188-2191
 ITW_HD_NOINLINE float bc6_eval_two_region(const float* px, const Bc6Entry& E, int shape, const float* fit)
 {
-    int q[16], dq[16];
-    u32 idx[2];
-    bc6_quantise(E, q, dq, fit, 2);
-    return bc6_assign(idx, px, 3, dq, shape_pattern(shape));
+    Bc6Seg seg[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { seg[j].a[c] = fit[8 * j + c]; seg[j].b[c] = fit[8 * j + 4 + c]; }
+    const Bc6Quant Q = bc6_quantise(E, seg, 2);
+    return bc6_assign(px, 3, shape_pattern(shape), Q).err;
+}
+
+// PCA segment of the masked texels (3 channels, not clamped), by value; K:857-905 via bc67_core's fit_segment
+ITW_HD_NOINLINE Bc6Seg bc6_fit(const float* px, int mask)
+{
+    float ep[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ep[i] = 0.0f;
+    fit_segment_inl(ep, px, mask, 3, false);
+    return Bc6Seg{{ep[0], ep[1], ep[2]}, {ep[4], ep[5], ep[6]}};
+}
+// Least-squares endpoints of the masked texels from their indices, by value; K:1198-1262 via bc67_core
+ITW_HD_NOINLINE Bc6Seg bc6_solve(const float* px, int bits, u32 idx0, u32 idx1, int mask)
+{
+    float ep[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ep[i] = 0.0f;
+    solve_endpoints_inl(ep, px, bits, idx0, idx1, mask, 3);
+    return Bc6Seg{{ep[0], ep[1], ep[2]}, {ep[4], ep[5], ep[6]}};
 }
 
 // ---- the generic chain: initial candidate + refinement + encode of one (block, role) ----
@@ -299,52 +354,74 @@ ITW_HD_NOINLINE void bc6_chain(Bc6Warp& W, const Bc6Params& P, int slot, int r)
     const Bc6Entry& E = two ? W.two[slot][r] : W.one[slot][r - W.ntwo[slot]];
     const int pairs = two ? 2 : 1, bits = two ? 3 : 4;
     int shape = 0;
-    float ep[16];
+    Bc6Seg seg[2];
 #pragma unroll
-    for (int i = 0; i < 16; i++) ep[i] = 0.0f;
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) seg[j].a[c] = seg[j].b[c] = 0.0f;
     if (two) {
         const int pos = W.win_pos[slot][r];
         if (pos < 0) { W.res_err[slot][r] = inf_f(); return; }
         shape = W.order[slot][pos] & 31;
-        for (int i = 0; i < 16; i++) ep[i] = W.fit[slot][pos][i];
+        const float* fit = W.fit[slot][pos];
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { seg[j].a[c] = fit[8 * j + c]; seg[j].b[c] = fit[8 * j + 4 + c]; }
     } else {
-        fit_segment(ep, px, 0xFFFF, 3, false);
+        seg[0] = bc6_fit(px, 0xFFFF);
     }
     const u32 pattern = two ? shape_pattern(shape) : 0u;
-    int best_q[16], dq[16];
-    u32 best_idx[2];
-    bc6_quantise(E, best_q, dq, ep, pairs);
-    float best_err = bc6_assign(best_idx, px, bits, dq, pattern);
+    const int mask0 = two ? shape_mask(shape, 0) : 0xFFFF, mask1 = two ? shape_mask(shape, 1) : 0;
+    Bc6Quant best_q = bc6_quantise(E, seg, pairs);
+    Bc6Search best = bc6_assign(px, bits, pattern, best_q);
 
     const int refine = two ? P.refine_2p : P.refine_1p;
     for (int it = 0; it < refine; it++) {
-        int q[16];
-        u32 idx[2];
-#pragma unroll
-        for (int i = 0; i < 16; i++) ep[i] = 0.0f;           // two-region: fresh array (F6); one-region: slots 3,7 hold decoded zeros
-        for (int j = 0; j < pairs; j++)
-            solve_endpoints(ep + 8 * j, px, bits, best_idx[0], best_idx[1], two ? shape_mask(shape, j) : 0xFFFF, 3);
-        bc6_quantise(E, q, dq, ep, pairs);
-        const float err = bc6_assign(idx, px, bits, dq, pattern);
+        seg[0] = bc6_solve(px, bits, best.idx0, best.idx1, mask0);
+        if (two) seg[1] = bc6_solve(px, bits, best.idx0, best.idx1, mask1);
+        const Bc6Quant q = bc6_quantise(E, seg, pairs);
+        const Bc6Search found = bc6_assign(px, bits, pattern, q);
         // two-region keeps the best iterate (K:2242); one-region keeps the last (K:2288-2293)
-        if (!two || err < best_err) {
-            for (int i = 0; i < 8 * pairs; i++) best_q[i] = q[i];
-            best_idx[0] = idx[0]; best_idx[1] = idx[1];
-            best_err = err;
-        }
+        if (!two || found.err < best.err) { best_q = q; best = found; }
     }
-    W.res_err[slot][r] = best_err;
-    BitSink s;
-    s.reset();
+    W.res_err[slot][r] = best.err;
+    // orientation: the anchor index of every subset must have a clear top bit -- swap that subset's endpoints and
+    // mirror its indices (K:1694-1733); the swap is a 32-bit rotate of the packed pair
+    const int half = (1 << bits) / 2;
+    int flips = 0;
+    u32 idx0 = best.idx0, idx1 = best.idx1;
     if (two) {                                                  // K:2982-3010
-        const int flips = orient_subsets(best_q, best_idx[0], best_idx[1], 3, 2, shape);
-        bc6_put_header(s, best_q, E.mode);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int k0 = shape_anchor(shape, j);
+            const int v = (int)(((k0 < 8 ? idx0 : idx1) >> (4 * (k0 & 7))) & 15u);
+            if (v >= half) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const u32 pair = (u32)(best_q.ch[c] >> (32 * j));
+                    const u32 swapped = (pair >> 16) | (pair << 16);
+                    best_q.ch[c] = (best_q.ch[c] & ~(0xFFFFFFFFull << (32 * j))) | ((unsigned long long)swapped << (32 * j));
+                }
+                flips |= shape_mask(shape, j);
+            }
+        }
+    } else if ((int)(idx0 & 15u) >= half) {                    // K:3012-3031
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const u32 pair = (u32)best_q.ch[c];
+            best_q.ch[c] = (best_q.ch[c] & 0xFFFFFFFF00000000ull) | (unsigned long long)((pair >> 16) | (pair << 16));
+        }
+        const u32 all = 0x11111111u * (u32)((1 << bits) - 1);
+        idx0 = all - idx0;
+        idx1 = all - idx1;
+    }
+    BitSink s = bc6_put_header(best_q.ch[0], best_q.ch[1], best_q.ch[2], E.mode, W.layout);
+    if (two) {
         s.put(5, (u32)shape);
-        put_indices(s, best_idx[0], best_idx[1], 3, flips, shape_anchor(shape, 1), -1);
-    } else {                                                    // K:3012-3031
-        orient_single(best_q, 4, best_idx[0], best_idx[1], 4);
-        bc6_put_header(s, best_q, E.mode);
-        put_indices(s, best_idx[0], best_idx[1], 4, 0, -1, -1);
+        put_indices(s, idx0, idx1, 3, flips, shape_anchor(shape, 1), -1);
+    } else {
+        put_indices(s, idx0, idx1, 4, 0, -1, -1);
     }
     u32* out = W.res_code[slot][r];
     out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
@@ -475,7 +552,11 @@ ITW_HD void bc6_phase_fits(int lane, Bc6Warp& W, const Bc6Params& P)
         float* ep = W.fit[slot][n];
 #pragma unroll
         for (int i = 0; i < 16; i++) ep[i] = 0.0f;               // never-written slots read as zero (F6)
-        for (int j = 0; j < 2; j++) fit_segment(ep + 8 * j, W.px[slot], shape_mask(shape, j), 3, false);
+        for (int j = 0; j < 2; j++) {
+            const Bc6Seg seg = bc6_fit(W.px[slot], shape_mask(shape, j));
+#pragma unroll
+            for (int c = 0; c < 3; c++) { ep[8 * j + c] = seg.a[c]; ep[8 * j + 4 + c] = seg.b[c]; }
+        }
     }
 }
 ITW_HD void bc6_phase_candidates(int lane, Bc6Warp& W, const Bc6Params& P)
@@ -563,8 +644,14 @@ bc6h_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc6Params P, long long
     extern __shared__ __align__(16) unsigned char bc6_smem[];
     __shared__ __align__(128) unsigned char stage[kTma ? 2 : 1][kTma ? 4 * kBc6TileRowBytes : 16];
     __shared__ __align__(8) unsigned long long full[2];
+    // header layouts in shared memory: bc6_put_header walks them step by step, and from global memory every step
+    // was a dependent L1/L2 round trip (long-scoreboard stalls, profiles/r1_final_bc6h_slow_ncu.txt)
+    __shared__ Bc6Step layout[14 * kBc6MaxSteps];
+    for (int i = threadIdx.x; i < 14 * kBc6MaxSteps; i += blockDim.x) layout[i] = d_bc6_layout[i / kBc6MaxSteps][i % kBc6MaxSteps];
     Bc6Warp& W = reinterpret_cast<Bc6Warp*>(bc6_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) W.layout = layout;
+    __syncthreads();
     const long long nbatches = (nblocks + kBc6Slots - 1) / kBc6Slots;
     const long long nwarps = (long long)gridDim.x * kBc6WarpsPerCta;
     const long long rounds = (nbatches + nwarps - 1) / nwarps;

@@ -331,9 +331,14 @@ __global__ void __launch_bounds__(128) decode_kernel(const uint8_t* __restrict__
         u32 px[16][2];
         decode_bc6h(px, w);
         uint8_t* row = dst + (long long)(4 * by) * stride + (long long)bx * 32;
+        const bool wide = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)stride) & 31u) == 0;
 #pragma unroll
         for (int y = 0; y < 4; y++, row += stride) {
-            if (kVec16) {
+            if (kVec16 && wide) {                      // one 32-byte sector per thread and row
+                const u32 v[8] = {px[4 * y][0], px[4 * y][1], px[4 * y + 1][0], px[4 * y + 1][1],
+                                  px[4 * y + 2][0], px[4 * y + 2][1], px[4 * y + 3][0], px[4 * y + 3][1]};
+                st_global_256(row, v);
+            } else if (kVec16) {
                 reinterpret_cast<uint4*>(row)[0] = make_uint4(px[4 * y][0], px[4 * y][1], px[4 * y + 1][0], px[4 * y + 1][1]);
                 reinterpret_cast<uint4*>(row)[1] = make_uint4(px[4 * y + 2][0], px[4 * y + 2][1], px[4 * y + 3][0], px[4 * y + 3][1]);
             } else {

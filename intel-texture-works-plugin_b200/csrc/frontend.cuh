@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(256) front_kernel_x4(FrontParams P, uint8_t* _
     Q.depth = kDepth;
     Q.planes = kPlanes;
     const bool vec = (kWords % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.data) | (uintptr_t)P.row_bytes) & 15u) == 0;
+    const bool wide_src = ((reinterpret_cast<uintptr_t>(P.data) | (uintptr_t)P.row_bytes) & 31u) == 0;
+    const bool wide_dst = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)dst_stride) & 31u) == 0;
     u32 wv[kQuads][kWords];
     bool inside[kQuads], live[kQuads];
 #pragma unroll
@@ -184,7 +186,15 @@ __global__ void __launch_bounds__(256) front_kernel_x4(FrontParams P, uint8_t* _
         inside[q] = live[q] && (x0 + 3 < P.width) && (y < P.height);
         if (inside[q]) {
             const u32* src = reinterpret_cast<const u32*>(P.data + (long long)y * P.row_bytes) + (long long)(x0 >> 2) * kWords;
-            if (vec) {
+            if (kWords % 8 == 0 && wide_src) {
+#pragma unroll
+                for (int i = 0; i < kWords / 8; i++) {
+                    u32 v[8];
+                    ld_global_nc_256(v, src + 8 * i);
+#pragma unroll
+                    for (int n = 0; n < 8; n++) wv[q][8 * i + n] = v[n];
+                }
+            } else if (vec) {
 #pragma unroll
                 for (int i = 0; i < kWords / 4; i++) {
                     const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
@@ -219,7 +229,10 @@ __global__ void __launch_bounds__(256) front_kernel_x4(FrontParams P, uint8_t* _
 #pragma unroll
             for (int t = 0; t < 4; t++) front_texel(out[t], Q, x0 + t, y);
         }
-        if (P.family == 2) {
+        if (P.family == 2 && wide_dst) {           // one 32-byte sector per quad
+            const u32 v[8] = {out[0][0], out[0][1], out[1][0], out[1][1], out[2][0], out[2][1], out[3][0], out[3][1]};
+            st_global_256(row + (long long)x0 * 8, v);
+        } else if (P.family == 2) {
             uint4* o = reinterpret_cast<uint4*>(row + (long long)x0 * 8);
             o[0] = make_uint4(out[0][0], out[0][1], out[1][0], out[1][1]);
             o[1] = make_uint4(out[2][0], out[2][1], out[3][0], out[3][1]);

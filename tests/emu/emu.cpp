@@ -81,6 +81,7 @@ void emu_CompressBlocksBC6H(const rgba_surface* src, uint8_t* dst, bc6h_enc_sett
     const Bc6Params P = bc6_params_from(*settings);
     const long long nblocks = (long long)(surf.width / 4) * (surf.height / 4);
     static thread_local Bc6Warp W;
+    W.layout = &h_bc6_layout[0][0];
     for (long long first_block = 0; first_block < nblocks; first_block += kBc6Slots) {
         const int nvalid = (int)((nblocks - first_block < kBc6Slots) ? (nblocks - first_block) : kBc6Slots);
         ITW_BC6_PROGRAM(ITW_PHASE_EMU)

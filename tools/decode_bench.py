@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--warm", type=int, default=3, help="untimed launches before the timed ones")
     a = ap.parse_args()
     import torch
     api = pkg.ItwBcn()
@@ -42,9 +43,9 @@ def main():
         # rotate over several destinations so that consecutive launches do not hit lines already in L2
         outs = [torch.empty(n * n * texel, dtype=torch.uint8, device="cuda") for _ in range(4)]
         ms = []
-        for i in range(a.reps + 3):
+        for i in range(a.reps + a.warm):
             api.decode_raw(fmt, blocks.data_ptr(), outs[i % 4].data_ptr(), n, n, n * texel)
-            if i >= 3:
+            if i >= a.warm:
                 ms.append(api.last_kernel_ms())
         t = float(np.median(ms))
         traffic = nblk * bpb + n * n * texel

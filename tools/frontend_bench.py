@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--warm", type=int, default=3, help="untimed launches before the timed ones")
     a = ap.parse_args()
     import torch
     api = pkg.ItwBcn()
@@ -44,10 +45,10 @@ def main():
         srcs = [torch.from_numpy(host).cuda() for _ in range(2)]
         outs = [torch.empty(n * n * texel, dtype=torch.uint8, device="cuda") for _ in range(3)]
         ms = []
-        for i in range(a.reps + 3):
+        for i in range(a.reps + a.warm):
             src = B.PixelSource(srcs[i % 2].data_ptr(), n, n, planes, depth, 0)
             api.convert_pixels_raw(fmt, src, flags, outs[i % 3].data_ptr(), n, n, n * texel)
-            if i >= 3:
+            if i >= a.warm:
                 ms.append(api.last_kernel_ms())
         t = float(np.median(ms))
         traffic = n * n * (planes * depth // 8 + texel)
@@ -64,9 +65,9 @@ def main():
         src = B.PixelSource(d_src.data_ptr(), n, n, planes, depth, 0)
         settings = api.profile(prof) if prof else None
         ms = []
-        for i in range(8):
+        for i in range(a.warm + max(a.reps, 1)):
             api.encode_pixels_raw(fmt, src, flags, blocks.data_ptr(), settings)
-            if i >= 3:
+            if i >= a.warm:
                 ms.append(api.last_kernel_ms())
         print(json.dumps({"op": "encode_pixels", "format": fmt, "profile": prof, "size": n, "kernel_ms": round(float(np.median(ms)), 4),
                           "mtexel_s": round(n * n / float(np.median(ms)) / 1e3, 1)}), flush=True)
