@@ -303,7 +303,19 @@ def main():
                 "note": "read-only variant: %.3f GB/s" % (size * size * READ_BYTES_PER_TEXEL[fmt] / (ms_per_step * 1e-3) / 1e9)}
     traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(traffic_path):
-        roofline["traffic"] = json.load(open(traffic_path)).get(f"{fmt}:{prof}:{size}")
+        counters = json.load(open(traffic_path))
+        roofline["traffic"] = counters.get(f"{fmt}:{prof}:{size}")
+        # The encoders are issue-bound, not HBM-bound: alongside the required HBM roofline,
+        # report the warp-instruction issue rate against 4 schedulers x SM count x the SM clock sampled DURING the
+        # timed region.  Instructions per launch come from the committed ncu capture of the same workload.
+        winst = counters.get("warp_inst", {}).get(f"{fmt}:{prof}:{size}")
+        if winst and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(0).multi_processor_count
+            peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
+            got = winst / (ms_per_step * 1e-3)
+            roofline["issue"] = {"warp_inst_per_launch": int(winst), "achieved_ginst_s": round(got / 1e9, 1),
+                                 "peak_ginst_s": round(peak_issue / 1e9, 1), "frac": round(got / peak_issue, 3),
+                                 "note": "4 warp schedulers/SM x SMs x median SM clock under load; instruction count from profiles/"}
 
     cpu_info = None
     if world == 1 and not args.no_cpu:
