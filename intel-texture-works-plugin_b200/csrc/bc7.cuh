@@ -205,8 +205,14 @@ ITW_HD void bc7_covariance(float (&cov)[10], float (&mean)[4], const int (&st)[1
 #pragma unroll
     for (int c = 0; c < 4; c++) mean[c] = (c < CH) ? div_by_rcp(s[c], n, rn) : 0.0f;
 }
+// By-value working set of the shape and chain phases: nvcc keeps these small structs in registers across the
+// non-inlined calls, whereas arrays handed over by pointer live in local memory (see bc6h.cuh).
+struct Bc7Seg { float v[8]; };                       // endpoints A (r,g,b,a) and B (r,g,b,a) of one subset
+struct Bc7Packed { u32 dec_a, dec_b, q_a, q_b; };    // decoded A, B and quantised A, B as RGBA bytes
+struct Bc7Search { int err; u32 idx0, idx1; };
+
 template <int CH>
-ITW_HD void bc7_fit_impl(float* ep, const View& v, u32 mask)
+ITW_HD void bc7_fit_impl(float (&ep)[8], const View& v, u32 mask)
 {
     u32 P[4][4];
     load_planes(P, v);
@@ -241,13 +247,17 @@ ITW_HD void bc7_fit_impl(float* ep, const View& v, u32 mask)
         ep[4 + c] = clamp_sse(hi * axis[c] + mean[c], 0.0f, 255.0f);
     }
 }
-// PCA line through the masked texels, clamped to [0,255]; K:834-905.  ep[0..3] = A, ep[4..7] = B;
-// components >= channels are left untouched.
-ITW_HD_NOINLINE void bc7_fit(float* ep, const Bc7Block* blk, int rot, int alpha, u32 mask, int channels)
+// PCA line through the masked texels, clamped to [0,255]; K:834-905.  v[0..3] = A, v[4..7] = B;
+// components >= channels are zero (the reference's never-written slots, rule F6).
+ITW_HD_NOINLINE Bc7Seg bc7_fit(const Bc7Block* blk, int rot, int alpha, u32 mask, int channels)
 {
     const View v{blk, rot, alpha};
-    if (channels == 4) bc7_fit_impl<4>(ep, v, mask);
-    else bc7_fit_impl<3>(ep, v, mask);
+    Bc7Seg seg;
+#pragma unroll
+    for (int i = 0; i < 8; i++) seg.v[i] = 0.0f;
+    if (channels == 4) bc7_fit_impl<4>(seg.v, v, mask);
+    else bc7_fit_impl<3>(seg.v, v, mask);
+    return seg;
 }
 
 // trace - lambda_max of a covariance; K:907-939 (eps on three diagonal slots only, K:918-920)
@@ -313,8 +323,9 @@ ITW_HD_NOINLINE int bc7_split_key(const Bc7Block* blk, int shape, int channels)
 //                                                         except in mode 0 -- reference behaviour, K:1003-1009)
 //   mode 1         one p-bit per pair        K:1024-1052  (a single running error sum over both endpoints)
 //   modes 2,4,5    no p-bit                  K:1054-1065
-ITW_HD_NOINLINE void bc7_quantise(u32* out, const float* ep, int mode, int channels)
+ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
 {
+    const float (&ep)[8] = seg.v;
     const int family = (mode == 1) ? 1 : ((mode == 2 || mode == 4 || mode == 5) ? 2 : 0);
     // stored bits per component including the p-bit: 2^qbits - 1 is K's `levels2` (p-bit modes) or `levels-1`
     const int qbits = (mode == 0 || mode == 2 || mode == 4) ? 5 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 8));
@@ -365,13 +376,15 @@ ITW_HD_NOINLINE void bc7_quantise(u32* out, const float* ep, int mode, int chann
     // decode all four bytes at once (K:1093-1122): v << (8-d) | that >> d, bytewise
     const int dbits = (mode == 3 || mode == 6) ? 8 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 5));
     const u32 lowmask = 0x01010101u * (0xFFu >> dbits);
+    u32 dec[2], qq[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const u32 q = pick1[i] ? cand1[i] : cand0[i];
         const u32 vv = q << (8 - dbits);
-        out[i] = vv + ((vv >> dbits) & lowmask);
-        out[2 + i] = q;
+        dec[i] = vv + ((vv >> dbits) & lowmask);
+        qq[i] = q;
     }
+    return Bc7Packed{dec[0], dec[1], qq[0], qq[1]};
 }
 
 // Integer interpolation of two packed RGBA endpoints with BC7 weight w (K:1172: ((64-w)a+wb+32)/64
@@ -387,15 +400,15 @@ ITW_HD u32 lerp_rgba(u32 a, u32 b, u32 w)
 // Index search; K:1133-1193.  ends[2j], ends[2j+1] = decoded endpoints A,B of subset j (RGBA bytes);
 // chmask zeroes the channels that do not take part (0x00FFFFFF for three-channel modes).
 // Returns the summed error (exact integer) and the sixteen 4-bit indices in idx[0..1].
-ITW_HD_NOINLINE int bc7_assign(u32* idx, u32 (*pal)[32], int lane, const Bc7Block* blk, int rot, int alpha, int bits,
-                               int pairs, u32 pattern, const u32* ends, u32 chmask)
+ITW_HD_NOINLINE Bc7Search bc7_assign(u32 (*pal)[32], int lane, const Bc7Block* blk, int rot, int alpha, int bits, int pairs,
+                                     u32 pattern, u32 e0, u32 e1, u32 e2, u32 e3, u32 e4, u32 e5, u32 chmask)
 {
     const View v{blk, rot, alpha};
     const int levels = 1 << bits;
     // per-subset constants go to lane-private shared memory too and are fetched by subset id in the texel
     // loop: the load/store pipe is nearly idle in this kernel while the ALU pipe (selects) is the busiest
     for (int j = 0; j < pairs; j++) {
-        const u32 a = ends[2 * j] & chmask, b = ends[2 * j + 1] & chmask;
+        const u32 a = ((j == 0) ? e0 : ((j == 1) ? e2 : e4)) & chmask, b = ((j == 0) ? e1 : ((j == 1) ? e3 : e5)) & chmask;
         const u32 aa = dp4a_u8(a, a, 0u), ab = dp4a_u8(a, b, 0u), bb = dp4a_u8(b, b, 0u);
         const float fdiv = (float)(int)(bb - 2u * ab + aa);      // sum of squared differences, exact
         const float frcp = 1.0f / fdiv;                          // inf when the endpoints coincide (-> NaN below, as 0/0)
@@ -433,15 +446,17 @@ ITW_HD_NOINLINE int bc7_assign(u32* idx, u32 (*pal)[32], int lane, const Bc7Bloc
         const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
         if (k < 8) out0 += bq; else out1 += bq;
     }
-    idx[0] = out0;
-    idx[1] = out1;
-    return total;
+    return Bc7Search{total, out0, out1};
 }
 
 // Least-squares endpoints of one subset from its indices; K:1198-1262.  The sums are exact integers.
-ITW_HD_NOINLINE void bc7_solve(float* ep, const Bc7Block* blk, int rot, int alpha, int bits, u32 idx0, u32 idx1, u32 mask,
-                               int channels)
+// Components >= channels are zero.
+ITW_HD_NOINLINE Bc7Seg bc7_solve(const Bc7Block* blk, int rot, int alpha, int bits, u32 idx0, u32 idx1, u32 mask, int channels)
 {
+    Bc7Seg seg;
+#pragma unroll
+    for (int i = 0; i < 8; i++) seg.v[i] = 0.0f;
+    float (&ep)[8] = seg.v;
     const View v{blk, rot, alpha};
     const u32 top = (1u << bits) - 1u;
     u32 sq1 = 0u, sqq = 0u, sum[4] = {0u, 0u, 0u, 0u}, atb1[4] = {0u, 0u, 0u, 0u};
@@ -482,6 +497,7 @@ ITW_HD_NOINLINE void bc7_solve(float* ep, const Bc7Block* blk, int rot, int alph
             ep[c] = a;
             ep[4 + c] = b;
         }
+    return seg;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -494,7 +510,9 @@ ITW_HD void bc7_write_partitioned(u32* out, u32 (&Q)[3][2], u32 idx0, u32 idx1, 
     const int bits = bc7_mode_bits(mode), pairs = bc7_pairs(mode), channels = (mode == 7) ? 4 : 3;
     const int half = (1 << bits) / 2;
     int flips = 0;
-    for (int j = 0; j < pairs; j++) {                           // anchor index MSB must be 0; K:1708-1733
+#pragma unroll
+    for (int j = 0; j < 3; j++) {                               // anchor index MSB must be 0; K:1708-1733
+        if (j >= pairs) continue;
         const int k0 = shape_anchor(shape, j);
         const int vv = (int)(((k0 < 8 ? idx0 : idx1) >> (4 * (k0 & 7))) & 15u);
         if (vv >= half) {
@@ -508,15 +526,23 @@ ITW_HD void bc7_write_partitioned(u32* out, u32 (&Q)[3][2], u32 idx0, u32 idx1, 
     s.put(mode == 0 ? 4 : 6, (u32)(shape & (mode == 0 ? 15 : 63)));
     const int width = (mode == 0) ? 4 : ((mode == 1) ? 6 : ((mode == 3) ? 7 : 5));
     const int drop = (mode == 2) ? 0 : 1;                      // p-bit modes store the value without its LSB
-    for (int c = 0; c < channels; c++)
-        for (int j = 0; j < pairs; j++) {
+    for (int c = 0; c < channels; c++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            if (j >= pairs) continue;
             s.put(width, qcomp(Q[j][0], c) >> drop);
             s.put(width, qcomp(Q[j][1], c) >> drop);
         }
-    if (mode == 1)
-        for (int j = 0; j < 2; j++) s.put(1, Q[j][0] & 1u);
-    if (mode == 0 || mode == 3 || mode == 7)
-        for (int j = 0; j < pairs; j++) { s.put(1, Q[j][0] & 1u); s.put(1, Q[j][1] & 1u); }
+    }
+    if (mode == 1) { s.put(1, Q[0][0] & 1u); s.put(1, Q[1][0] & 1u); }
+    if (mode == 0 || mode == 3 || mode == 7) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            if (j >= pairs) continue;
+            s.put(1, Q[j][0] & 1u);
+            s.put(1, Q[j][1] & 1u);
+        }
+    }
     put_indices(s, idx0, idx1, bits, flips, shape_anchor(shape, 1), (pairs == 3) ? shape_anchor(shape, 2) : -1);
     out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
 }
@@ -641,7 +667,8 @@ ITW_HD void scalar_solve(float (&ep)[2], const Bc7Block* blk, int shift, int bit
         ep[1] = ep[0];
     }
 }
-ITW_HD_NOINLINE int bc7_scalar_channel(int* aq, u32* aidx, const Bc7Block* blk, int rotation, int abits, int aepbits, int rch)
+struct Bc7Scalar { int err, q0, q1; u32 idx0, idx1; };
+ITW_HD_NOINLINE Bc7Scalar bc7_scalar_channel(const Bc7Block* blk, int rotation, int abits, int aepbits, int rch)
 {
     const int shift = 8 * rotation;
     int lo = 255, hi = 0;                                        // K:1542-1548
@@ -662,9 +689,7 @@ ITW_HD_NOINLINE int bc7_scalar_channel(int* aq, u32* aidx, const Bc7Block* blk, 
         scalar_quantise(q, e, ep, aepbits);
         err = scalar_assign(a0, a1, blk, shift, abits, e);
     }
-    aq[0] = q[0]; aq[1] = q[1];
-    aidx[0] = a0; aidx[1] = a1;
-    return err;
+    return Bc7Scalar{err, q[0], q[1], a0, a1};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -710,8 +735,7 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
     const int alpha = (P.channels == 4) ? 1 : 0;
     const u32 pattern = (role.kind == 0) ? shape_pattern(role.shape) : 0u;
 
-    u32 ends[6], Q[3][2], idx[2], best_idx[2];
-    float ep[8];
+    u32 ends[6], Q[3][2];
     // initial candidate
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -719,48 +743,49 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
         ends[2 * j] = ends[2 * j + 1] = 0u;
     }
     float tail_a = 0.0f, tail_b = 0.0f;                          // ep[3], ep[7] carried between iterations (quirk Q5)
-    for (int j = 0; j < pairs; j++) {
-        u32 packed[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++) ep[i] = 0.0f;                // never-written slots read as zero (F6)
+    for (int j = 0; j < 3; j++) {
+        if (j >= pairs) continue;
         const u32 mask = (role.kind == 0) ? (u32)shape_mask(role.shape, j) : 0xFFFFu;
-        bc7_fit(ep, blk, rot, alpha, mask, channels);
-        if (role.kind == 2 && channels == 3) ep[3] = ep[7] = 255.0f;     // K:1664-1667
-        bc7_quantise(packed, ep, mode, channels);
-        tail_a = (float)(packed[0] >> 24); tail_b = (float)(packed[1] >> 24);
-        if (j == 0) { ends[0] = packed[0]; ends[1] = packed[1]; Q[0][0] = packed[2]; Q[0][1] = packed[3]; }
-        else if (j == 1) { ends[2] = packed[0]; ends[3] = packed[1]; Q[1][0] = packed[2]; Q[1][1] = packed[3]; }
-        else { ends[4] = packed[0]; ends[5] = packed[1]; Q[2][0] = packed[2]; Q[2][1] = packed[3]; }
+        Bc7Seg seg = bc7_fit(blk, rot, alpha, mask, channels);   // slots >= channels are zero (F6)
+        if (role.kind == 2 && channels == 3) seg.v[3] = seg.v[7] = 255.0f;     // K:1664-1667
+        const Bc7Packed pk = bc7_quantise(seg, mode, channels);
+        tail_a = (float)(pk.dec_a >> 24); tail_b = (float)(pk.dec_b >> 24);
+        ends[2 * j] = pk.dec_a; ends[2 * j + 1] = pk.dec_b;
+        Q[j][0] = pk.q_a; Q[j][1] = pk.q_b;
     }
-    int best_err = bc7_assign(best_idx, W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends, chmask);
+    Bc7Search best = bc7_assign(W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends[0], ends[1], ends[2], ends[3], ends[4],
+                                ends[5], chmask);
 
     const int refine = P.refine[mode];
     for (int it = 0; it < refine; it++) {
         u32 nQ[3][2];
 #pragma unroll
         for (int j = 0; j < 3; j++) nQ[j][0] = nQ[j][1] = 0u;
-        for (int j = 0; j < pairs; j++) {
-            u32 packed[4];
 #pragma unroll
-            for (int i = 0; i < 8; i++) ep[i] = 0.0f;
-            if (role.kind != 0) { ep[3] = tail_a; ep[7] = tail_b; }      // these arrays live across iterations in K
+        for (int j = 0; j < 3; j++) {
+            if (j >= pairs) continue;
             const u32 mask = (role.kind == 0) ? (u32)shape_mask(role.shape, j) : 0xFFFFu;
-            bc7_solve(ep, blk, rot, alpha, bits, best_idx[0], best_idx[1], mask, channels);
-            bc7_quantise(packed, ep, mode, vote_refine);
-            tail_a = (float)(packed[0] >> 24); tail_b = (float)(packed[1] >> 24);
-            if (j == 0) { ends[0] = packed[0]; ends[1] = packed[1]; nQ[0][0] = packed[2]; nQ[0][1] = packed[3]; }
-            else if (j == 1) { ends[2] = packed[0]; ends[3] = packed[1]; nQ[1][0] = packed[2]; nQ[1][1] = packed[3]; }
-            else { ends[4] = packed[0]; ends[5] = packed[1]; nQ[2][0] = packed[2]; nQ[2][1] = packed[3]; }
+            Bc7Seg seg = bc7_solve(blk, rot, alpha, bits, best.idx0, best.idx1, mask, channels);
+            // K's arrays live across iterations in modes 4-6: a fourth slot the solve does not write keeps the
+            // previous iteration's decoded value
+            if (role.kind != 0 && channels < 4) { seg.v[3] = tail_a; seg.v[7] = tail_b; }
+            const Bc7Packed pk = bc7_quantise(seg, mode, vote_refine);
+            tail_a = (float)(pk.dec_a >> 24); tail_b = (float)(pk.dec_b >> 24);
+            ends[2 * j] = pk.dec_a; ends[2 * j + 1] = pk.dec_b;
+            nQ[j][0] = pk.q_a; nQ[j][1] = pk.q_b;
         }
-        const int err = bc7_assign(idx, W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends, chmask);
+        const Bc7Search found = bc7_assign(W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends[0], ends[1], ends[2], ends[3],
+                                           ends[4], ends[5], chmask);
         // partitioned modes keep the best iterate (K:1348); modes 4,5,6 keep the last (K:1598-1603, :1677-1682)
-        if (role.kind != 0 || err < best_err) {
+        if (role.kind != 0 || found.err < best.err) {
 #pragma unroll
             for (int j = 0; j < 3; j++) { Q[j][0] = nQ[j][0]; Q[j][1] = nQ[j][1]; }
-            best_idx[0] = idx[0]; best_idx[1] = idx[1];
-            best_err = err;
+            best = found;
         }
     }
+    int best_err = best.err;
+    const u32 best_idx[2] = {best.idx0, best.idx1};
 
     u32* out = W.res_code[slot][r];
     if (role.kind == 0) {
@@ -772,10 +797,9 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
         bc7_write_partitioned(out, Q, best_idx[0], best_idx[1], role.shape, mode);
     } else if (role.kind == 1) {
         const int abits = (mode == 4 && !role.swap) ? 3 : 2, aepbits = (mode == 4) ? 6 : 8;
-        int aq[2];
-        u32 aidx[2];
-        best_err += bc7_scalar_channel(aq, aidx, blk, role.rotation, abits, aepbits, P.rch);
-        bc7_write_mode45(out, Q[0][0], Q[0][1], best_idx[0], best_idx[1], aq[0], aq[1], aidx[0], aidx[1], mode, role.rotation,
+        const Bc7Scalar sc = bc7_scalar_channel(blk, role.rotation, abits, aepbits, P.rch);
+        best_err += sc.err;
+        bc7_write_mode45(out, Q[0][0], Q[0][1], best_idx[0], best_idx[1], sc.q0, sc.q1, sc.idx0, sc.idx1, mode, role.rotation,
                          role.swap);
     } else {
         bc7_write_mode6(out, Q[0][0], Q[0][1], best_idx[0], best_idx[1]);
@@ -823,29 +847,26 @@ ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, i
     u32 ends_a[6], ends_b[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) ends_a[i] = ends_b[i] = 0u;
-    for (int j = 0; j < pairs; j++) {
-        float ep[8];
-        u32 packed[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++) ep[i] = 0.0f;
-        bc7_fit(ep, blk, 3, 1, (u32)shape_mask(shape, j), channels);
+    for (int j = 0; j < 3; j++) {
+        if (j >= pairs) continue;
+        const Bc7Seg seg = bc7_fit(blk, 3, 1, (u32)shape_mask(shape, j), channels);
         if (do_a) {
-            bc7_quantise(packed, ep, mode_a, channels);
-            if (j == 0) { ends_a[0] = packed[0]; ends_a[1] = packed[1]; }
-            else if (j == 1) { ends_a[2] = packed[0]; ends_a[3] = packed[1]; }
-            else { ends_a[4] = packed[0]; ends_a[5] = packed[1]; }
+            const Bc7Packed pk = bc7_quantise(seg, mode_a, channels);
+            ends_a[2 * j] = pk.dec_a; ends_a[2 * j + 1] = pk.dec_b;
         }
         if (do_b) {
-            bc7_quantise(packed, ep, mode_b, channels);
-            if (j == 0) { ends_b[0] = packed[0]; ends_b[1] = packed[1]; }
-            else if (j == 1) { ends_b[2] = packed[0]; ends_b[3] = packed[1]; }
-            else { ends_b[4] = packed[0]; ends_b[5] = packed[1]; }
+            const Bc7Packed pk = bc7_quantise(seg, mode_b, channels);
+            ends_b[2 * j] = pk.dec_a; ends_b[2 * j + 1] = pk.dec_b;
         }
     }
     const u32 pattern = shape_pattern(shape);
-    u32 idx[2];
-    if (do_a) W.cand_err[slot][0][n] = bc7_assign(idx, W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_a), pairs, pattern, ends_a, chmask);
-    if (do_b) W.cand_err[slot][1][n] = bc7_assign(idx, W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_b), pairs, pattern, ends_b, chmask);
+    if (do_a)
+        W.cand_err[slot][0][n] = bc7_assign(W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_a), pairs, pattern, ends_a[0], ends_a[1], ends_a[2],
+                                            ends_a[3], ends_a[4], ends_a[5], chmask).err;
+    if (do_b)
+        W.cand_err[slot][1][n] = bc7_assign(W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_b), pairs, pattern, ends_b[0], ends_b[1], ends_b[2],
+                                            ends_b[3], ends_b[4], ends_b[5], chmask).err;
 }
 // shapes of a pair of mode slots that walk the same list: (0,1) three-subset, (2,3) ranked two-subset,
 // (4,4) mode 7
