@@ -92,17 +92,18 @@ struct View {
 };
 ITW_HD u32 view_tex(const View& v, int k)
 {
-    u32 t = v.b->tex[k];
-    if (v.rot < 3) {
-        u32 sel = (0x3210u & ~(0xFu << (4 * v.rot))) | (7u << (4 * v.rot));     // byte `rot` <- byte 3 of the 2nd operand
-        t = byte_perm(t, v.alpha ? t : 0xFFFFFFFFu, sel);
-    }
-    return t;
+    const u32 t = v.b->tex[k];
+    // byte `rot` <- byte 3 of the 2nd operand; rot = 3 with alpha reproduces t, so only "rot = 3 without alpha" (identity
+    // views of RGB profiles) needs the plain selector
+    const u32 swap_sel = (0x3210u & ~(0xFu << (4 * v.rot))) | (7u << (4 * v.rot));
+    const u32 sel = (v.rot < 3) ? swap_sel : 0x3210u;
+    return byte_perm(t, v.alpha ? t : 0xFFFFFFFFu, sel);
 }
-ITW_HD u32 view_plane(const View& v, int c, int i)
+ITW_HD u32 view_plane(const View& v, int c, int i)          // branch-free: one load from a selected plane, one select
 {
-    if (c == v.rot) return v.alpha ? v.b->plane[3][i] : 0xFFFFFFFFu;
-    return v.b->plane[c][i];
+    const bool swapped = (c == v.rot);
+    const u32 p = v.b->plane[swapped ? 3 : c][i];
+    return (swapped && !v.alpha) ? 0xFFFFFFFFu : p;
 }
 ITW_HD u32 nibble_to_bytemask(u32 nib) { return (((nib & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
@@ -340,7 +341,13 @@ ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
     // the reference's separate multiply and add.
     // Modes 0-3 never emit a 4th component and their index search ignores it; it only matters when it votes
     // (alpha profiles refining modes 0/3, quirk Q1).  Otherwise it is skipped (its byte stays 0).
-    const int ncomp = (mode <= 3 && votes <= 3) ? 3 : 4;
+    const bool four = !(mode <= 3 && votes <= 3);
+    // Branch-free per component: the no-p-bit family is the p-bit formula with scale 1 instead of 1/2 (t*1 + 0.5 rounds
+    // once, like t + 0.5) and both candidates equal.  Components 0..2 always take part and always vote (votes >= 3);
+    // only the fourth is conditional.
+    const bool plain = (family == 2);
+    const float half = plain ? 1.0f : 0.5f;
+    const int step = plain ? 1 : 2, top0 = plain ? top : top - 1;
     u32 cand0[2] = {0u, 0u}, cand1[2] = {0u, 0u};
     bool pick1[2] = {false, false};
     float e0 = 0.0f, e1 = 0.0f;
@@ -350,22 +357,16 @@ ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
         u32 c0 = 0u, c1 = 0u;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            if (c >= ncomp) continue;
+            if (c == 3 && !four) continue;
             const float x = ep[4 * i + c];
             const float t = div255(x) * ftop;
-            int v0, v1;
-            if (family == 2) {
-                v0 = v1 = clampi(trunc_i(t + 0.5f), 0, top);
-            } else {                                                      // ((t - b)/2 + 0.5) truncated, *2 + b
-                v0 = clampi(trunc_i(fma_rn(t, 0.5f, 0.5f)) * 2, 0, top - 1);
-                v1 = clampi(trunc_i(fma_rn(t - 1.0f, 0.5f, 0.5f)) * 2 + 1, 1, top);
-            }
+            const int v0 = clampi(trunc_i(fma_rn(t, half, 0.5f)) * step, 0, top0);
+            const int v1p = clampi(trunc_i(fma_rn(t - 1.0f, 0.5f, 0.5f)) * 2 + 1, 1, top);      // ((t - 1)/2 + 0.5) truncated, *2 + 1
+            const int v1 = plain ? v0 : v1p;
             c0 |= (u32)v0 << (8 * c);
             c1 |= (u32)v1 << (8 * c);
-            if (c < votes) {
-                e0 += sq(x - (float)expand_bits(v0, vote_bits));
-                e1 += sq(x - (float)expand_bits(v1, vote_bits));
-            }
+            const float d0 = sq(x - (float)expand_bits(v0, vote_bits)), d1 = sq(x - (float)expand_bits(v1, vote_bits));
+            if (c < 3 || votes == 4) { e0 += d0; e1 += d1; }
         }
         const bool p = !(e0 < e1);
         if (i == 0) { cand0[0] = c0; cand1[0] = c1; pick1[0] = p; }
@@ -471,12 +472,11 @@ ITW_HD_NOINLINE Bc7Seg bc7_solve(const Bc7Block* blk, int rot, int alpha, int bi
         sq1 = dp4a_u8(qm, 0x01010101u, sq1);
         sqq = dp4a_u8(qm, qm, sqq);
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (c < channels) {
-                const u32 p = view_plane(v, c, i);
-                sum[c] = dp4a_u8(ones, p, sum[c]);
-                atb1[c] = dp4a_u8(xm, p, atb1[c]);
-            }
+        for (int c = 0; c < 4; c++) {                           // channels >= 3; an unused fourth channel sums zeros
+            const u32 p = (c < 3 || channels == 4) ? view_plane(v, c, i) : 0u;
+            sum[c] = dp4a_u8(ones, p, sum[c]);
+            atb1[c] = dp4a_u8(xm, p, atb1[c]);
+        }
     }
     const float ftop = (float)top, count = (float)popcount16(mask & 0xFFFFu);
     const float fsq1 = (float)sq1, fsqq = (float)sqq;
@@ -487,16 +487,16 @@ ITW_HD_NOINLINE Bc7Seg bc7_solve(const Bc7Block* blk, int rot, int alpha, int bi
     float scale = ftop / det;
     bool flat = fabsf(det) < 0.001f;
 #pragma unroll
-    for (int c = 0; c < 4; c++)
-        if (c < channels) {
-            const float fs = (float)sum[c], fa1 = (float)atb1[c];
-            float atb2 = ftop * fs - fa1;
-            float a = (fa1 * cyy - atb2 * cxy) * scale;
-            float b = (atb2 * cxx - fa1 * cxy) * scale;
-            if (flat) { a = fs / count; b = a; }
-            ep[c] = a;
-            ep[4 + c] = b;
-        }
+    for (int c = 0; c < 4; c++) {
+        const float fs = (float)sum[c], fa1 = (float)atb1[c];
+        float atb2 = ftop * fs - fa1;
+        float a = (fa1 * cyy - atb2 * cxy) * scale;
+        float b = (atb2 * cxx - fa1 * cxy) * scale;
+        if (flat) { a = fs / count; b = a; }
+        const bool used = (c < 3 || channels == 4);
+        ep[c] = used ? a : 0.0f;
+        ep[4 + c] = used ? b : 0.0f;
+    }
     return seg;
 }
 
@@ -923,8 +923,10 @@ ITW_HD void bc7_phase_winners(int lane, Bc7Warp& W, const Bc7Params& P, int ma, 
 }
 ITW_HD void bc7_phase_chains(int lane, Bc7Warp& W, const Bc7Params& P)
 {
-    const int nroles = bc7_role_count(P);
-    for (int t = lane; t < W.nvalid * nroles; t += 32) bc7_chain(W, P, lane, t / nroles, t % nroles);
+    // role-major task order: the lanes of a warp pass hold the same KIND of role (partitioned / mode 4-5 / mode 6) for
+    // different blocks, so each kind's code path is walked once per pass instead of once per block
+    const int nroles = bc7_role_count(P), nv = W.nvalid;
+    for (int t = lane; t < nv * nroles; t += 32) bc7_chain(W, P, lane, t % nv, t / nv);
 }
 // first strict minimum over the roles in the reference's order, then the 16-byte store; K:2027
 ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* dst, long long first_block)
