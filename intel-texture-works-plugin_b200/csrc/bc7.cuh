@@ -486,13 +486,16 @@ ITW_HD_NOINLINE Bc7Seg bc7_solve(const Bc7Block* blk, int rot, int alpha, int bi
     float det = cxx * cyy - cxy * cxy;
     float scale = ftop / det;
     bool flat = fabsf(det) < 0.001f;
+    const float rcount = 1.0f / count;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const float fs = (float)sum[c], fa1 = (float)atb1[c];
         float atb2 = ftop * fs - fa1;
         float a = (fa1 * cyy - atb2 * cxy) * scale;
         float b = (atb2 * cxx - fa1 * cxy) * scale;
-        if (flat) { a = fs / count; b = a; }
+        // integer sum / integer count (1..16): the exact FMA-corrected quotient (tests/test_exact_division.py); a plain
+        // IEEE division would take its slow path for every zero sum
+        if (flat) { a = div_by_rcp(fs, count, rcount); b = a; }
         const bool used = (c < 3 || channels == 4);
         ep[c] = used ? a : 0.0f;
         ep[4 + c] = used ? b : 0.0f;
