@@ -608,7 +608,8 @@ ITW_HD void bc7_write_mode6(u32* out, u32 qa, u32 qb, u32 i0, u32 i1)
 // integers, so the index search and the least-squares sums are exact integer arithmetic; the projection
 // (x - e0)/(e1 - e0 + 0.001f) keeps the reference's float expression (K:1510) with the exact quotient
 // (domain proved in tests/test_exact_division.py).
-ITW_HD int scalar_texel(const Bc7Block* blk, int k, int shift) { return (int)((blk->tex[k] >> shift) & 255u); }
+// The sixteen texels of the channel are the four packed words of its plane (pl[i] byte j = texel 4i+j); the palette
+// (at most 8 byte-sized entries) is packed into one 64-bit register and read with a shift.
 ITW_HD void scalar_quantise(int (&q)[2], int (&e)[2], const float (&ep)[2], int epbits)
 {
     const int top = (1 << epbits) - 1;
@@ -618,45 +619,59 @@ ITW_HD void scalar_quantise(int (&q)[2], int (&e)[2], const float (&ep)[2], int 
         e[i] = expand_bits(q[i], epbits);
     }
 }
-ITW_HD int scalar_assign(u32& idx0, u32& idx1, const Bc7Block* blk, int shift, int bits, const int (&e)[2])
+ITW_HD int scalar_assign(u32& idx0, u32& idx1, const u32 (&pl)[4], int bits, const int (&e)[2])
 {
     const int levels = 1 << bits;
     const float flevels = (float)levels;
     const float den = (float)(e[1] - e[0]) + 0.001f, rden = 1.0f / den;
-    u32 out0 = 0u, out1 = 0u;
-    int total = 0;
-#pragma unroll 1
-    for (int k = 0; k < 16; k++) {
-        const int a = scalar_texel(blk, k, shift);
-        const float proj = div_by_rcp((float)(a - e[0]), den, rden);
-        const int q1 = clampi(trunc_i(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);
-        const int w0 = bc7_weight(bits, q1 - 1), w1 = bc7_weight(bits, q1);
-        const int d0 = (((64 - w0) * e[0] + w0 * e[1] + 32) >> 6) - a;
-        const int d1 = (((64 - w1) * e[0] + w1 * e[1] + 32) >> 6) - a;
-        const int err0 = d0 * d0, err1 = d1 * d1;
-        const bool first = err0 < err1;
-        total += first ? err0 : err1;
-        const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
-        if (k < 8) out0 += bq; else out1 += bq;
+    unsigned long long pal = 0ull;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int w = bc7_weight(bits, q);
+        const u32 v = (q < levels) ? (u32)(((64 - w) * e[0] + w * e[1] + 32) >> 6) : 0u;
+        pal |= (unsigned long long)v << (8 * q);
     }
-    idx0 = out0;
-    idx1 = out1;
+    u32 out[2] = {0u, 0u};
+    int total = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll 1
+        for (int i = 0; i < 2; i++) {                          // one plane word = four texels per iteration
+            const u32 word = pl[2 * h + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int a = (int)((word >> (8 * j)) & 255u);
+                const float proj = div_by_rcp((float)(a - e[0]), den, rden);
+                const int q1 = clampi(trunc_i(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);
+                const u32 two = (u32)(pal >> (8 * (q1 - 1)));  // entries q1-1 and q1
+                const int d0 = (int)(two & 255u) - a, d1 = (int)((two >> 8) & 255u) - a;
+                const int err0 = d0 * d0, err1 = d1 * d1;
+                const bool first = err0 < err1;
+                total += first ? err0 : err1;
+                out[h] += (u32)(first ? q1 - 1 : q1) << (16 * i + 4 * j);
+            }
+        }
+    }
+    idx0 = out[0];
+    idx1 = out[1];
     return total;
 }
-ITW_HD void scalar_solve(float (&ep)[2], const Bc7Block* blk, int shift, int bits, u32 idx0, u32 idx1)
+ITW_HD void scalar_solve(float (&ep)[2], const u32 (&pl)[4], int bits, u32 idx0, u32 idx1)
 {
-    const int itop = (1 << bits) - 1;
-    int iatb1 = 0, isq1 = 0, isqq = 0, isum = 0;
-#pragma unroll 1
-    for (int k = 0; k < 16; k++) {
-        const int a = scalar_texel(blk, k, shift);
-        const int q = (int)(((k < 8 ? idx0 : idx1) >> (4 * (k & 7))) & 15u);
-        isq1 += q;
-        isqq += q * q;
-        isum += a;
-        iatb1 += (itop - q) * a;
+    const u32 utop = (1u << bits) - 1u;
+    u32 usq1 = 0u, usqq = 0u, usum = 0u, uatb1 = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u32 n = (((i < 2) ? idx0 : idx1) >> (16 * (i & 1))) & 0xFFFFu;     // four 4-bit indices ...
+        n = (n | (n << 8)) & 0x00FF00FFu;
+        n = (n | (n << 4)) & 0x0F0F0F0Fu;                                  // ... one per byte
+        const u32 xm = utop * 0x01010101u - n;                             // (levels-1) - q, bytewise, no borrows
+        usq1 = dp4a_u8(n, 0x01010101u, usq1);
+        usqq = dp4a_u8(n, n, usqq);
+        usum = dp4a_u8(pl[i], 0x01010101u, usum);
+        uatb1 = dp4a_u8(xm, pl[i], uatb1);
     }
-    const float top = (float)itop, atb1 = (float)iatb1, sq1 = (float)isq1, sqq = (float)isqq, sum = (float)isum;
+    const float top = (float)utop, atb1 = (float)uatb1, sq1 = (float)usq1, sqq = (float)usqq, sum = (float)usum;
     float atb2 = top * sum - atb1;
     float cxx = 16.0f * sq(top) - (2.0f * top) * sq1 + sqq;
     float cyy = sqq;
@@ -666,31 +681,35 @@ ITW_HD void scalar_solve(float (&ep)[2], const Bc7Block* blk, int shift, int bit
     ep[0] = clamp_sse((atb1 * cyy - atb2 * cxy) * scale, 0.0f, 255.0f);
     ep[1] = clamp_sse((atb2 * cxx - atb1 * cxy) * scale, 0.0f, 255.0f);
     if (fabsf(det) < 0.001f) {
-        ep[0] = sum / 16.0f;
+        ep[0] = sum * 0.0625f;                                             // sum / 16, exact
         ep[1] = ep[0];
     }
 }
 struct Bc7Scalar { int err, q0, q1; u32 idx0, idx1; };
 ITW_HD_NOINLINE Bc7Scalar bc7_scalar_channel(const Bc7Block* blk, int rotation, int abits, int aepbits, int rch)
 {
-    const int shift = 8 * rotation;
+    u32 pl[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) pl[i] = blk->plane[rotation][i];
     int lo = 255, hi = 0;                                        // K:1542-1548
-#pragma unroll 1
-    for (int k = 0; k < 16; k++) {
-        const int a = scalar_texel(blk, k, shift);
-        lo = mini(lo, a);
-        hi = maxi(hi, a);
-    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int a = (int)((pl[i] >> (8 * j)) & 255u);
+            lo = mini(lo, a);
+            hi = maxi(hi, a);
+        }
     float ep[2] = {(float)lo, (float)hi};
     int q[2], e[2];
     u32 a0, a1;
     scalar_quantise(q, e, ep, aepbits);
-    int err = scalar_assign(a0, a1, blk, shift, abits, e);
+    int err = scalar_assign(a0, a1, pl, abits, e);
 #pragma unroll 1
     for (int it = 0; it < rch; it++) {
-        scalar_solve(ep, blk, shift, abits, a0, a1);
+        scalar_solve(ep, pl, abits, a0, a1);
         scalar_quantise(q, e, ep, aepbits);
-        err = scalar_assign(a0, a1, blk, shift, abits, e);
+        err = scalar_assign(a0, a1, pl, abits, e);
     }
     return Bc7Scalar{err, q[0], q[1], a0, a1};
 }
