@@ -38,6 +38,9 @@ struct ThreadCtx {
     uint8_t* d_in = nullptr;  size_t d_in_cap = 0;
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* d_mid = nullptr; size_t d_mid_cap = 0;      // itw_encode_pixels: the converted surface between the two kernels
+    // band pipeline of the compute-bound encoders (encode_banded): copy-in / copy-out streams and per-band events
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t band_in[4] = {nullptr, nullptr, nullptr, nullptr}, band_done[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 0;
     std::string err;
     // itw_encode_batch: three copy/compute lanes so that H2D of tile i+1, the kernel of tile i and
@@ -56,6 +59,14 @@ struct ThreadCtx {
         if (ev1) cudaEventDestroy(ev1);
         cudaFree(d_in); cudaFree(d_out); cudaFree(d_mid);
         d_mid = nullptr; d_mid_cap = 0;
+        if (copy_in) cudaStreamDestroy(copy_in);
+        if (copy_out) cudaStreamDestroy(copy_out);
+        copy_in = copy_out = nullptr;
+        for (int i = 0; i < 4; i++) {
+            if (band_in[i]) cudaEventDestroy(band_in[i]);
+            if (band_done[i]) cudaEventDestroy(band_done[i]);
+            band_in[i] = band_done[i] = nullptr;
+        }
         for (auto& l : lanes) { if (l.stream) cudaStreamDestroy(l.stream); cudaFree(l.d_in); cudaFree(l.d_out); l = Lane(); }
         stream = nullptr; ev0 = ev1 = nullptr; d_in = d_out = nullptr; d_in_cap = d_out_cap = 0;
         cudaGetLastError();
@@ -206,6 +217,66 @@ int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* setting
 
 int encode_many(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings);
 
+// Host surface -> host blocks for the COMPUTE-bound encoders (BC7, BC6H): the surface is cut into four row bands whose
+// H2D copies, kernels and D2H copies run on three streams, so that all but the first (small) band's input copy and all
+// but the last band's output copy hide behind the kernels.  (For BC1-BC5 the copies ARE the cost -- see encode_any.)
+// Bands are whole block rows; the kernels see each band as an independent surface, exactly as the reference's own
+// callers do (win32Threads.cpp:217-230), so the output is unchanged.
+int encode_banded(int format, const rgba_surface* src, uint8_t* dst, const void* settings, const FormatInfo& f)
+{
+    ThreadCtx& c = tls;
+    if (!c.copy_in) {
+        ITW_CUDA(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
+        ITW_CUDA(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; i++) {
+            ITW_CUDA(cudaEventCreateWithFlags(&c.band_in[i], cudaEventDisableTiming));
+            ITW_CUDA(cudaEventCreateWithFlags(&c.band_done[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t row_bytes = (size_t)src->width * f.texel_bytes;
+    const size_t block_row_bytes = (size_t)(src->width >> 2) * f.bpb;
+    const int block_rows = src->height >> 2;
+    if (grow(c.d_in, c.d_in_cap, row_bytes * src->height)) return -1;
+    if (grow(c.d_out, c.d_out_cap, block_row_bytes * block_rows)) return -1;
+    // 1/16 of the rows first (its copy is the only exposed one), then three equal parts
+    int first[5];
+    first[0] = 0;
+    first[1] = block_rows / 16 > 0 ? block_rows / 16 : 1;
+    const int rest = block_rows - first[1];
+    first[2] = first[1] + rest / 3;
+    first[3] = first[1] + (2 * rest) / 3;
+    first[4] = block_rows;
+    for (int b = 0; b < 4; b++) {
+        const int r0 = first[b], r1 = first[b + 1];
+        if (r1 <= r0) continue;
+        const size_t rows = (size_t)(r1 - r0) * 4;
+        uint8_t* d_band = c.d_in + (size_t)r0 * 4 * row_bytes;
+        const uint8_t* h_band = src->ptr + (size_t)r0 * 4 * (size_t)src->stride;
+        if ((size_t)src->stride == row_bytes)
+            ITW_CUDA(cudaMemcpyAsync(d_band, h_band, row_bytes * rows, cudaMemcpyHostToDevice, c.copy_in));
+        else
+            ITW_CUDA(cudaMemcpy2DAsync(d_band, row_bytes, h_band, (size_t)src->stride, row_bytes, rows, cudaMemcpyHostToDevice, c.copy_in));
+        ITW_CUDA(cudaEventRecord(c.band_in[b], c.copy_in));
+        ITW_CUDA(cudaStreamWaitEvent(c.stream, c.band_in[b], 0));
+        if (b == 0) ITW_CUDA(cudaEventRecord(c.ev0, c.stream));
+        const SurfaceView v{d_band, src->width, (int)rows, (int)row_bytes};
+        uint8_t* d_blocks = c.d_out + (size_t)r0 * block_row_bytes;
+        if (launch(format, v, d_blocks, settings, c.stream)) {          // bad settings: nothing may stay in flight towards dst
+            cudaStreamSynchronize(c.copy_in); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(c.copy_out);
+            return -1;
+        }
+        ITW_CUDA(cudaEventRecord(c.band_done[b], c.stream));
+        ITW_CUDA(cudaStreamWaitEvent(c.copy_out, c.band_done[b], 0));
+        ITW_CUDA(cudaMemcpyAsync(dst + (size_t)r0 * block_row_bytes, d_blocks, (size_t)(r1 - r0) * block_row_bytes, cudaMemcpyDeviceToHost,
+                                 c.copy_out));
+    }
+    ITW_CUDA(cudaEventRecord(c.ev1, c.stream));
+    c.timed = true;
+    ITW_CUDA(cudaStreamSynchronize(c.copy_out));
+    ITW_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
 // The CompressBlocks* path: src and dst may each be host or device memory.
 int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* settings)
 {
@@ -221,6 +292,8 @@ int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* se
     const size_t row_bytes = (size_t)src->width * f.texel_bytes;
     const size_t out_bytes = (size_t)(src->width >> 2) * (src->height >> 2) * f.bpb;
     const bool src_dev = is_device_pointer(src->ptr), dst_dev = is_device_pointer(dst);
+    if (!src_dev && !dst_dev && (format == ITW_FORMAT_BC7 || format == ITW_FORMAT_BC6H) && src->height >= 256)
+        return encode_banded(format, src, dst, settings, f);
 
     // Device-resident operands were produced by the caller's own streams.  The legacy default stream orders
     // after every blocking stream (torch's default stream included), which gives the synchronous call the

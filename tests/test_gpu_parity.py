@@ -182,3 +182,34 @@ def test_batch_entry_streams_independent_tiles():
                      [o.data_ptr() for o in douts], settings)
     torch.cuda.synchronize()
     assert all(np.array_equal(o.cpu().numpy(), w) for o, w in zip(douts, want))
+
+
+def test_banded_host_path_equals_device_path_and_oracle():
+    """Host surfaces of 256+ rows go through the band pipeline of the compute-bound encoders (copy-in, kernels and
+    copy-out on three streams): same bytes as the single-launch device path, and as the oracle on a crop."""
+    import torch
+    lib, oracle = T.product(), T.oracle()
+    for fmt, prof, h, w, pad in (("BC7", "veryfast", 1024, 512, 0), ("BC7", "alpha_veryfast", 260, 64, 16), ("BC6H", "bc6h_veryfast", 516, 256, 8)):
+        texel = T.binding.FORMATS[fmt][2]
+        img = _rand_img(fmt, h, w, seed=h + w)
+        settings = lib.profile(prof)
+        d_in = torch.from_numpy(img.copy().view(np.uint8).reshape(-1)).cuda()
+        d_out = torch.zeros((h // 4) * (w // 4) * 16, dtype=torch.uint8, device="cuda")
+        lib.encode_raw(fmt, d_in.data_ptr(), w, h, w * texel, d_out.data_ptr(), settings)
+        want = d_out.cpu().numpy()
+        assert np.array_equal(lib.encode(fmt, img, settings), want), (fmt, "tight rows")
+        if pad:                                                        # padded host stride
+            wide = np.zeros((h, w * texel + pad), np.uint8)
+            wide[:, :w * texel] = img.view(np.uint8).reshape(h, w * texel)
+            got = np.zeros_like(want)
+            lib.encode_raw(fmt, wide.ctypes.data, w, h, wide.strides[0], got.ctypes.data, settings)
+            assert np.array_equal(got, want), (fmt, "padded stride")
+        crop = np.ascontiguousarray(img[:64, :64])
+        rows = want.reshape(h // 4, (w // 4) * 16)[:16, :16 * 16].reshape(-1)
+        assert np.array_equal(T.run(oracle, fmt, crop, prof), rows), (fmt, "oracle crop")
+    bad = lib.profile("slow")                                          # an error inside the pipeline leaves nothing in flight
+    bad.fastSkipTreshold_mode1 = 65
+    with pytest.raises(RuntimeError, match="fastSkipTreshold"):
+        lib.encode("BC7", np.zeros((512, 64, 4), np.uint8), bad)
+    assert np.array_equal(lib.encode("BC7", _rand_img("BC7", 256, 64, seed=1), lib.profile("veryfast")),
+                          lib.encode("BC7", _rand_img("BC7", 256, 64, seed=1), lib.profile("veryfast")))
