@@ -190,9 +190,19 @@ size_t itw_mip_scratch_bytes(int width, int height, int levels, int first_level)
  * level l (out[0] = *level0 when no padding is needed).  Enqueued on `cuda_stream`; returns 0 on success. */
 int itw_generate_mips_device(const rgba_surface* level0, int levels, rgba_surface* out, uint8_t* scratch,
                              void* cuda_stream);
-/* The complete save path of one LDR texture (IntelPlugin.cpp:2117-2171): `tops` = array_size HOST or
- * device RGBA8 surfaces holding level 0 only; mips are generated on the GPU, every level is encoded, and
- * the DDS file is written to `file` (host).  Returns the file size, 0 on error. */
+/* RGBA16F chain for BC6H textures.  For BC6H the plug-in forces DirectXTex's own (non-WIC) generator
+ * (IntelPlugin.cpp:2117-2127), which IS in the reference tree: box filter ((p0+p1)+p2+p3)*0.25 in float
+ * when width and height are powers of two, the two-tap linear filter otherwise
+ * (DirectXTex/DirectXTexMipmaps.cpp:715-905, Filters.h:33-112), each level re-read from its stored halves.
+ * Same conventions as itw_generate_mips_device with 8-byte texels; scratch needs TWICE
+ * itw_mip_scratch_bytes(...).  Bit-exact to that code including its stale fourth tap on wide textures
+ * (csrc/mips_f16.cuh); half conversions as in section 6. */
+int itw_generate_mips_device_f16(const rgba_surface* level0, int levels, rgba_surface* out, uint8_t* scratch,
+                                 void* cuda_stream);
+/* The complete save path of one texture (IntelPlugin.cpp:2117-2171): `tops` = array_size HOST or
+ * device surfaces holding level 0 only (RGBA8; RGBA16F for BC6H_UF16 / _SF16); mips are generated on the
+ * GPU, every level is encoded, and the DDS file is written to `file` (host).  Returns the file size, 0 on
+ * error. */
 size_t itw_dds_encode_texture(const itw_dds_desc* desc, const rgba_surface* tops, const void* settings,
                               uint8_t* file, size_t capacity);
 

@@ -21,6 +21,7 @@
 #include "mips.cuh"
 #include "decode.cuh"
 #include "frontend.cuh"
+#include "mips_f16.cuh"
 #include "itw_params.h"
 
 using namespace itw;

@@ -1,0 +1,106 @@
+// mips_f16.cuh -- mip chain of RGBA16F textures (the BC6H save path), pinned to the reference's own filter code.
+//
+// For BC6H the plug-in forces DirectXTex's non-WIC generator (IntelPlugin.cpp:2117-2127: TEX_FILTER_DEFAULT |
+// TEX_FILTER_SEPARATE_ALPHA | TEX_FILTER_FORCE_NON_WIC), i.e. code that IS in the reference tree:
+//   GenerateMipMaps                DirectXTex/DirectXTexMipmaps.cpp:2611-2650   filter = BOX if width and height are powers
+//                                                                               of two, else LINEAR -- chosen ONCE from level 0
+//   _Generate2DMipsBoxFilter       :715-805    with AVERAGE4 (Filters.h:33-39):  ((p0 + p1) + p2) + p3) * 0.25
+//   _Generate2DMipsLinearFilter    :809-905    with _CreateLinearFilter / BILINEAR_INTERPOLATE (Filters.h:60-112)
+// Every level is read back from its stored halves (XMLoadHalf4) and written through XMStoreHalf4, so a level depends only
+// on the previous level's half bits: one independent pass per level, one thread per output texel.  Float operations are
+// the reference's, in its order, without contraction; the half conversions are the DirectXMath 3.06 restatement of
+// frontend.cuh (same caveat: DirectXMath is not in the reference tree).  Padding to multiples of 4 (IntelPlugin.cpp:892-928)
+// is the coordinate clamp used by mips.cuh.
+//
+// Reference quirk kept on purpose (bit-exact drop-in): in the box loop the fourth tap pointer `urow3` is computed ONCE as
+// `urow1 + 1` (:738) and is only redirected when the width reaches 1 (:749-752).  When the HEIGHT reaches 1 first (wide
+// power-of-two textures) `urow1` is redirected to `urow0` (:744-747) but `urow3` keeps pointing into the second scanline
+// buffer, which is no longer loaded: the fourth tap then reads the LAST ROW of the last source level that still had two
+// rows, at column 2x+1.  `stale_row` carries that row; a buffer that was never loaded (level 0 itself one texel high) reads
+// as zero (rule F6).
+#pragma once
+#include "frontend.cuh"
+
+namespace itw {
+
+struct MipTap { int u0, u1; float w0, w1; };
+// _CreateLinearFilter for one destination coordinate, clamp addressing; Filters.h:67-100
+ITW_HD MipTap mip_linear_tap(int source, int dest, int u)
+{
+    const float scale = (float)source / (float)dest;
+    const float srcB = ((float)u + 0.5f) * scale + 0.5f;
+    int isrcB = (int)srcB, isrcA = isrcB - 1;
+    if (isrcA < 0) isrcA = 0;
+    if (isrcB >= source) isrcB = source - 1;
+    const float weight = 1.0f + (float)isrcB - srcB;
+    return MipTap{isrcA, isrcB, weight, 1.0f - weight};
+}
+// the two-tap degenerate cases of the box loop: a 1-texel-wide (-high) source reads the same column (row) twice; :742-752
+ITW_HD MipTap mip_box_tap(int source, int u)
+{
+    return MipTap{2 * u, (source > 1) ? 2 * u + 1 : 2 * u, 0.0f, 0.0f};
+}
+ITW_HD void mip_load_f16(float (&v)[4], const uint8_t* row, int x)
+{
+    const u32* p = reinterpret_cast<const u32*>(row + (size_t)x * 8);
+    const u32 lo = p[0], hi = p[1];
+    v[0] = front_float_from_half(lo & 0xFFFFu);
+    v[1] = front_float_from_half(lo >> 16);
+    v[2] = front_float_from_half(hi & 0xFFFFu);
+    v[3] = front_float_from_half(hi >> 16);
+}
+// One texel of the padded level (dw x dh valid, any x / y inside the padded storage) from the previous level's valid region
+ITW_HD void mip_f16_texel(u32 (&out)[2], const uint8_t* src, int sw, int sh, long long sstride, int dw, int dh, int x, int y, bool box,
+                          const uint8_t* stale_row)
+{
+    const int cx = mini(x, dw - 1), cy = mini(y, dh - 1);
+    const MipTap tx = box ? mip_box_tap(sw, cx) : mip_linear_tap(sw, dw, cx);
+    const MipTap ty = box ? mip_box_tap(sh, cy) : mip_linear_tap(sh, dh, cy);
+    const uint8_t* r0 = src + (long long)ty.u0 * sstride;
+    const uint8_t* r1 = src + (long long)ty.u1 * sstride;
+    float a[4], b[4], c[4], d[4], res[4];
+    mip_load_f16(a, r0, tx.u0);       // (row u0, column u0)
+    mip_load_f16(b, r0, tx.u1);       // (row u0, column u1)
+    mip_load_f16(c, r1, tx.u0);       // (row u1, column u0)
+    mip_load_f16(d, r1, tx.u1);       // (row u1, column u1)
+    if (box && sh <= 1 && sw > 1) {   // the stale fourth tap, see the header
+        if (stale_row) mip_load_f16(d, stale_row, 2 * cx + 1);
+        else d[0] = d[1] = d[2] = d[3] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (box) {
+            // AVERAGE4(urow0[x2], urow1[x2], urow0[x2+1], urow1[x2+1])
+            res[i] = (((a[i] + c[i]) + b[i]) + d[i]) * 0.25f;
+        } else {
+            // y.w0 * (r0[x.u0]*x.w0 + r0[x.u1]*x.w1) + y.w1 * (r1[x.u0]*x.w0 + r1[x.u1]*x.w1)
+            res[i] = (ty.w0 * (a[i] * tx.w0 + b[i] * tx.w1)) + (ty.w1 * (c[i] * tx.w0 + d[i] * tx.w1));
+        }
+    }
+    out[0] = front_half_from_float(res[0]) | (front_half_from_float(res[1]) << 16);
+    out[1] = front_half_from_float(res[2]) | (front_half_from_float(res[3]) << 16);
+}
+
+#if defined(__CUDACC__)
+// grid: (ceil(pw/64), ph); thread = one padded output texel.  32 B read + 8 B written per texel.
+__global__ void __launch_bounds__(64) mip_f16_kernel(const uint8_t* __restrict__ src, int sw, int sh, long long sstride, uint8_t* __restrict__ dst,
+                                                     int dw, int dh, int pw, long long dstride, int box, const uint8_t* __restrict__ stale_row)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y;
+    if (x >= pw) return;
+    u32 out[2];
+    mip_f16_texel(out, src, sw, sh, sstride, dw, dh, x, y, box != 0, stale_row);
+    *reinterpret_cast<uint2*>(dst + (long long)y * dstride + (long long)x * 8) = make_uint2(out[0], out[1]);
+}
+// edge-replicating copy of level 0 into padded storage (8-byte texels)
+__global__ void __launch_bounds__(64) pad_f16_kernel(const uint8_t* __restrict__ src, int sw, int sh, long long sstride, uint8_t* __restrict__ dst, int pw,
+                                                     long long dstride)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y;
+    if (x >= pw) return;
+    const u32* p = reinterpret_cast<const u32*>(src + (long long)mini(y, sh - 1) * sstride + (long long)mini(x, sw - 1) * 8);
+    *reinterpret_cast<uint2*>(dst + (long long)y * dstride + (long long)x * 8) = make_uint2(p[0], p[1]);
+}
+#endif
+
+}  // namespace itw

@@ -168,3 +168,85 @@ extern "C" int oracle_itw_convert_pixels(int format, const itw_pixel_source* s, 
     }
     return 0;
 }
+
+// =====================================================================================================================
+// RGBA16F mip chain of the BC6H save path: DirectXTex's non-WIC generators, restated in their scanline form.
+//   GenerateMipMaps                 DirectXTex/DirectXTexMipmaps.cpp:2611-2650 (BOX when both sizes are powers of two, else LINEAR)
+//   _Generate2DMipsBoxFilter        :715-805, AVERAGE4 Filters.h:33-39
+//   _Generate2DMipsLinearFilter     :809-905, _CreateLinearFilter / BILINEAR_INTERPOLATE Filters.h:60-112
+// Pinned by tests/test_mips_f16.py against the reference's own function bodies (oracle/build_ref_frontend.py).
+// `out` receives `levels` tightly packed levels one after the other.
+// =====================================================================================================================
+namespace {
+struct Tap { size_t u0, u1; float w0, w1; };
+void linear_taps(size_t source, size_t dest, std::vector<Tap>& lf)                 // Filters.h:67-100, clamp addressing
+{
+    lf.resize(dest);
+    const float scale = float(source) / float(dest);
+    for (size_t u = 0; u < dest; ++u) {
+        const float srcB = (float(u) + 0.5f) * scale + 0.5f;
+        ptrdiff_t isrcB = ptrdiff_t(srcB), isrcA = isrcB - 1;
+        if (isrcA < 0) isrcA = 0;
+        if (size_t(isrcB) >= source) isrcB = ptrdiff_t(source) - 1;
+        const float weight = 1.0f + float(isrcB) - srcB;
+        lf[u] = Tap{size_t(isrcA), size_t(isrcB), weight, 1.0f - weight};
+    }
+}
+void load_row(std::vector<float>& row, const uint16_t* src, size_t width)
+{
+    for (size_t i = 0; i < width * 4; i++) row[i] = float_from_half(src[i]);
+}
+}  // namespace
+
+extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int levels, uint16_t* out)
+{
+    memcpy(out, level0, (size_t)w * h * 8);
+    const bool box = w > 0 && h > 0 && !(w & (w - 1)) && !(h & (h - 1));
+    size_t width = (size_t)w, height = (size_t)h;
+    const uint16_t* src = out;
+    uint16_t* dst = out + width * height * 4;
+    // the box loop's scanline buffers live across levels (:730-739); `second` is only reloaded while the source has two rows,
+    // and the fourth tap keeps reading it when the height reaches one before the width does (reference behaviour)
+    std::vector<float> first((size_t)w * 4, 0.0f), second((size_t)w * 4, 0.0f), r0((size_t)w * 4), r1((size_t)w * 4);
+    std::vector<Tap> lx, ly;
+    for (int level = 1; level < levels; level++) {
+        const size_t nwidth = width > 1 ? width >> 1 : 1, nheight = height > 1 ? height >> 1 : 1;
+        if (box) {
+            for (size_t y = 0; y < nheight; y++) {
+                load_row(first, src + (height > 1 ? 2 * y : y) * width * 4, width);
+                if (height > 1) load_row(second, src + (2 * y + 1) * width * 4, width);
+                const std::vector<float>& u1 = height > 1 ? second : first;        // urow1
+                for (size_t x = 0; x < nwidth; x++) {
+                    const size_t x2 = x << 1;
+                    for (int c = 0; c < 4; c++) {
+                        const float p0 = first[x2 * 4 + c], p1 = u1[x2 * 4 + c];
+                        const float p2 = width > 1 ? first[(x2 + 1) * 4 + c] : first[x2 * 4 + c];            // urow2
+                        const float p3 = width > 1 ? second[(x2 + 1) * 4 + c] : u1[x2 * 4 + c];              // urow3 (stale when height <= 1)
+                        float v = p0 + p1;
+                        v = v + p2;
+                        v = v + p3;
+                        dst[(y * nwidth + x) * 4 + c] = half_from_float(v * 0.25f);
+                    }
+                }
+            }
+        } else {
+            linear_taps(width, nwidth, lx);
+            linear_taps(height, nheight, ly);
+            for (size_t y = 0; y < nheight; y++) {
+                load_row(r0, src + ly[y].u0 * width * 4, width);
+                load_row(r1, src + ly[y].u1 * width * 4, width);
+                for (size_t x = 0; x < nwidth; x++)
+                    for (int c = 0; c < 4; c++) {
+                        const float a = r0[lx[x].u0 * 4 + c] * lx[x].w0 + r0[lx[x].u1 * 4 + c] * lx[x].w1;
+                        const float b = r1[lx[x].u0 * 4 + c] * lx[x].w0 + r1[lx[x].u1 * 4 + c] * lx[x].w1;
+                        dst[(y * nwidth + x) * 4 + c] = half_from_float((ly[y].w0 * a) + (ly[y].w1 * b));
+                    }
+            }
+        }
+        src = dst;
+        dst += nwidth * nheight * 4;
+        width = nwidth;
+        height = nheight;
+    }
+    return 0;
+}

@@ -12,6 +12,7 @@
 #include "../../intel-texture-works-plugin_b200/csrc/mips.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/decode.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/frontend.cuh"
+#include "../../intel-texture-works-plugin_b200/csrc/mips_f16.cuh"
 
 using namespace itw;
 
@@ -120,6 +121,16 @@ int emu_itw_convert_pixels(int format, const itw_pixel_source* src, uint32_t fla
             memcpy(dst->ptr + (size_t)y * dst->stride + (size_t)x * texel, out, texel);
         }
     return 0;
+}
+// one padded RGBA16F mip level, texel by texel, through the kernel's own per-texel routine (csrc/mips_f16.cuh)
+void emu_mip_level_f16(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int pw, int ph, int box, const uint8_t* stale_row)
+{
+    for (int y = 0; y < ph; y++)
+        for (int x = 0; x < pw; x++) {
+            u32 out[2];
+            mip_f16_texel(out, src, sw, sh, sstride, dw, dh, x, y, box != 0, stale_row);
+            memcpy(dst + ((size_t)y * pw + x) * 8, out, 8);
+        }
 }
 // the product's profile tables (csrc/itw_params.h), exported so the emulation is self-contained
 #define EMU_BC7(name, row) void emu_GetProfile_##name(bc7_enc_settings* s) { bc7_fill_profile(s, row); }

@@ -60,6 +60,8 @@ def ref_frontend():
     lib.ref_convert_pixels.restype = ctypes.c_int
     lib.ref_convert_pixels.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_uint, ctypes.c_void_p]
+    lib.ref_mip_chain_f16.restype = ctypes.c_int
+    lib.ref_mip_chain_f16.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.ref_float_to_half.restype = ctypes.c_ushort
     lib.ref_float_to_half.argtypes = [ctypes.c_float]
     lib.ref_half_to_float.restype = ctypes.c_float
