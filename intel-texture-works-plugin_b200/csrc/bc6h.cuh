@@ -98,7 +98,7 @@ ITW_HD int bc6_quant1(float e, int bits)
     // +-0 / 65535 * top + 0.5 = 0.5 -> 0.  The never-written fourth component is always zero here and a zero
     // numerator sends the IEEE division to its slow path, so it is answered directly (same result).
     if (e == 0.0f) return 0;
-    return clampi(cvt_x86(e / (256.0f * 256.0f - 1.0f) * (float)top + 0.5f), 0, top);
+    return clampi(cvt_x86(div_by_rcp(e, 65535.0f, 1.0f / 65535.0f) * (float)top + 0.5f), 0, top);   // e / 65535, see bc6_assign
 }
 // 8*pairs values: quantise, clamp RGB into the entry's window, decode in place
 ITW_HD void bc6_quant_dequant(const Bc6Entry& E, int* q, float* ep, int pairs)
@@ -240,7 +240,7 @@ ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32
     const int levels = 1 << bits;
     const float flevels = (float)levels;
     int ea[2][3], eb[2][3];
-    float div[2];
+    float div[2], rdiv[2];
     const u32 D[2][3] = {{d00, d01, d02}, {d10, d11, d12}};
 #pragma unroll
     for (int j = 0; j < 2; j++) {
@@ -252,6 +252,7 @@ ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32
             d2 += sq((float)(eb[j][c] - ea[j][c]));          // K:1155; the difference of two exact integers is exact
         }
         div[j] = d2;
+        rdiv[j] = 1.0f / d2;                                 // inf when the endpoints coincide: 0 * inf = NaN below, as 0 / 0
     }
     float total = 0.0f;
     u32 out0 = 0u, out1 = 0u;
@@ -267,7 +268,9 @@ ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32
             t[c] = px[16 * c + k];
             proj += (t[c] - (float)a[c]) * (float)(b[c] - a[c]);
         }
-        proj /= (second ? div[1] : div[0]);
+        // the FMA-corrected quotient equals the IEEE quotient for every pair of normal floats (proved by exhaustion over
+        // all 2^46 significand pairs, tests/test_gpu_division.py); proj is 0 or >= 2^-22 in magnitude and div >= 1
+        proj = div_by_rcp(proj, second ? div[1] : div[0], second ? rdiv[1] : rdiv[0]);
         const int q1 = clampi(cvt_x86(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);   // proj*levels is exact
         const int w0 = bc7_weight(bits, q1 - 1), w1 = bc7_weight(bits, q1);
         float err0 = 0.0f, err1 = 0.0f;
