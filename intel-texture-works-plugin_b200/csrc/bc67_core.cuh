@@ -79,18 +79,21 @@ ITW_HD void masked_moments(float (&st)[15], const float* px, int mask, int chann
 // cov = sum(xy) - sum(x)*sum(y)/n; K:805-823.  Slots not owned by `channels` are zero.
 ITW_HD void covariance_of(float (&cov)[10], const float (&st)[15], int channels)
 {
-    cov[0] = st[0] - st[10] * st[10] / st[14];
-    cov[1] = st[1] - st[10] * st[11] / st[14];
-    cov[2] = st[2] - st[10] * st[12] / st[14];
-    cov[4] = st[4] - st[11] * st[11] / st[14];
-    cov[5] = st[5] - st[11] * st[12] / st[14];
-    cov[7] = st[7] - st[12] * st[12] / st[14];
+    // x / n with the FMA-corrected quotient: equal to the IEEE quotient for all normal operands (proved by exhaustion,
+    // tests/test_gpu_division.py; the numerators are 0 or products of texel sums, far from the subnormal range)
+    const float n = st[14], rn = 1.0f / n;
+    cov[0] = st[0] - div_by_rcp(st[10] * st[10], n, rn);
+    cov[1] = st[1] - div_by_rcp(st[10] * st[11], n, rn);
+    cov[2] = st[2] - div_by_rcp(st[10] * st[12], n, rn);
+    cov[4] = st[4] - div_by_rcp(st[11] * st[11], n, rn);
+    cov[5] = st[5] - div_by_rcp(st[11] * st[12], n, rn);
+    cov[7] = st[7] - div_by_rcp(st[12] * st[12], n, rn);
     cov[3] = cov[6] = cov[8] = cov[9] = 0.0f;
     if (channels == 4) {
-        cov[3] = st[3] - st[10] * st[13] / st[14];
-        cov[6] = st[6] - st[11] * st[13] / st[14];
-        cov[8] = st[8] - st[12] * st[13] / st[14];
-        cov[9] = st[9] - st[13] * st[13] / st[14];
+        cov[3] = st[3] - div_by_rcp(st[10] * st[13], n, rn);
+        cov[6] = st[6] - div_by_rcp(st[11] * st[13], n, rn);
+        cov[8] = st[8] - div_by_rcp(st[12] * st[13], n, rn);
+        cov[9] = st[9] - div_by_rcp(st[13] * st[13], n, rn);
     }
 }
 
@@ -102,8 +105,9 @@ ITW_HD void fit_segment_inl(float (&ep)[8], const float* px, int mask, int chann
     float st[15], cov[10], mean[4], axis[4];
     masked_moments(st, px, mask, channels);
     covariance_of(cov, st, channels);
+    const float rcount = 1.0f / st[14];
 #pragma unroll
-    for (int c = 0; c < 4; c++) mean[c] = (c < channels) ? st[10 + c] / st[14] : 0.0f;
+    for (int c = 0; c < 4; c++) mean[c] = (c < channels) ? div_by_rcp(st[10 + c], st[14], rcount) : 0.0f;
 
     const float inv_var = 1.0f / (256.0f * 256.0f);
 #pragma unroll
@@ -174,53 +178,6 @@ ITW_HD_NOINLINE int split_bound_key(const float* px, int shape, const float (&fu
     return shape + (int)((unsigned)cvt_x86(bound) * 64u);   // wrapping multiply, as the ISPC int does
 }
 
-// ---------------------------------------------------------------------------------------------
-// index search; K:1133-1193
-// ---------------------------------------------------------------------------------------------
-// Per texel: project on its subset's segment, then keep the better of the two neighbouring palette
-// entries, decoded with the integer BC7 interpolation.  The per-texel error is truncated through
-// int (cvttss2si) before it is summed -- K:1178-1189, which matters for BC6H (quirk Q3).
-// idx: sixteen 4-bit indices, texel k in nibble k%8 of word k/8.  ep = [subset][A rgba, B rgba].
-ITW_HD_NOINLINE float assign_indices(u32& idx0, u32& idx1, const float* px, int bits, const float* ep, u32 pattern,
-                            int channels)
-{
-    const int levels = 1 << bits;
-    const float flevels = (float)levels;
-    float total = 0.0f;
-    u32 out[2] = {0u, 0u};
-#pragma unroll 2
-    for (int k = 0; k < 16; k++) {
-        const float* e = ep + 8 * ((pattern >> (2 * k)) & 3u);
-        float proj = 0.0f, div = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (c < channels) {
-                float d = e[4 + c] - e[c];
-                proj += (px[16 * c + k] - e[c]) * d;
-                div += sq(d);
-            }
-        proj /= div;
-        int q1 = clampi(cvt_x86(proj * flevels + 0.5f), 1, levels - 1);
-        float fw0 = (float)bc7_weight(bits, q1 - 1), fw1 = (float)bc7_weight(bits, q1);
-        float err0 = 0.0f, err1 = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (c < channels) {
-                float d0 = (float)cvt_x86(((64.0f - fw0) * e[c] + fw0 * e[4 + c] + 32.0f) / 64.0f);
-                float d1 = (float)cvt_x86(((64.0f - fw1) * e[c] + fw1 * e[4 + c] + 32.0f) / 64.0f);
-                err0 += sq(d0 - px[16 * c + k]);
-                err1 += sq(d1 - px[16 * c + k]);
-            }
-        int best_err = cvt_x86(err1), best_q = q1;
-        if (err0 < err1) { best_err = cvt_x86(err0); best_q = q1 - 1; }
-        out[k >> 3] += (u32)best_q << (4 * (k & 7));
-        total += (float)best_err;
-    }
-    idx0 = out[0];
-    idx1 = out[1];
-    return total;
-}
-
 // Least-squares endpoints of one subset from its current indices; K:1198-1262
 ITW_HD void solve_endpoints_inl(float (&ep)[8], const float* px, int bits, u32 idx0, u32 idx1, int mask, int channels)
 {
@@ -262,7 +219,7 @@ ITW_HD void solve_endpoints_inl(float (&ep)[8], const float* px, int bits, u32 i
 }
 
 // ---------------------------------------------------------------------------------------------
-// BC7 endpoint quantisation; K:976-1128
+// small BC7 format helpers; K:976-981
 // ---------------------------------------------------------------------------------------------
 ITW_HD int expand_bits(int v, int bits)
 {
@@ -271,63 +228,6 @@ ITW_HD int expand_bits(int v, int bits)
 }
 ITW_HD int bc7_pairs(int mode) { return (mode == 0 || mode == 2) ? 3 : ((mode == 1 || mode == 3 || mode == 7) ? 2 : 1); }
 
-// One endpoint pair (8 values), in place: q receives the quantised integers, ep the decoded
-// values.  `channels` = components that vote on the p-bit (K:1011-1020); all four are produced.
-ITW_HD_NOINLINE void bc7_quantise_pair(int* q, float* ep, int mode, int channels)
-{
-    if (mode == 0 || mode == 3 || mode == 6 || mode == 7) {            // unique p-bits; K:983-1022
-        const int bits = (mode == 0) ? 4 : ((mode == 7) ? 5 : 7);
-        const int levels2 = (1 << bits) * 2 - 1;
-        const float flevels2 = (float)levels2;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            int cand0[4], cand1[4];
-            float e0 = 0.0f, e1 = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                float t = ep[4 * i + c] / 255.0f * flevels2;
-                int v0 = cvt_x86(t / 2.0f + 0.5f) * 2;                 // (t - 0)/2: subtracting 0.0f is exact
-                int v1 = cvt_x86((t - 1.0f) / 2.0f + 0.5f) * 2 + 1;
-                cand0[c] = clampi(v0, 0, levels2 - 1);
-                cand1[c] = clampi(v1, 1, levels2);
-                if (c < channels) {
-                    float d0 = (mode == 0) ? (float)expand_bits(cand0[c], 5) : (float)cand0[c];
-                    float d1 = (mode == 0) ? (float)expand_bits(cand1[c], 5) : (float)cand1[c];
-                    e0 += sq(ep[4 * i + c] - d0);
-                    e1 += sq(ep[4 * i + c] - d1);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; c++) q[4 * i + c] = (e0 < e1) ? cand0[c] : cand1[c];
-        }
-    } else if (mode == 1) {                                             // shared p-bit; K:1024-1052
-        int cand0[8], cand1[8];
-        float e0 = 0.0f, e1 = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            float t = ep[i] / 255.0f * 127.0f;
-            cand0[i] = clampi(cvt_x86(t / 2.0f + 0.5f) * 2, 0, 126);
-            cand1[i] = clampi(cvt_x86((t - 1.0f) / 2.0f + 0.5f) * 2 + 1, 1, 127);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                e0 += sq(ep[4 * j + c] - (float)expand_bits(cand0[4 * j + c], 7));
-                e1 += sq(ep[4 * j + c] - (float)expand_bits(cand1[4 * j + c], 7));
-            }
-#pragma unroll
-        for (int i = 0; i < 8; i++) q[i] = (e0 < e1) ? cand0[i] : cand1[i];
-    } else {                                                            // modes 2,4,5; K:1054-1065
-        const int top = (1 << ((mode == 5) ? 7 : 5)) - 1;
-#pragma unroll
-        for (int i = 0; i < 8; i++) q[i] = clampi(cvt_x86(ep[i] / 255.0f * (float)top + 0.5f), 0, top);
-    }
-    // decode; K:1093-1122
-    const int dbits = (mode == 3 || mode == 6) ? 8 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 5));
-#pragma unroll
-    for (int i = 0; i < 8; i++) ep[i] = (float)expand_bits(q[i], dbits);
-}
 
 // ---------------------------------------------------------------------------------------------
 // bitstream helpers; K:1694-1805
@@ -343,23 +243,6 @@ ITW_HD void put_indices(BitSink& s, u32 idx0, u32 idx1, int bits, int flips, int
         bool narrow = (k == 0) || (k == anchor1) || (k == anchor2);
         s.put(narrow ? bits - 1 : bits, (u32)q);
     }
-}
-// Make each subset's anchor index < levels/2 by swapping the subset's endpoints and mirroring its
-// indices; returns the texel mask of mirrored texels; K:1708-1733
-ITW_HD int orient_subsets(int* q, u32 idx0, u32 idx1, int bits, int pairs, int shape)
-{
-    const int half = (1 << bits) / 2;
-    int flips = 0;
-    for (int j = 0; j < pairs; j++) {
-        int k0 = shape_anchor(shape, j);
-        int v = (int)(((k0 < 8 ? idx0 : idx1) >> (4 * (k0 & 7))) & 15u);
-        if (v >= half) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) { int t = q[8 * j + c]; q[8 * j + c] = q[8 * j + 4 + c]; q[8 * j + 4 + c] = t; }
-            flips |= shape_mask(shape, j);
-        }
-    }
-    return flips;
 }
 // Single-subset variant (BC7 modes 4,5,6; BC6H one-region modes); K:1694-1706
 ITW_HD void orient_single(int* q, int width, u32& idx0, u32& idx1, int bits)
