@@ -218,9 +218,29 @@ ITW_HD int bc6_mode_epb(int mode)
     if (mode < 12) return (int)((t >> (5 * mode)) & 31ull);
     return (mode == 12) ? 12 : 16;
 }
+// delta bits of endpoints 1..3 per channel (r | g << 4 | b << 8); modes 9 and 10 store plain values
+ITW_HD u32 bc6_mode_delta_bits(int mode)
+{
+    switch (mode) {
+        case 0: case 5: return 0x555u;
+        case 1: return 0x666u;
+        case 2: return 0x445u;       // r 5, g 4, b 4
+        case 3: return 0x454u;       // r 4, g 5, b 4
+        case 4: return 0x544u;       // r 4, g 4, b 5
+        case 6: return 0x556u;       // r 6, g 5, b 5
+        case 7: return 0x565u;       // r 5, g 6, b 5
+        case 8: return 0x655u;       // r 5, g 5, b 6
+        case 11: return 0x999u;
+        case 12: return 0x888u;
+        case 13: return 0x444u;
+        default: return 0u;
+    }
+}
 // out[k][0] = r | g << 16, out[k][1] = b | 0x3C00 << 16 (half bit patterns, alpha = 1.0).  Returns false for the
-// reserved mode fields (decoded as opaque black, BC6HBC7.cpp:1088-1106).
-ITW_HD_NOINLINE bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
+// reserved mode fields (decoded as opaque black, BC6HBC7.cpp:1088-1106).  The twelve endpoint fields are gathered
+// into three 64-bit registers (per channel: endpoints 0..3, 16 bits each) -- no per-thread arrays, hence no local
+// memory (the array version wrote 349 MB of spills to DRAM for a 128 MB surface, profiles/r1_final2_decode_ncu.txt).
+ITW_HD bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
 {
     const u32 m2 = w[0] & 3u;
     const u32 field = (m2 < 2u) ? m2 : (w[0] & 31u);
@@ -239,44 +259,59 @@ ITW_HD_NOINLINE bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
 #else
     const Bc6Step* steps = h_bc6_layout[mode];
 #endif
-    int fld[13], nbits[13];
-    for (int i = 0; i < 13; i++) fld[i] = nbits[i] = 0;
+    unsigned long long ch0 = 0ull, ch1 = 0ull, ch2 = 0ull;
     for (int i = 0; i < kBc6MaxSteps; i++) {
         const int f = steps[i].f, bit = steps[i].b, n = steps[i].n;
         if (n == 0) break;
-        if (n > 0) {
-            fld[f] |= (int)(b.get(n) << bit);
-            if (bit + n > nbits[f]) nbits[f] = bit + n;
-        } else {
-            for (int j = 0; j < -n; j++) fld[f] |= (int)(b.get(1) << (bit - j));
-            if (bit + 1 > nbits[f]) nbits[f] = bit + 1;
+        u32 v;                                               // the field's bits, already at their positions
+        if (n > 0) v = b.get(n) << bit;
+        else {
+            v = 0u;
+            for (int j = 0; j < -n; j++) v |= b.get(1) << (bit - j);
         }
+        if (f == 0) continue;                                // mode prefix
+        const int e = (f - 1) / 3, c = (f - 1) % 3;
+        const unsigned long long add = (unsigned long long)v << (16 * e);
+        if (c == 0) ch0 |= add; else if (c == 1) ch1 |= add; else ch2 |= add;
     }
     const int regions = (mode < 10) ? 2 : 1;
     const int epb = bc6_mode_epb(mode);
-    const bool delta = !(mode == 9 || mode == 10);
-    int e[4][3];
-    for (int i = 0; i < 4; i++)
-        for (int c = 0; c < 3; c++) {
-            int v = fld[1 + 3 * i + c];
-            if (delta && i > 0) {
-                const int nb = nbits[1 + 3 * i + c];
-                if (nb > 0 && (v & (1 << (nb - 1)))) v -= 1 << nb;
-                v = (fld[1 + c] + v) & ((1 << epb) - 1);
+    const u32 dbits = bc6_mode_delta_bits(mode);
+    const u32 mask = (1u << epb) - 1u;
+    u32 lo[2][3], hi[2][3];                                  // decoded endpoints A, B per subset and channel
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const unsigned long long chv = (c == 0) ? ch0 : ((c == 1) ? ch1 : ch2);
+        const u32 base = (u32)chv & 0xFFFFu;
+        const int nb = (int)((dbits >> (4 * c)) & 15u);
+        u32 ep[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            u32 v = (u32)(chv >> (16 * i)) & 0xFFFFu;
+            if (i > 0 && nb > 0) {
+                if (v & (1u << (nb - 1))) v -= 1u << nb;     // sign-extend the delta (wraps, masked below)
+                v = (base + v) & mask;
             }
-            e[i][c] = bc6_dequant(v, epb);
+            ep[i] = (u32)bc6_dequant((int)v, epb);
         }
+        lo[0][c] = ep[0]; hi[0][c] = ep[1]; lo[1][c] = ep[2]; hi[1][c] = ep[3];
+    }
     const int shape = (regions == 2) ? (int)b.get(5) : 0;
     const u32 pattern = (regions == 2) ? shape_pattern(shape) : 0u;
     const int anchor1 = (regions == 2) ? shape_anchor(shape, 1) : -1;
     const int ib = (regions == 2) ? 3 : 4;
+#pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int s = (int)((pattern >> (2 * k)) & 3u);
+        const bool second = ((pattern >> (2 * k)) & 3u) != 0u;
         const bool anchor = (k == 0) || (k == anchor1);
         const int q = (int)b.get(anchor ? ib - 1 : ib);
         const int wt = bc7_weight(ib, q);
         u32 h[3];
-        for (int c = 0; c < 3; c++) h[c] = (u32)(((((64 - wt) * e[2 * s][c] + wt * e[2 * s + 1][c] + 32) >> 6) * 31) >> 6);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int a = (int)(second ? lo[1][c] : lo[0][c]), bb = (int)(second ? hi[1][c] : hi[0][c]);
+            h[c] = (u32)(((((64 - wt) * a + wt * bb + 32) >> 6) * 31) >> 6);
+        }
         px[k][0] = h[0] | (h[1] << 16);
         px[k][1] = h[2] | 0x3C000000u;
     }

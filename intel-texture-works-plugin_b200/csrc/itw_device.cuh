@@ -235,9 +235,8 @@ __device__ __forceinline__ void tma_load_row(void* smem_dst, const void* gmem_sr
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one whole 32-byte sector per thread and instruction.
-// Two 128-bit stores to the halves of a sector reach L2 as two partial writes; when the surface is larger than L2
-// they are written back separately (2.75x DRAM write amplification measured on the RGBA16F decode).
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one whole 32-byte sector per thread and instruction,
+// half the memory instructions of the 128-bit form for 8-byte texels.
 __device__ __forceinline__ void st_global_256(void* p, const u32 (&v)[8])     // p: 32-byte aligned
 {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
