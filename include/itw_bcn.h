@@ -137,9 +137,10 @@ const char* itw_get_last_error(void);
 /* Number of kernel launches issued by this library since load (all threads); bench evidence. */
 uint64_t itw_kernel_launch_count(void);
 
-/* Device time in milliseconds of the most recent encode issued by this thread, measured with CUDA
- * events on the launching stream around the kernel(s) only (no copies).  Valid after the call
- * has completed (the CompressBlocks* entry points are synchronous for host buffers). */
+/* Device time in milliseconds of the most recent call issued by this thread (encode, decode, convert),
+ * measured with CUDA events on the launching stream around the kernel(s) only (no copies).  For host
+ * surfaces BC7 / BC6H run as four pipelined row bands: the span then covers the four kernels including
+ * the short waits for the later bands' input copies.  Valid after the call has completed. */
 float itw_last_kernel_ms(void);
 
 /* ---------------------------------------------------------------------------------------------
