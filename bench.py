@@ -326,7 +326,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": round(e2e_value, 3), "unit": "Mtexels/s", "h2d_bytes_per_step": in_bytes * world,
                     "d2h_bytes_per_step": out_bytes * world, "steps": e2e_steps},
-            "gpu_launches": int(launches) * world,    # every rank launches the same number (one per step) "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_info,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_info,
             "wall_ms_per_step": round(wall / args.steps * 1e3, 4)}
     print(json.dumps(line))
     if world > 1:
