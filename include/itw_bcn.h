@@ -253,6 +253,15 @@ int itw_convert_pixels(int format, const itw_pixel_source* src, uint32_t flags, 
 int itw_encode_pixels(int format, const itw_pixel_source* src, uint32_t flags, const void* settings,
                       uint8_t* dst_blocks);
 
+/* The plug-in's whole save path (IntelPlugin.cpp:2062-2171) in one call: `sources` = array_size pixel
+ * sources (level 0 of a 2-D texture, or the faces of a cube map) of desc->width x desc->height texels.
+ * CopyDataForEncoding + FlipXYChannelNormalMap -> mip chain (as itw_dds_encode_texture) ->
+ * NormalizeNormalMapChain on EVERY level when ITW_FRONT_NORMALIZE is set (the plug-in normalises after
+ * the chain exists, :2149-2152) -> pad -> encode -> DDS blob in `file` (host).  Returns the file size, 0 on
+ * error. */
+size_t itw_dds_encode_pixels(const itw_dds_desc* desc, const itw_pixel_source* sources, uint32_t flags,
+                             const void* settings, uint8_t* file, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

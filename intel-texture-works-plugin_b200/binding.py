@@ -46,7 +46,7 @@ EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "Comp
             "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
             "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file",
             "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture", "itw_decode", "itw_convert_pixels", "itw_encode_pixels",
-            "itw_generate_mips_device_f16"]
+            "itw_generate_mips_device_f16", "itw_dds_encode_pixels"]
            + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
 
 
@@ -227,6 +227,24 @@ class ItwBcn(EncoderApi):
         if got != n:
             self.check()
             raise RuntimeError("itw_dds_encode_texture failed")
+        return out
+
+    def dds_encode_pixels(self, desc, pixel_arrays, flags=0, settings=None):
+        """itw_dds_encode_pixels: `pixel_arrays` = host numpy H x W x planes arrays (one per array item); the plug-in's whole save path."""
+        n = self.lib.itw_dds_file_bytes(ctypes.byref(desc))
+        if not n:
+            raise ValueError("unsupported DDS description")
+        keep = [np.ascontiguousarray(a) for a in pixel_arrays]
+        srcs = (PixelSource * len(keep))(*[PixelSource(a.ctypes.data, a.shape[1], a.shape[0], a.shape[2], a.itemsize * 8, 0) for a in keep])
+        out = np.zeros(n, np.uint8)
+        f = self.lib.itw_dds_encode_pixels
+        f.restype = ctypes.c_size_t
+        f.argtypes = [ctypes.POINTER(DdsDesc), ctypes.POINTER(PixelSource), ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        sp = ctypes.cast(ctypes.byref(settings), ctypes.c_void_p) if settings is not None else None
+        got = f(ctypes.byref(desc), srcs, flags, sp, out.ctypes.data, n)
+        if got != n:
+            self.check()
+            raise RuntimeError("itw_dds_encode_pixels failed")
         return out
 
     def dds_encode_file(self, desc, images, settings=None):

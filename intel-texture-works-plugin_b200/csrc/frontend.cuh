@@ -83,6 +83,30 @@ ITW_HD u32 front_load_raw(const uint8_t* p, int depth)
     return *reinterpret_cast<const u32*>(p);
 }
 
+// NormalizeNormalMapChain on one texel; IP:1565-1584 (bytes around 128) and :1586-1607 (halves, unit length)
+ITW_HD void front_normalize_ldr(u32& r, u32& g, u32& b)
+{
+    const float fr = (float)((int)r - 128), fg = (float)((int)g - 128), fb = (float)((int)b - 128);
+    float m = sqrtf(fr * fr + fg * fg + fb * fb);
+    if (m > 0.0f) {
+        m = 127.0f / m;
+        r = (u32)(int)(fr * m + 128.0f) & 255u;
+        g = (u32)(int)(fg * m + 128.0f) & 255u;
+        b = (u32)(int)(fb * m + 128.0f) & 255u;
+    } else { r = 128u; g = 128u; b = 255u; }
+}
+ITW_HD void front_normalize_hdr(u32& r, u32& g, u32& b)
+{
+    const float fr = front_float_from_half(r), fg = front_float_from_half(g), fb = front_float_from_half(b);
+    float m = sqrtf(fr * fr + fg * fg + fb * fb);
+    if (m > 0.0f) {
+        m = 1.0f / m;
+        r = front_half_from_float(fr * m);
+        g = front_half_from_float(fg * m);
+        b = front_half_from_float(fb * m);
+    } else { r = 0u; g = 0u; b = 0x3C00u; }
+}
+
 // raw[c] = element of plane c (valid for c < planes) -> out[0] (RGBA8) or out[0..1] (RGBA16F: r | g << 16, b | a << 16)
 ITW_HD void front_compose(u32 (&out)[2], const FrontParams& P, const u32 (&raw)[4])
 {
@@ -98,16 +122,7 @@ ITW_HD void front_compose(u32 (&out)[2], const FrontParams& P, const u32 (&raw)[
             if (P.flags & kFrontFlipX) r = front_half_from_float(1.0f - fr);
             if (P.flags & kFrontFlipY) g = front_half_from_float(1.0f - fg);
         }
-        if (P.flags & kFrontNormalize) {                                                          // IP:1586-1607
-            const float fr = front_float_from_half(r), fg = front_float_from_half(g), fb = front_float_from_half(b);
-            float m = sqrtf(fr * fr + fg * fg + fb * fb);
-            if (m > 0.0f) {
-                m = 1.0f / m;
-                r = front_half_from_float(fr * m);
-                g = front_half_from_float(fg * m);
-                b = front_half_from_float(fb * m);
-            } else { r = 0u; g = 0u; b = 0x3C00u; }
-        }
+        if (P.flags & kFrontNormalize) front_normalize_hdr(r, g, b);
         out[0] = r | (g << 16);
         out[1] = b | (a << 16);
         return;
@@ -121,16 +136,7 @@ ITW_HD void front_compose(u32 (&out)[2], const FrontParams& P, const u32 (&raw)[
     const u32 a = alpha ? front_ldr_value(raw[3], P.depth, gamma) : 255u;
     if (P.flags & kFrontFlipX) r = 255u - r;                                                       // IP:1519-1527
     if (P.flags & kFrontFlipY) g = 255u - g;
-    if (P.flags & kFrontNormalize) {                                                               // IP:1565-1584
-        const float fr = (float)((int)r - 128), fg = (float)((int)g - 128), fb = (float)((int)b - 128);
-        float m = sqrtf(fr * fr + fg * fg + fb * fb);
-        if (m > 0.0f) {
-            m = 127.0f / m;
-            r = (u32)(int)(fr * m + 128.0f) & 255u;
-            g = (u32)(int)(fg * m + 128.0f) & 255u;
-            b = (u32)(int)(fb * m + 128.0f) & 255u;
-        } else { r = 128u; g = 128u; b = 255u; }
-    }
+    if (P.flags & kFrontNormalize) front_normalize_ldr(r, g, b);
     out[0] = r | (g << 8) | (b << 16) | (a << 24);
     out[1] = 0u;
 }
@@ -158,6 +164,27 @@ __global__ void __launch_bounds__(256) front_kernel(FrontParams P, uint8_t* __re
     uint8_t* row = dst + (long long)y * dst_stride;
     if (P.family == 2) *reinterpret_cast<uint2*>(row + (long long)x * 8) = make_uint2(out[0], out[1]);
     else *reinterpret_cast<u32*>(row + (long long)x * 4) = out[0];
+}
+// NormalizeNormalMapChain over one stored (padded) level, in place: the plug-in normalises every level AFTER the mip
+// chain exists (IP:2149-2152); per-texel, so it commutes with the edge replication of the padding.
+__global__ void __launch_bounds__(256) normalize_kernel(uint8_t* __restrict__ ptr, int w, int h, long long stride, int hdr)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    if (hdr) {
+        u32* p = reinterpret_cast<u32*>(ptr + (long long)y * stride + (long long)x * 8);
+        u32 r = p[0] & 0xFFFFu, g = p[0] >> 16, b = p[1] & 0xFFFFu;
+        const u32 a = p[1] >> 16;
+        front_normalize_hdr(r, g, b);
+        p[0] = r | (g << 16);
+        p[1] = b | (a << 16);
+    } else {
+        u32* p = reinterpret_cast<u32*>(ptr + (long long)y * stride + (long long)x * 4);
+        const u32 v = *p;
+        u32 r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
+        front_normalize_ldr(r, g, b);
+        *p = r | (g << 8) | (b << 16) | (v & 0xFF000000u);
+    }
 }
 // Fast path: one thread per TWO quads of four destination texels -> 128-bit stores; the 4 * planes * depth/8 source
 // bytes of a quad are contiguous and 4-byte aligned, and are fetched as 32-bit words into registers (all indices are

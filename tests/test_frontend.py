@@ -170,3 +170,45 @@ def test_gpu_front_end_device_pointers_and_errors():
         p.convert_pixels("BC7", source(8, 3, 16, 16, seed=1), 1)
     with pytest.raises(RuntimeError):                       # destination of the wrong size
         p.convert_pixels_raw("BC7", src, 0, d_dst.data_ptr(), 120, 64, 128 * 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt,dxgi,prof,depth,planes,flags,w,h,items,cube", [
+    ("BC5", 83, None, 8, 3, 4 | 8 | 16, 64, 32, 1, 0),                 # normal map: flip X/Y at the top, normalise every level
+    ("BC3", 77, None, 16, 4, 1, 50, 27, 1, 0),                         # odd size, alpha
+    ("BC7", 98, "veryfast", 8, 3, 0, 32, 32, 6, 1),                    # cube map
+    ("BC6H", 95, "bc6h_veryfast", 32, 3, 16, 32, 16, 1, 0),            # HDR normal map, wide power of two (stale-tap levels)
+    ("BC6H", 95, "bc6h_veryfast", 16, 4, 1, 20, 12, 1, 0)])            # HDR, linear-filter chain
+def test_gpu_whole_save_path_from_planes(fmt, dxgi, prof, depth, planes, flags, w, h, items, cube):
+    """itw_dds_encode_pixels == oracle convert (+flip) -> mip chain -> oracle normalise of every level -> pad -> encode -> DDS offsets."""
+    import ctypes
+    import test_mips as LM
+    import test_mips_f16 as HM
+    o, p = T.oracle(), T.product()
+    hdr = fmt == "BC6H"
+    srcs = []
+    for i in range(items):
+        px = source(depth, planes, w, h, seed=70 + i)
+        if depth == 32:
+            px = np.clip(np.nan_to_num(px, nan=0.5, posinf=1.0, neginf=0.0), 0, 4).astype(np.float32)
+        srcs.append(px)
+    levels = LM.full_levels(w, h)
+    d = B.DdsDesc(w, h, levels, items, dxgi, cube)
+    s = p.profile(prof) if prof else None
+    blob = p.dds_encode_pixels(d, srcs, flags, s)
+    norm = flags & B.FRONT_NORMALIZE
+    for item in range(items):
+        top = o.convert_pixels(fmt, srcs[item], flags & ~B.FRONT_NORMALIZE, pad=False)
+        chain = HM.oracle_chain(top, levels) if hdr else [lv[:max(1, h >> i), :max(1, w >> i)] for i, lv in enumerate(LM.reference_chain(top, levels))]
+        for mip in range(levels):
+            lv = np.ascontiguousarray(chain[mip])
+            if norm:                                               # the oracle's normalise pass through an identity conversion
+                if hdr:
+                    rgb = o.convert_pixels(fmt, lv.view(np.float16).astype(np.float32), B.FRONT_NORMALIZE, pad=False)
+                    lv = np.concatenate([rgb[..., :3], lv[..., 3:]], axis=2)
+                else:
+                    lv = o.convert_pixels(fmt, lv, B.FRONT_NORMALIZE | B.FRONT_HAS_ALPHA, pad=False)
+            padded = HM.pad4(lv)
+            want = o.encode(fmt, np.ascontiguousarray(padded), o.profile(prof) if prof else None)
+            off = p.lib.itw_dds_image_offset(ctypes.byref(d), item, mip)
+            assert np.array_equal(blob[off:off + want.size], want), (item, mip)
