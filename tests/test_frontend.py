@@ -212,3 +212,21 @@ def test_gpu_whole_save_path_from_planes(fmt, dxgi, prof, depth, planes, flags, 
             want = o.encode(fmt, np.ascontiguousarray(padded), o.profile(prof) if prof else None)
             off = p.lib.itw_dds_image_offset(ctypes.byref(d), item, mip)
             assert np.array_equal(blob[off:off + want.size], want), (item, mip)
+
+
+def test_oracle_matches_committed_reference_digests():
+    """The digests were produced by the reference's own function bodies (tests/golden/make_golden_frontend.py); they keep the
+    oracle pinned where neither /root/reference nor a prebuilt oracle/_ref exists."""
+    import hashlib
+    import json
+    import os
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frontend_digests.json")))
+    o = T.oracle()
+    n = 0
+    for fmt, depth, planes in CASES:
+        px = source(depth, planes, 13, 7, seed=depth + planes)
+        for flags in flag_sets(fmt, depth, planes):
+            got = hashlib.sha256(o.convert_pixels(fmt, px, flags).tobytes()).hexdigest()
+            assert got == golden["convert"][f"{fmt}:{depth}:{planes}:{flags}"], (fmt, depth, planes, flags)
+            n += 1
+    assert n == len(golden["convert"])

@@ -140,3 +140,15 @@ def test_gpu_bc6h_texture_save_path():
                 off = lib.lib.itw_dds_image_offset(ctypes.byref(d), item, mip)
                 want = lib.encode("BC6H", np.ascontiguousarray(pad4(chain[mip])), s)
                 assert np.array_equal(blob[off:off + want.size], want), (item, mip)
+
+
+def test_oracle_matches_committed_reference_digests():
+    import hashlib
+    import json
+    import os
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frontend_digests.json")))["mip_chain_f16"]
+    assert len(golden) == len(SIZES)
+    for h, w in SIZES:
+        img = random_f16(h, w, seed=h * 131 + w)
+        chain = oracle_chain(img, full_levels(w, h))
+        assert hashlib.sha256(b"".join(l.tobytes() for l in chain)).hexdigest() == golden[f"{h}x{w}"], (h, w)
