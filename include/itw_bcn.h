@@ -134,6 +134,10 @@ int itw_set_device(int device);
  * the reference's void signature, so this is the only error channel for them. */
 const char* itw_get_last_error(void);
 
+/* Free the calling thread's device buffers, streams and events now (they are otherwise kept for the next
+ * call and freed when the thread exits); the next call re-creates what it needs. */
+void itw_release(void);
+
 /* Number of kernel launches issued by this library since load (all threads); bench evidence. */
 uint64_t itw_kernel_launch_count(void);
 

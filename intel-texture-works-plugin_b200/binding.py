@@ -46,7 +46,7 @@ EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "Comp
             "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
             "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file",
             "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture", "itw_decode", "itw_convert_pixels", "itw_encode_pixels",
-            "itw_generate_mips_device_f16", "itw_dds_encode_pixels"]
+            "itw_generate_mips_device_f16", "itw_dds_encode_pixels", "itw_release"]
            + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
 
 

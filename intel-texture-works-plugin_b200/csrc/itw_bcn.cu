@@ -661,6 +661,14 @@ int itw_set_device(int device)
 
 const char* itw_get_last_error(void) { return tls.err.c_str(); }
 
+void itw_release(void)
+{
+    if (tls.stream) cudaStreamSynchronize(tls.stream);
+    tls.release();
+    tls.device = -1;
+    tls.timed = false;
+}
+
 uint64_t itw_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 float itw_last_kernel_ms(void)

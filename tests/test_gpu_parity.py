@@ -213,3 +213,17 @@ def test_banded_host_path_equals_device_path_and_oracle():
         lib.encode("BC7", np.zeros((512, 64, 4), np.uint8), bad)
     assert np.array_equal(lib.encode("BC7", _rand_img("BC7", 256, 64, seed=1), lib.profile("veryfast")),
                           lib.encode("BC7", _rand_img("BC7", 256, 64, seed=1), lib.profile("veryfast")))
+
+
+def test_release_frees_and_next_call_recreates():
+    """itw_release drops the thread's device buffers / streams; later calls (all three host paths) still give the same bytes."""
+    lib = T.product()
+    img = _rand_img("BC7", 512, 64, seed=9)
+    s = lib.profile("veryfast")
+    want = lib.encode("BC7", img, s)                      # banded path
+    small = lib.encode("BC1", img[:64])                   # single-launch path
+    lib.lib.itw_release.restype = None
+    lib.lib.itw_release()
+    lib.lib.itw_release()                                 # idempotent
+    assert np.array_equal(lib.encode("BC7", img, s), want)
+    assert np.array_equal(lib.encode("BC1", img[:64]), small)
