@@ -15,8 +15,11 @@
 // Outside the normal-half range other DirectXMath versions differ: unpinned there.
 #pragma once
 #include "itw_device.cuh"
+#include "gamma_table.cuh"
 
 namespace itw {
+
+ITW_TABLE_DECL(uint32_t, gamma_threshold, 255)
 
 struct FrontParams {
     const uint8_t* data;
@@ -59,15 +62,34 @@ ITW_HD u32 front_byte(double v)
     if (!(v == v)) return 0u;
     return (u32)(int)(v * 255.0) & 255u;
 }
+// ConvertTo8Bit(double, gammaCorrect): (unsigned char)(pow((double)v, 1/2.2) * 255) with FloatToByte's clamps; IPh:41-48, :67-76.
+// On [0, 1] this is a monotone step function of the float v, so it is evaluated WITHOUT pow as the number of thresholds
+// T[k] <= v in the generated table (tools/gen_gamma_table.py: bisection on the oracle's own conversion); non-negative floats
+// order like their bit patterns.  Outside [0, 1]: v > 1 -> 255; pow of a negative number is NaN -> 0, except
+// pow(-inf, y) = +inf -> 255; pow(-0) = +0 -> 0; NaN -> 0.  The double-precision pow this replaces ran at 0.11 of the HBM
+// roofline (FP64 rate), the table search is bandwidth-bound like the other conversions.
+ITW_HD u32 front_gamma_byte(float v)
+{
+    if (!(v == v)) return 0u;
+    if (v > 1.0f) return 255u;
+    if (v < 0.0f) return (float_bits(v) == 0xFF800000u) ? 255u : 0u;
+    const u32 b = float_bits(v) & 0x7FFFFFFFu;                  // -0 counts as +0
+    u32 pos = 0u;
+#pragma unroll
+    for (u32 step = 128u; step >= 1u; step >>= 1) {
+        const u32 t = pos + step;
+        if (t <= 255u && ITW_TABLE(gamma_threshold)[t - 1u] <= b) pos = t;
+    }
+    return pos;
+}
 // one source element (raw bits: the 8/16-bit integer, or the float's bit pattern) -> byte; IPh:56-76.
 // 16-bit: FloatToByte(v / 32768.0) = floor(v * 255 / 32768) exactly
 ITW_HD u32 front_ldr_value(u32 raw, int depth, bool gamma)
 {
     if (depth == 8) return raw;
     if (depth == 16) return (raw > 32768u) ? 255u : ((raw * 255u) >> 15);
-    double v = (double)bits_float(raw);
-    if (gamma) v = pow(v, 1 / 2.2);
-    return front_byte(v);
+    if (gamma) return front_gamma_byte(bits_float(raw));
+    return front_byte((double)bits_float(raw));
 }
 // one source element -> half bits; IPh:79-96
 ITW_HD u32 front_hdr_value(u32 raw, int depth)

@@ -250,3 +250,7 @@ extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int le
     }
     return 0;
 }
+
+// ConvertTo8Bit(double, gammaCorrect = true) of one float, exported for tools/gen_gamma_table.py (which derives the product's
+// threshold table from THIS function, i.e. from the C library's pow) and for tests.
+extern "C" int oracle_gamma_byte(float v) { return to8(v, true); }

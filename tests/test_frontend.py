@@ -6,6 +6,7 @@ depth x plane count x format family x flag combination; (2) the kernel's per-tex
 tests/emu) against the oracle; (3) the restated half conversion against IEEE round-to-nearest-even where every
 DirectXMath version agrees.  GPU: itw_convert_pixels / itw_encode_pixels through the C-ABI against the oracle."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -230,3 +231,23 @@ def test_oracle_matches_committed_reference_digests():
             assert got == golden["convert"][f"{fmt}:{depth}:{planes}:{flags}"], (fmt, depth, planes, flags)
             n += 1
     assert n == len(golden["convert"])
+
+
+def test_gamma_table_equals_pow_around_every_threshold_and_on_a_dense_sample():
+    """The kernel evaluates the 32-bit gamma conversion from a threshold table (csrc/gamma_table.cuh) instead of pow: the
+    emulated routine must equal the oracle (C library pow) on both float neighbours of all 255 thresholds, on a dense
+    sample of [0, 1.05] and on the special values."""
+    import re
+    o, e = T.oracle(), T.emu()
+    text = open(os.path.join(T.ROOT, "intel-texture-works-plugin_b200", "csrc", "gamma_table.cuh")).read()
+    bits = np.array([int(x, 16) for x in re.findall(r"0x([0-9A-F]{8})u", text)], np.uint32)
+    assert bits.size == 255 and np.all(np.diff(bits.astype(np.int64)) > 0)
+    near = np.concatenate([bits - 2, bits - 1, bits, bits + 1, bits + 2]).view(np.float32)
+    rng = np.random.default_rng(5)
+    dense = (rng.random(1 << 20, dtype=np.float32) * np.float32(1.05)).astype(np.float32)
+    tiny = (rng.random(4096, dtype=np.float32) * np.float32(1e-4)).astype(np.float32)
+    vals = np.concatenate([near, dense, tiny, SPECIALS, -SPECIALS])
+    vals = np.resize(vals, (1027, 1024, 1)).astype(np.float32)
+    got = e.convert_pixels("BC7", vals, B.FRONT_GAMMA, pad=False)
+    want = o.convert_pixels("BC7", vals, B.FRONT_GAMMA, pad=False)
+    assert np.array_equal(got, want)
