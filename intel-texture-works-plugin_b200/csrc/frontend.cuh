@@ -67,20 +67,25 @@ ITW_HD u32 front_byte(double v)
 // T[k] <= v in the generated table (tools/gen_gamma_table.py: bisection on the oracle's own conversion); non-negative floats
 // order like their bit patterns.  Outside [0, 1]: v > 1 -> 255; pow of a negative number is NaN -> 0, except
 // pow(-inf, y) = +inf -> 255; pow(-0) = +0 -> 0; NaN -> 0.  The double-precision pow this replaces ran at 0.11 of the HBM
-// roofline (FP64 rate), the table search is bandwidth-bound like the other conversions.
+// roofline (FP64 rate).
 ITW_HD u32 front_gamma_byte(float v)
 {
     if (!(v == v)) return 0u;
     if (v > 1.0f) return 255u;
     if (v < 0.0f) return (float_bits(v) == 0xFF800000u) ? 255u : 0u;
     const u32 b = float_bits(v) & 0x7FFFFFFFu;                  // -0 counts as +0
-    u32 pos = 0u;
-#pragma unroll
-    for (u32 step = 128u; step >= 1u; step >>= 1) {
-        const u32 t = pos + step;
-        if (t <= 255u && ITW_TABLE(gamma_threshold)[t - 1u] <= b) pos = t;
-    }
-    return pos;
+    // start from a cheap single-precision estimate (any value would do: the two loops below make the count exact) and
+    // walk to the entry whose thresholds bracket v -- two table reads in the common case instead of a binary search's eight
+#if defined(__CUDA_ARCH__)
+    const float est = __powf(v, 0.45454545f) * 255.0f;
+#else
+    const float est = powf(v, 0.45454545f) * 255.0f;
+#endif
+    int k = (int)est;
+    k = (k < 0) ? 0 : ((k > 255) ? 255 : k);
+    while (k > 0 && ITW_TABLE(gamma_threshold)[k - 1] > b) k--;
+    while (k < 255 && ITW_TABLE(gamma_threshold)[k] <= b) k++;
+    return (u32)k;
 }
 // one source element (raw bits: the 8/16-bit integer, or the float's bit pattern) -> byte; IPh:56-76.
 // 16-bit: FloatToByte(v / 32768.0) = floor(v * 255 / 32768) exactly
