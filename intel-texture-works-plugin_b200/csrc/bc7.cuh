@@ -18,14 +18,19 @@
 // uses packed-byte integer instructions instead -- same values, ~6x fewer instructions:
 //   * raw moments of a subset (K:763-803): IDP.4A dot products over channel-planar packed bytes;
 //   * index search (K:1133-1193): the projection numerator / denominator are integer dot
-//     products (then ONE IEEE float division, as in the reference), the two candidate palette
+//     products (then ONE float division, evaluated as the FMA-corrected quotient that equals the
+//     IEEE one -- tests/test_exact_division.py, tests/test_gpu_division.py), the two candidate palette
 //     entries are integer interpolations (the reference truncates them through int, K:1172-1173)
 //     and their squared errors are VABSDIFF4 + IDP.4A;
 //   * least-squares sums (K:1198-1230): IDP.4A over index bytes.
 // Everything that rounds (covariance, power iteration, endpoint solve, quantisation) follows the
 // reference's float expression order exactly (DESIGN.md "Canonical float model").
 //
-// The phases are per-lane functions separated by warp barriers; tests/emu drives the same
+// Structure for speed: the non-inlined routines exchange their results BY VALUE (small structs stay
+// in registers across calls; arrays passed by pointer would live in local memory), the inner routines are branch-free
+// (rotation views via PRMT selectors, the fourth component via zero operands), and chain tasks are scheduled role-major.
+//
+// The phases are per-lane functions separated by barriers; tests/emu drives the same
 // functions lane by lane on the CPU (test-only).
 #pragma once
 #include "bc67_core.cuh"
