@@ -218,8 +218,8 @@ size_t itw_dds_encode_texture(const itw_dds_desc* desc, const rgba_surface* tops
  * `blocks` holds (width/4)*(height/4) blocks in raster order; dst->ptr is WRITTEN: RGBA8 texels
  * (4 B) for BC1/BC3/BC4/BC5/BC7 (BC4: r,0,0,255; BC5: r,g,0,255), RGBA16F texels (8 B, half bit
  * patterns, alpha = 1.0) for BC6H_UF16.  width/height multiples of 4; either side may be host or
- * device memory; synchronous.  BC7 and BC6H are exact by the format definition; the BC1-BC5 palettes
- * use the integer formulas stated in csrc/decode.cuh.  Returns 0 on success.
+ * device memory; synchronous.  BC7 and BC6H are exact by the format definition; BC1-BC5 equal
+ * DirectXTex's float decoders rounded to nearest (csrc/decode.cuh).  Returns 0 on success.
  * ------------------------------------------------------------------------------------------- */
 int itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst);
 

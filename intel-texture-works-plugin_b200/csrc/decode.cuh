@@ -6,9 +6,11 @@
 //
 // Contract.  BC7 and BC6H are integer-exact by the format definition (interpolation ((64-w)a + wb + 32) >> 6,
 // BC6H un-quantisation and the final (x*31)>>6 to half bits; DirectXTex/BC6HBC7.cpp:1077-1236, :1937-2144), so the
-// result is THE decode.  BC1/BC3/BC4/BC5 palettes are defined here with the usual integer formulas (bit-replicated
-// 565, (2a+b+1)/3, ((7-i)a + ib + 3)/7 ...); DirectXTex computes them in float (BC.cpp:322-370, BC4BC5.cpp:42-95)
-// and may differ by one LSB -- parity with the plug-in's preview is unpinned for those four formats.
+// result is THE decode.  DirectXTex decodes BC1-BC5 to FLOAT texels (BC.cpp:322-370, :897-936, BC4BC5.cpp:42-95) and the
+// preview stores them as UNORM8 through DirectXMath.  Here: BC1 / BC3 colours evaluate DirectXTex's float expressions and
+// round to nearest; the 8-value alpha / BC4 / BC5 ramps use integer formulas that equal round-to-nearest of DirectXTex's
+// float ramps for EVERY endpoint pair and index (tests/test_bc45_vs_directxtex.py, tests/test_decode.py, both against the
+// reference's own decoder bodies).  What stays outside the tree is only the rounding mode of that final store.
 // The numpy restatement of exactly these rules is tests/bcn_decode.py.
 #pragma once
 #include "bc6h.cuh"
@@ -36,29 +38,31 @@ struct BitReader {
 };
 
 // ---- BC1 colour block -> packed RGBA (alpha 255, or 0 for the transparent code of 3-colour mode) ----
-ITW_HD u32 expand565(u32 c)
-{
-    const u32 r = (c >> 11) & 31u, g = (c >> 5) & 63u, b = c & 31u;
-    return ((r << 3) | (r >> 2)) | (((g << 2) | (g >> 4)) << 8) | (((b << 3) | (b >> 2)) << 16);
-}
-ITW_HD u32 mix_rgb(u32 a, u32 b, u32 wa, u32 wb, u32 add, u32 div)     // per channel (wa*a + wb*b + add) / div
-{
-    u32 out = 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const u32 x = (a >> (8 * c)) & 255u, y = (b >> (8 * c)) & 255u;
-        out |= ((wa * x + wb * y + add) / div) << (8 * c);
-    }
-    return out;
-}
+// DirectXTex's DecodeBC1 (BC.cpp:322-370) in its own float operations -- endpoint = n * (1/31) or n * (1/63), interpolants
+// (c1 - c0) * t + c0 with t = 1/3, 2/3 or 1/2 (XMVectorLerp: a multiply, then an add) -- followed by the UNORM8 store as
+// x * 255 + 0.5 truncated.  The float part is checked against the reference's own body (tests/test_decode.py); the store is
+// DirectXMath (outside the tree), round-to-nearest is the assumption.  Note that this is NOT bit replication of the 5/6-bit
+// endpoints: 7/31 decodes to 58, not 57.
+ITW_HD u32 unorm8_of(float x) { return (u32)(int)(x * 255.0f + 0.5f); }
 ITW_HD void decode_bc1_colour(u32 (&px)[16], u32 w0, u32 w1, bool force4)
 {
     const u32 c0 = w0 & 0xFFFFu, c1 = w0 >> 16;
-    const u32 a = expand565(c0), b = expand565(c1);
     const bool four = (c0 > c1) || force4;
-    const u32 p0 = a | 0xFF000000u, p1 = b | 0xFF000000u;
-    const u32 p2 = (four ? mix_rgb(a, b, 2, 1, 1, 3) : mix_rgb(a, b, 1, 1, 0, 2)) | 0xFF000000u;
-    const u32 p3 = four ? (mix_rgb(a, b, 1, 2, 1, 3) | 0xFF000000u) : 0u;
+    u32 p0 = 0xFF000000u, p1 = 0xFF000000u, p2 = 0xFF000000u, p3 = four ? 0xFF000000u : 0u;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {                               // c = 0: red (bits 11..15), 1: green (5..10), 2: blue (0..4)
+        const int shift = (c == 0) ? 11 : ((c == 1) ? 5 : 0);
+        const u32 mask = (c == 1) ? 63u : 31u;
+        const float scale = (c == 1) ? (1.0f / 63.0f) : (1.0f / 31.0f);
+        const float f0 = (float)((c0 >> shift) & mask) * scale, f1 = (float)((c1 >> shift) & mask) * scale;
+        const float len = f1 - f0;
+        const float f2 = four ? (len * (1.0f / 3.0f) + f0) : (len * 0.5f + f0);
+        const float f3 = len * (2.0f / 3.0f) + f0;
+        p0 |= unorm8_of(f0) << (8 * c);
+        p1 |= unorm8_of(f1) << (8 * c);
+        p2 |= unorm8_of(f2) << (8 * c);
+        if (four) p3 |= unorm8_of(f3) << (8 * c);
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const u32 q = (w1 >> (2 * k)) & 3u;

@@ -14,7 +14,25 @@ and, for the RGBA16F mip chain of the BC6H save path (TEX_FILTER_FORCE_NON_WIC, 
   3rdParty/DirectXTex/DirectXTex/Filters.h               AVERAGE4, LinearFilter, _CreateLinearFilter, BILINEAR_INTERPOLATE (:29-112)
 
 (shimmed there: XMVECTOR and its + and * operators as four scalar IEEE operations, and _LoadScanlineLinear /
-_StoreScanlineLinear for R16G16B16A16_FLOAT as the half conversions below -- in the reference they are XMLoadHalf4 / XMStoreHalf4).
+_StoreScanlineLinear for R16G16B16A16_FLOAT as the half conversions below -- in the reference they are XMLoadHalf4 / XMStoreHalf4),
+
+and the BC4 / BC5 encoders the plug-in reaches through DirectX::Compress (IntelPlugin.cpp:272):
+
+  3rdParty/DirectXTex/DirectXTex/BC4BC5.cpp   the whole DirectX namespace body: BC4_UNORM, FindEndPointsBC4U, FindClosestUNORM,
+                                              D3DXEncodeBC4U / BC5U (and the decoders / SNORM variants, unused here)
+  3rdParty/DirectXTex/DirectXTex/BC.h         template OptimizeAlpha (:727-856)
+
+(shimmed there: XMVectorGetX / XMVectorSet / XMStoreFloat4A as plain member access; the texel floats handed to the encoders are
+byte * (1/255), rule F7 -- in the reference they come from XMLoadUByteN4 inside _CompressBC, DirectXMath again),
+
+and the BC1 / BC3 DECODERS of the preview path (DirectX::Decompress, IntelPlugin.cpp:1051-1066):
+
+  3rdParty/DirectXTex/DirectXTex/BC.cpp       DecodeBC1 (:322-370), D3DXDecodeBC1 (:722-726), D3DXDecodeBC3 (:897-936)
+  3rdParty/DirectXTex/DirectXTex/BC.h         struct D3DX_BC1 / D3DX_BC3 (:282-301)
+
+(shimmed there: XMLoadU565, XMVectorSwizzle, XMVectorSelect, XMVectorLerp -- "(V1 - V0) * t + V0", a multiply then an add --,
+XMVectorZero, XMVectorSetW).  The decoders return FLOAT texels; the final store to RGBA8 is DirectXMath's XMStoreUByteN4, whose
+rounding is outside the tree: the tests compare against round-to-nearest of these floats.
 
 Neither file compiles here (Photoshop SDK, Windows, DirectXTex), but these functions only touch a handful of
 fields.  This recipe cuts exactly those function bodies out of the files WHERE THEY LIE under /root/reference
@@ -44,6 +62,9 @@ PLUGIN_H = os.path.join(REF_ROOT, "IntelCompressionPlugin", "IntelPlugin.h")
 PLUGIN_CPP = os.path.join(REF_ROOT, "IntelCompressionPlugin", "IntelPlugin.cpp")
 MIPMAPS_CPP = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "DirectXTexMipmaps.cpp")
 FILTERS_H = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "Filters.h")
+BC45_CPP = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "BC4BC5.cpp")
+BC_H = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "BC.h")
+BC_CPP = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "BC.cpp")
 OUT_DIR = os.path.join(HERE, "_ref")
 OUT_SO = os.path.join(OUT_DIR, "libitw_ref_frontend.so")
 
@@ -263,6 +284,110 @@ extern "C" int ref_mip_chain_f16(const unsigned short* level0, int w, int h, int
 """
 
 
+BC45_SHIM_TOP = r"""
+// ---- DirectXTex BC4 / BC5 encoders: shim -----------------------------------------------------------------
+#define _Out_
+#define _Inout_
+#define _Use_decl_annotations_
+#define UNREFERENCED_PARAMETER(x) ((void)(x))
+#define NUM_PIXELS_PER_BLOCK 16
+#define _isnan(x) ((x) != (x))            // MSVC CRT name, used by the SNORM helpers
+struct XMFLOAT4A { float x, y, z, w; };
+inline float XMVectorGetX(XMVECTOR v) { return v.f[0]; }
+inline XMVECTOR XMVectorSet(float x, float y, float z, float w) { return XMVECTOR{{x, y, z, w}}; }
+inline void XMStoreFloat4A(XMFLOAT4A* d, XMVECTOR v) { d->x = v.f[0]; d->y = v.f[1]; d->z = v.f[2]; d->w = v.f[3]; }
+namespace DirectX {
+"""
+
+BC45_SHIM_BOTTOM = r"""
+// `texels` = 16 floats per channel, already byte * (1/255)
+extern "C" void ref_encode_bc4u(const float* r, uint8_t* out8)
+{
+    XMVECTOR c[16];
+    for (int i = 0; i < 16; i++) c[i] = XMVECTOR{{r[i], 0.0f, 0.0f, 1.0f}};
+    DirectX::D3DXEncodeBC4U(out8, c, 0);
+}
+extern "C" void ref_encode_bc5u(const float* r, const float* g, uint8_t* out16)
+{
+    XMVECTOR c[16];
+    for (int i = 0; i < 16; i++) c[i] = XMVECTOR{{r[i], g[i], 0.0f, 1.0f}};
+    DirectX::D3DXEncodeBC5U(out16, c, 0);
+}
+// decoded channel values as floats (D3DXDecodeBC4U, BC4BC5.cpp:373-386): 16 floats
+extern "C" void ref_decode_bc4u(const uint8_t* in8, float* out16)
+{
+    XMVECTOR c[16];
+    DirectX::D3DXDecodeBC4U(c, in8);
+    for (int i = 0; i < 16; i++) out16[i] = c[i].f[0];
+}
+"""
+
+
+def cut_bc45(cpp, bch):
+    m = re.search(r"^template\s*<bool bRange>\s*void OptimizeAlpha\s*\(", bch, re.M)
+    if not m:
+        raise RuntimeError("OptimizeAlpha not found in BC.h")
+    optimize = cut_function(bch, m.start())
+    a = cpp.index("namespace DirectX")
+    a = cpp.index("{", a) + 1
+    b = cpp.rindex("} // namespace")
+    return optimize + "\n" + cpp[a:b] + "\n}  // namespace DirectX\n"
+
+
+BC13_SHIM_TOP = r"""
+// ---- DirectXTex BC1 / BC3 decoders: shim -----------------------------------------------------------------
+#define _In_
+struct XMU565 { uint16_t v; };
+struct XMVECTORU32 { uint32_t u[4]; };
+static const XMVECTORF32 g_XMIdentityR3 = {0.0f, 0.0f, 0.0f, 1.0f};
+static const XMVECTORU32 g_XMSelect1110 = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u};
+inline XMVECTOR XMLoadU565(const XMU565* p) { return XMVECTOR{{(float)(p->v & 31), (float)((p->v >> 5) & 63), (float)((p->v >> 11) & 31), 0.0f}}; }
+template <int A, int B, int C, int D> inline XMVECTOR XMVectorSwizzle(XMVECTOR v) { return XMVECTOR{{v.f[A], v.f[B], v.f[C], v.f[D]}}; }
+inline XMVECTOR XMVectorSelect(XMVECTOR a, XMVECTOR b, const XMVECTORU32& c)
+{
+    return XMVECTOR{{c.u[0] ? b.f[0] : a.f[0], c.u[1] ? b.f[1] : a.f[1], c.u[2] ? b.f[2] : a.f[2], c.u[3] ? b.f[3] : a.f[3]}};
+}
+inline XMVECTOR XMVectorLerp(XMVECTOR v0, XMVECTOR v1, float t)          // DirectXMath: Length = V1 - V0; Length * t + V0 (mul, add)
+{
+    XMVECTOR r;
+    for (int i = 0; i < 4; i++) { float l = v1.f[i] - v0.f[i]; float m = l * t; r.f[i] = m + v0.f[i]; }
+    return r;
+}
+inline XMVECTOR XMVectorZero() { return XMVECTOR{{0.0f, 0.0f, 0.0f, 0.0f}}; }
+inline XMVECTOR XMVectorSetW(XMVECTOR v, float w) { v.f[3] = w; return v; }
+#pragma pack(push, 1)
+"""
+
+BC13_SHIM_BOTTOM = r"""
+// 16 texels x (r, g, b, a) floats
+extern "C" void ref_decode_bc1(const uint8_t* in8, float* out64)
+{
+    XMVECTOR c[16];
+    D3DXDecodeBC1(c, in8);
+    for (int i = 0; i < 16; i++) for (int k = 0; k < 4; k++) out64[4 * i + k] = c[i].f[k];
+}
+extern "C" void ref_decode_bc3(const uint8_t* in16, float* out64)
+{
+    XMVECTOR c[16];
+    D3DXDecodeBC3(c, in16);
+    for (int i = 0; i < 16; i++) for (int k = 0; k < 4; k++) out64[4 * i + k] = c[i].f[k];
+}
+"""
+
+
+def cut_bc13(cpp, bch):
+    a = bch.index("struct D3DX_BC1")
+    b = bch.index("#pragma pack(pop)", a)
+    structs = bch[a:b] + "#pragma pack(pop)\n"
+    out = [structs]
+    for pat in (r"^inline static void DecodeBC1\s*\(", r"^void D3DXDecodeBC1\s*\(", r"^void D3DXDecodeBC3\s*\("):
+        m = re.search(pat, cpp, re.M)
+        if not m:
+            raise RuntimeError(pat + " not found in BC.cpp")
+        out.append(cut_function(cpp, m.start()))
+    return "\n\n".join(out)
+
+
 def cut_static_function(src, name):
     m = re.search(r"^static\s+HRESULT\s+" + name + r"\s*\(", src, re.M)
     if not m:
@@ -330,7 +455,11 @@ def build(verbose=True):
         filt = open(FILTERS_H, encoding="utf-8", errors="replace").read()
         unit = (SHIM_TOP + cut_inlines(hdr) + SHIM_CLASS + cut_members(cpp) + SHIM_BOTTOM + MIP_SHIM_TOP + cut_filters(filt)
                 + cut_static_function(mips, "_Generate2DMipsBoxFilter") + "\n" + cut_static_function(mips, "_Generate2DMipsLinearFilter")
-                + MIP_SHIM_BOTTOM)
+                + MIP_SHIM_BOTTOM
+                + BC45_SHIM_TOP + cut_bc45(open(BC45_CPP, encoding="utf-8", errors="replace").read(),
+                                           open(BC_H, encoding="utf-8", errors="replace").read()) + BC45_SHIM_BOTTOM
+                + BC13_SHIM_TOP + cut_bc13(open(BC_CPP, encoding="utf-8", errors="replace").read(),
+                                           open(BC_H, encoding="utf-8", errors="replace").read()) + BC13_SHIM_BOTTOM)
         path = os.path.join(tmp, "frontend_ref.cpp")
         open(path, "w").write(unit)
         cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-fno-fast-math", "-mfpmath=sse", "-msse2",

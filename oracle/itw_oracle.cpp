@@ -1312,6 +1312,8 @@ void bc6_encode_block(Bc6Block& blk)                                            
 
 // ==========================================================================================
 // BC4 / BC5 (DirectXTex path; IntelPlugin.cpp:272 -> DirectXTex/BC4BC5.cpp, BC.h:727-856)
+// PINNING: byte-identical to DirectXTex's own encoder bodies (oracle/build_ref_frontend.py -> tests/test_bc45_vs_directxtex.py);
+// the byte -> float texel load (rule F7) is the one assumption.
 // ==========================================================================================
 // OptimizeAlpha<false> (DirectXTex/BC.h:727-856): Newton refinement of the two endpoints of a
 // `steps`-entry ramp over values in [0,1].

@@ -59,26 +59,32 @@ def anchors_of(ns, shape):
 
 
 # ---- BC1 / BC3 / BC4 / BC5 ----
-def _565(c):
-    r, g, b = (c >> 11) & 31, (c >> 5) & 63, c & 31
-    return np.array([(r << 3) | (r >> 2), (g << 2) | (g >> 4), (b << 3) | (b >> 2)], np.int32)
+def _unorm8(x):
+    return int(np.float32(np.float32(x) * np.float32(255.0)) + np.float32(0.5))
 
 
 def decode_bc1_block(blk, force4=False):
+    """DirectXTex DecodeBC1 (BC.cpp:322-370) in float32, stored as x * 255 + 0.5 truncated; NOT 565 bit replication."""
     c0, c1 = int.from_bytes(bytes(blk[0:2]), "little"), int.from_bytes(bytes(blk[2:4]), "little")
     idx = int.from_bytes(bytes(blk[4:8]), "little")
-    a, b = _565(c0), _565(c1)
-    if c0 > c1 or force4:
-        pal = [a, b, (2 * a + b + 1) // 3, (a + 2 * b + 1) // 3]
-        alpha = [255] * 4
-    else:
-        pal = [a, b, (a + b) // 2, np.zeros(3, np.int32)]
-        alpha = [255, 255, 255, 0]
+    four = c0 > c1 or force4
+    pal = np.zeros((4, 4), np.int32)
+    pal[:, 3] = 255
+    if not four:
+        pal[3, 3] = 0
+    for c, (shift, mask, scale) in enumerate(((11, 31, np.float32(1.0) / np.float32(31.0)), (5, 63, np.float32(1.0) / np.float32(63.0)),
+                                              (0, 31, np.float32(1.0) / np.float32(31.0)))):
+        f0 = np.float32((c0 >> shift) & mask) * scale
+        f1 = np.float32((c1 >> shift) & mask) * scale
+        ln = np.float32(f1 - f0)
+        third, two_thirds = np.float32(1.0) / np.float32(3.0), np.float32(2.0) / np.float32(3.0)
+        f2 = np.float32(np.float32(ln * third) + f0) if four else np.float32(np.float32(ln * np.float32(0.5)) + f0)
+        f3 = np.float32(np.float32(ln * two_thirds) + f0)
+        pal[0, c], pal[1, c], pal[2, c] = _unorm8(f0), _unorm8(f1), _unorm8(f2)
+        pal[3, c] = _unorm8(f3) if four else 0
     out = np.zeros((16, 4), np.int32)
     for k in range(16):
-        q = (idx >> (2 * k)) & 3
-        out[k, :3] = pal[q]
-        out[k, 3] = alpha[q]
+        out[k] = pal[(idx >> (2 * k)) & 3]
     return out
 
 

@@ -3,8 +3,9 @@
 reference's own kernel.ispc + ispc_texcomp.cpp compiled scalar by oracle/build_ref.py.
 
 Run here (where /root/reference exists):   python tests/golden/make_golden.py
-BC4/BC5 are not part of the ISPC reference; their digests come from the oracle port and are marked
-as such (parity for them is pinned to the DirectXTex source by reading only)."""
+BC4/BC5 are not part of the ISPC reference: their digests come from DirectXTex's own encoder bodies
+(oracle/_ref/libitw_ref_frontend.so, cut from BC4BC5.cpp / BC.h by oracle/build_ref_frontend.py), fed with
+texel floats byte * (1/255)."""
 import hashlib
 import json
 import os
@@ -18,11 +19,15 @@ def main():
     ref = T.ref()
     assert ref is not None, "needs /root/reference (or a prebuilt oracle/_ref/libitw_ref.so)"
     digests, inputs, source = {}, {}, {}
+    import test_bc45_vs_directxtex as DX
+    dxlib = DX.ref_lib()
     for fmt, prof in T.ALL_CASES:
-        api, tag = (T.oracle(), "oracle-port") if fmt in ("BC4", "BC5") else (ref, "reference-source")
         for name, img in T.corpus_for(fmt).items():
-            digests[f"{fmt}:{prof}:{name}"] = hashlib.sha256(T.run(api, fmt, img, prof).tobytes()).hexdigest()
-            source[fmt] = tag
+            if fmt in ("BC4", "BC5"):
+                data, source[fmt] = DX.ref_encode(dxlib, fmt, img), "DirectXTex encoder bodies (oracle/build_ref_frontend.py)"
+            else:
+                data, source[fmt] = T.run(ref, fmt, img, prof), "reference-source"
+            digests[f"{fmt}:{prof}:{name}"] = hashlib.sha256(data.tobytes()).hexdigest()
     for fmt in ("BC7", "BC6H"):
         for name, img in T.corpus_for(fmt).items():
             inputs[f"{fmt}:{name}"] = hashlib.sha256(img.tobytes()).hexdigest()

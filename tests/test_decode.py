@@ -135,3 +135,67 @@ def test_gpu_encode_decode_round_trip_full_size():
     d_a = torch.empty_like(d_img)
     p.decode_raw("BC4", d_blocks.data_ptr(), d_a.data_ptr(), n, n, n * 4)
     assert int((d_a[..., 0].int() - d_img[..., 0].int()).abs().max()) <= 1
+
+
+def _ref_decoders():
+    import ctypes
+    lib = T.ref_frontend()
+    if lib is None:
+        pytest.skip("reference bodies not built (no /root/reference and no prebuilt oracle/_ref)")
+    for name in ("ref_decode_bc1", "ref_decode_bc3"):
+        getattr(lib, name).restype = None
+        getattr(lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    return lib
+
+
+def _rounded(floats):
+    """the UNORM8 store assumed for the preview: x * 255 + 0.5 truncated, evaluated in float32"""
+    f = floats.astype(np.float32)
+    return (f * np.float32(255.0) + np.float32(0.5)).astype(np.int64)
+
+
+def test_bc1_bc3_decode_equals_directxtex_decoder_bodies_rounded():
+    """csrc/decode.cuh (through the emulation) against DirectXTex's OWN DecodeBC1 / D3DXDecodeBC3 bodies (float texels,
+    cut by oracle/build_ref_frontend.py), rounded to nearest: every 5- and 6-bit endpoint pair in both palette modes,
+    every alpha endpoint pair, plus random blocks."""
+    lib, e = _ref_decoders(), T.emu()
+    blocks = []
+    idx = 0
+    for k in range(16):
+        idx |= (k % 4) << (2 * k)
+    idx_bytes = np.frombuffer(int(idx).to_bytes(4, "little"), np.uint8)
+    for n0 in range(64):                                   # all endpoint pairs per channel (5-bit values repeat mod 32)
+        for n1 in range(64):
+            c0 = ((n0 & 31) << 11) | (n0 << 5) | (n1 & 31)
+            c1 = ((n1 & 31) << 11) | (n1 << 5) | (n0 & 31)
+            blocks.append(np.concatenate([np.frombuffer(int(c0).to_bytes(2, "little") + int(c1).to_bytes(2, "little"), np.uint8), idx_bytes]))
+    rng = np.random.default_rng(12)
+    blocks += [rng.integers(0, 256, 8, dtype=np.uint8) for _ in range(4096 - len(blocks) % 4096)]
+    bc1 = np.concatenate(blocks)
+    n = bc1.size // 8
+    h = 4 * (n // 64)
+    got = e.decode("BC1", bc1[: (h // 4) * 64 * 8], 256, h).reshape(h // 4, 4, 64, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
+    for i in range(got.shape[0]):
+        out = np.zeros(64, np.float32)
+        blk = np.ascontiguousarray(bc1[8 * i:8 * i + 8])
+        lib.ref_decode_bc1(blk.ctypes.data, out.ctypes.data)
+        assert np.array_equal(got[i].astype(np.int64), _rounded(out).reshape(16, 4)), i
+    # BC3: colour block always in four-colour mode + every alpha endpoint pair
+    blocks = []
+    aidx = 0
+    for k in range(16):
+        aidx |= (k % 8) << (3 * k)
+    aidx_bytes = np.frombuffer(int(aidx).to_bytes(6, "little"), np.uint8)
+    for a0 in range(256):
+        for a1 in range(0, 256, 3):
+            colour = rng.integers(0, 256, 8, dtype=np.uint8)
+            blocks.append(np.concatenate([np.array([a0, a1], np.uint8), aidx_bytes, colour]))
+    blocks = blocks[: (len(blocks) // 64) * 64]
+    bc3 = np.concatenate(blocks)
+    h = 4 * (len(blocks) // 64)
+    got = e.decode("BC3", bc3, 256, h).reshape(h // 4, 4, 64, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
+    for i in range(got.shape[0]):
+        out = np.zeros(64, np.float32)
+        blk = np.ascontiguousarray(bc3[16 * i:16 * i + 16])
+        lib.ref_decode_bc3(blk.ctypes.data, out.ctypes.data)
+        assert np.array_equal(got[i].astype(np.int64), _rounded(out).reshape(16, 4)), i
