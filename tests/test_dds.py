@@ -108,3 +108,41 @@ def test_encode_file_equals_per_level_encodes():
         off = lib.lib.itw_dds_image_offset(ctypes.byref(d), 0, mip)
         want = lib.encode("BC7", np.ascontiguousarray(chain[mip]), s)
         assert np.array_equal(blob[off:off + want.size], want), mip
+
+
+def test_header_equals_directxtex_header_encoder():
+    """itw_dds_write_header against the reference's OWN _EncodeDDSHeader body (DirectXTexDDS.cpp:441-675 + DDS.h, cut by
+    oracle/build_ref_dds.py): every block-compressed format the library writes x sizes x mip counts x plain / cube / array."""
+    import ctypes
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(T.ROOT, "oracle"))
+    try:
+        import build_ref_dds
+        try:
+            path = build_ref_dds.build(verbose=False)
+        except FileNotFoundError:
+            pytest.skip("reference not present and no prebuilt oracle/_ref/libitw_ref_dds.so")
+    finally:
+        sys.path.pop(0)
+    ref = ctypes.CDLL(path)
+    ref.ref_dds_header.restype = ctypes.c_size_t
+    ref.ref_dds_header.argtypes = [ctypes.c_uint32] * 6 + [ctypes.c_void_p, ctypes.c_size_t]
+    lib = T.product().lib
+    n = 0
+    for fmt in (71, 72, 77, 78, 80, 83, 95, 96, 98, 99):
+        for (w, h) in ((256, 256), (60, 36), (1, 1), (4096, 2048), (5, 300)):
+            for mips in (1, 2, 5):
+                if mips > max(w, h).bit_length():                  # more levels than the size has
+                    continue
+                for (items, cube) in ((1, 0), (6, 1), (3, 0), (12, 1)):
+                    d = D(w, h, mips, items, fmt, cube)
+                    want = np.zeros(160, np.uint8)
+                    size = ref.ref_dds_header(w, h, mips, items, fmt, cube, want.ctypes.data, 160)
+                    assert size in (128, 148)
+                    got = np.zeros(160, np.uint8)
+                    assert lib.itw_dds_header_bytes(ctypes.byref(d)) == size, (fmt, w, h, mips, items, cube)
+                    assert lib.itw_dds_write_header(ctypes.byref(d), got.ctypes.data, 160) == size
+                    assert np.array_equal(got[:size], want[:size]), (fmt, w, h, mips, items, cube)
+                    n += 1
+    assert n == 520
