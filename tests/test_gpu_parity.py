@@ -227,3 +227,21 @@ def test_release_frees_and_next_call_recreates():
     lib.lib.itw_release()                                 # idempotent
     assert np.array_equal(lib.encode("BC7", img, s), want)
     assert np.array_equal(lib.encode("BC1", img[:64]), small)
+
+
+def test_baseline_configs_c1_c2_c3_against_the_oracle():
+    """SURVEY.md 8d / BASELINE configs.  C1 (BC1, 512^2 gradient): the whole image against the oracle.  C2 / C3 (4096^2 random
+    RGBA8 / RGBA16F, the seeded generators of synth.py): full-size encodes through the C-ABI, every 64th block row against the
+    oracle (the oracle needs seconds per band at these profiles)."""
+    lib, oracle = T.product(), T.oracle()
+    c1 = T.synth.gradient_rgba8(512, 512)
+    assert c1[0, 511, 0] == 255 and c1[511, 0, 1] == 255 and c1[511, 511, 2] == 255
+    assert np.array_equal(lib.encode("BC1", c1), T.run(oracle, "BC1", c1, None))
+    c2 = T.synth.random_rgba8(4096, 4096)
+    c3 = T.synth.random_rgba16f(4096, 4096)
+    for fmt, prof, img in (("BC7", "slow", c2), ("BC7", "alpha_slow", c2), ("BC6H", "bc6h_slow", c3)):
+        got = lib.encode(fmt, img, lib.profile(prof)).reshape(1024, 1024 * 16)
+        for row in (0, 448, 1023):
+            band = np.ascontiguousarray(img[4 * row:4 * row + 4, :512])          # 128 blocks of that block row
+            want = T.run(oracle, fmt, band, prof)
+            assert np.array_equal(got[row, :128 * 16], want), (fmt, prof, row)
