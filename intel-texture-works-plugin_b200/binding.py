@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path():
-    return os.path.join(HERE, "libitw_bcn.so")
+    # ITW_BCN_LIB selects another build of the same sources (tools/tune_unroll.sh); there is no other implementation to fall back to
+    return os.environ.get("ITW_BCN_LIB", os.path.join(HERE, "libitw_bcn.so"))
 
 
 class RgbaSurface(ctypes.Structure):          # ispc_texcomp.h:19-25

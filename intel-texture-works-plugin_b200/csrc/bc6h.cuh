@@ -13,6 +13,10 @@
 #pragma once
 #include "bc67_core.cuh"
 
+#ifndef ITW_BC6_ASSIGN_UNROLL
+#define ITW_BC6_ASSIGN_UNROLL 8           // tuned on B200, tools/tune_unroll.sh
+#endif
+
 namespace itw {
 
 struct Bc6Params {
@@ -256,7 +260,7 @@ ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32
     }
     float total = 0.0f;
     u32 out0 = 0u, out1 = 0u;
-#pragma unroll 2
+    ITW_UNROLL(ITW_BC6_ASSIGN_UNROLL)
     for (int k = 0; k < 16; k++) {
         const bool second = ((pattern >> (2 * k)) & 3u) != 0u;
         int a[3], b[3];

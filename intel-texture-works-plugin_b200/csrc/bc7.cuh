@@ -35,6 +35,14 @@
 #pragma once
 #include "bc67_core.cuh"
 
+// unroll factors of the two hottest loops (tuned on B200, tools/tune_unroll.sh)
+#ifndef ITW_BC7_ASSIGN_UNROLL
+#define ITW_BC7_ASSIGN_UNROLL 16
+#endif
+#ifndef ITW_BC7_POWER_UNROLL
+#define ITW_BC7_POWER_UNROLL 4
+#endif
+
 namespace itw {
 
 // bc7_enc_settings (ispc_texcomp.h:27-41) flattened to ints for the device
@@ -160,7 +168,7 @@ template <int CH, int kIterations>
 ITW_HD void bc7_power_axis(float (&axis)[4], const float (&m)[10])
 {
     float v0 = 1.0f, v1 = 1.0f, v2 = 1.0f, v3 = 1.0f;
-#pragma unroll 2
+    ITW_UNROLL(ITW_BC7_POWER_UNROLL)
     for (int it = 0; it < kIterations; it++) {
         float a0, a1, a2, a3 = 0.0f;
         if (CH == 3) {
@@ -428,7 +436,7 @@ ITW_HD_NOINLINE Bc7Search bc7_assign(u32 (*pal)[32], int lane, const Bc7Block* b
     const float flevels = (float)levels;
     int total = 0;
     u32 out0 = 0u, out1 = 0u;
-#pragma unroll 8
+    ITW_UNROLL(ITW_BC7_ASSIGN_UNROLL)
     for (int k = 0; k < 16; k++) {
         const u32 t = view_tex(v, k) & chmask;
         const int j = (int)((pattern >> (2 * k)) & 3u);

@@ -30,6 +30,10 @@
 
 #include "itw_tables.cuh"
 
+// `#pragma unroll N` with N from a macro (pragmas are not macro-expanded): ITW_UNROLL(N)
+#define ITW_PRAGMA(x) _Pragma(#x)
+#define ITW_UNROLL(n) ITW_PRAGMA(unroll n)
+
 namespace itw {
 
 typedef uint32_t u32;
