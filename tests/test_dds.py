@@ -146,3 +146,29 @@ def test_header_equals_directxtex_header_encoder():
                     assert np.array_equal(got[:size], want[:size]), (fmt, w, h, mips, items, cube)
                     n += 1
     assert n == 520
+
+
+def test_reader_survives_corrupted_and_random_headers():
+    """itw_dds_read_header parses untrusted bytes: mutated valid headers and random buffers, truncated at random, must be
+    rejected or yield a description the library can size -- never crash."""
+    import ctypes
+    lib = T.product().lib
+    d = D(64, 64, 3, 1, 98, 0)
+    n = lib.itw_dds_header_bytes(ctypes.byref(d))
+    good = np.zeros(200, np.uint8)
+    lib.itw_dds_write_header(ctypes.byref(d), good.ctypes.data, 200)
+    rng = np.random.default_rng(0)
+    out = D()
+    accepted = 0
+    for _ in range(20000):
+        b = good.copy()
+        for _ in range(int(rng.integers(1, 6))):
+            b[rng.integers(0, n)] = rng.integers(0, 256)
+        if lib.itw_dds_read_header(b.ctypes.data, int(rng.integers(0, n + 8)), ctypes.byref(out)):
+            accepted += 1
+            assert lib.itw_dds_file_bytes(ctypes.byref(out)) > 0
+    assert accepted > 0
+    for _ in range(20000):
+        b = rng.integers(0, 256, 200, dtype=np.uint8)
+        b[:4] = good[:4]
+        lib.itw_dds_read_header(b.ctypes.data, int(rng.integers(0, 200)), ctypes.byref(out))
