@@ -87,3 +87,30 @@ def test_profiles_identical_across_implementations():
     for name in B.BC7_PROFILES + B.BC6H_PROFILES:
         got = [_fields(a.profile(name)) for a in apis]
         assert all(g == got[0] for g in got), name
+
+
+def test_no_cpu_fallback_when_there_is_no_gpu():
+    """On a machine without a CUDA device every compute entry point must FAIL LOUDLY (error string, output untouched):
+    the product has no CPU path.  (Skipped where a GPU exists.)"""
+    import ctypes
+    import numpy as np
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present")
+    except ImportError:
+        pass
+    lib = T.product()
+    img = np.full((8, 8, 4), 77, np.uint8)
+    out = np.full(4 * 16, 0xAB, np.uint8)
+    surf = T.binding.RgbaSurface(img.ctypes.data, 8, 8, 32)
+    for fmt, settings in (("BC1", None), ("BC3", None), ("BC4", None), ("BC5", None), ("BC7", lib.profile("veryfast"))):
+        out[:] = 0xAB
+        with pytest.raises(RuntimeError, match="libitw_bcn"):
+            lib.encode_raw(fmt, img.ctypes.data, 8, 8, 32, out.ctypes.data, settings)
+        assert (out == 0xAB).all(), fmt                      # nothing was written
+    with pytest.raises(RuntimeError):
+        lib.decode("BC1", np.zeros(32, np.uint8), 8, 8)
+    with pytest.raises(RuntimeError):
+        lib.convert_pixels("BC7", img, 1)
+    assert lib.last_error() != ""
