@@ -18,22 +18,31 @@
 namespace itw {
 
 // LSB-first reader over one 128-bit block
+// The block is kept in four 32-bit registers and CONSUMED: every read returns the low n bits and funnel-shifts the whole
+// 128-bit value right by n (n < 32), four SHF instructions, no position bookkeeping and no branches.
+ITW_HD u32 funnel_r(u32 lo, u32 hi, int n)     // low word of (hi:lo) >> n, 0 <= n < 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, n);
+#else
+    return (u32)((((unsigned long long)hi << 32) | lo) >> n);
+#endif
+}
 struct BitReader {
-    unsigned long long lo, hi;
-    int pos;
-    ITW_HD void init(const u32 (&w)[4])
+    u32 w0, w1, w2, w3;
+    ITW_HD void init(const u32 (&w)[4]) { w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3]; }
+    ITW_HD void skip(int n)                   // 0 <= n < 32
     {
-        lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
-        hi = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
-        pos = 0;
+        w0 = funnel_r(w0, w1, n);
+        w1 = funnel_r(w1, w2, n);
+        w2 = funnel_r(w2, w3, n);
+        w3 >>= n;
     }
     ITW_HD u32 get(int n)                     // 0 <= n <= 16
     {
-        unsigned long long v;
-        if (pos >= 64) v = hi >> (pos - 64);
-        else v = (lo >> pos) | ((pos == 0) ? 0ull : (hi << (64 - pos)));
-        pos += n;
-        return (u32)v & ((1u << n) - 1u);
+        const u32 v = w0 & ((1u << n) - 1u);
+        skip(n);
+        return v;
     }
 };
 
@@ -132,7 +141,7 @@ ITW_HD bool decode_bc7(u32 (&px)[16], const u32 (&w)[4])
     BitReader b;
     b.init(w);
     const int mode = lowest_set_bit(w[0] & 255u);
-    b.pos = mode + 1;
+    b.skip(mode + 1);
     const Bc7ModeDesc d = bc7_mode_desc(mode);
     const int shape = (int)b.get(d.pb), rot = (int)b.get(d.rb), isel = (int)b.get(d.isb);
     const int ne = 2 * d.ns;
