@@ -121,14 +121,68 @@ int itw_bytes_per_block(int format);
 int itw_encode_device(int format, const rgba_surface* src, uint8_t* dst, const void* settings,
                       void* cuda_stream);
 
-/* Batched encode of `count` independent surfaces (config C5's tile stream; the coarse seam the
- * plug-in's CompressImageMT/ST offer, win32Threads.h:57-58).  Host surfaces are pipelined
- * H2D / encode / D2H over internal streams; dst[i] receives surface i's blocks. */
+/* Batched encode of `count` independent surfaces (config C5's tile stream).  Host surfaces are pipelined
+ * H2D / encode / D2H over internal streams (and dealt round-robin over the devices of itw_set_devices);
+ * dst[i] receives surface i's blocks.  Synchronous.  Ordering: device-resident operands are ordered after the work
+ * already enqueued on the legacy default stream / blocking streams at the time of the call (as for
+ * CompressBlocks*); producers on NON-blocking streams must be synchronised by the caller.  The same rule holds for the
+ * device-resident surfaces of itw_dds_encode_file / itw_dds_encode_texture / itw_dds_encode_pixels. */
 int itw_encode_batch(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count,
                      const void* settings);
 
 /* Select the CUDA device used by this thread's subsequent calls (default: current device). */
 int itw_set_device(int device);
+
+/* Multi-GPU in ONE process (the analogue of the reference's thread pool, win32Threads.cpp:98-274, which
+ * fans row bands of one surface over its workers, :211-249).  After itw_set_devices(list, n >= 2) every HOST -> HOST
+ * call of CompressBlocks* / CompressImage* is cut into one band of whole block rows per device; each device copies
+ * in, encodes and copies out its band on its own PCIe link, straight into the caller's dst.  itw_encode_batch deals
+ * its tiles round-robin over the devices (config C5's tile stream).  Bands and tiles are independent, so the output is
+ * byte-identical to the single-device one; there is no collective.  Device-resident operands stay on their device.
+ * n == 1 makes that device the process-wide default; n == 0 restores the single-device behaviour (the calling
+ * thread's current device / itw_set_device).  Process-wide; not to be called concurrently with encodes.
+ * Returns 0 on success. */
+int itw_set_devices(const int* devices, int count);
+/* The devices selected by itw_set_devices (written to devices[0..capacity)); returns their number, 0 if none. */
+int itw_get_devices(int* devices, int capacity);
+
+/* Deferred mode for hosts that keep the reference's slice loop (IntelPlugin.cpp:851-879: one CompressImageMT per
+ * 256 K-texel slice of the image).  Between itw_begin_deferred() and itw_flush(), host -> host encodes issued by the
+ * calling thread are only ENQUEUED (copy-in, kernel, copy-out on internal streams, pipelined over three lanes) and
+ * return at once; src and dst must stay valid and untouched until itw_flush(), which waits for all of them and returns
+ * 0 or the first failure (text in itw_get_last_error).  Two added lines in the host: begin before the loop, flush after. */
+int itw_begin_deferred(void);
+int itw_flush(void);
+
+/* ---- the reference's coarse seam: 3rdParty/Intel/Source/win32Threads.h:24, :52-80 (win32Threads.cpp:192-330) ----
+ * Same names and argument meaning; BYTE is spelled uint8_t and DXGI_FORMAT is passed as int (the enum's underlying
+ * type).  CompressImageBC* = GetProfile + CompressBlocks* (win32Threads.cpp:289-330).  CompressImageMT / ST call
+ * `cmpFunc` ONCE for the whole surface: the reference's per-thread bands (win32Threads.cpp:217-230) become one GPU
+ * launch, or one band per device after itw_set_devices / InitWin32Threads -- same bytes, bands being independent. */
+typedef void(CompressionFunc)(const rgba_surface* input, uint8_t* output);
+int  GetProcessorCount(void);      /* visible CUDA devices, 1 or more (win32Threads.h:52) */
+void InitWin32Threads(void);       /* select every visible GPU (itw_set_devices) -- the pool the reference builds here */
+void DestroyThreads(void);         /* back to single-device behaviour */
+int  GetBytesPerBlock(int dxgi_format);
+bool CompressImageMT(const rgba_surface* input, uint8_t* output, CompressionFunc* cmpFunc, int compformat);
+bool CompressImageST(const rgba_surface* input, uint8_t* output, CompressionFunc* cmpFunc, int compformat);
+void CompressImageBC1(const rgba_surface* input, uint8_t* output);
+void CompressImageBC3(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_ultrafast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_veryfast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_fast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_basic(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_slow(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_alpha_ultrafast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_alpha_veryfast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_alpha_fast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_alpha_basic(const rgba_surface* input, uint8_t* output);
+void CompressImageBC7_alpha_slow(const rgba_surface* input, uint8_t* output);
+void CompressImageBC6H_veryfast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC6H_fast(const rgba_surface* input, uint8_t* output);
+void CompressImageBC6H_basic(const rgba_surface* input, uint8_t* output);
+void CompressImageBC6H_slow(const rgba_surface* input, uint8_t* output);
+void CompressImageBC6H_veryslow(const rgba_surface* input, uint8_t* output);
 
 /* Last error message of the calling thread ("" if none).  The CompressBlocks* entry points keep
  * the reference's void signature, so this is the only error channel for them. */
@@ -265,6 +319,46 @@ int itw_encode_pixels(int format, const itw_pixel_source* src, uint32_t flags, c
  * error. */
 size_t itw_dds_encode_pixels(const itw_dds_desc* desc, const itw_pixel_source* sources, uint32_t flags,
                              const void* settings, uint8_t* file, size_t capacity);
+
+/* ---------------------------------------------------------------------------------------------
+ * Section 7 -- row-sharded encode over several GPUs, one process per GPU:
+ * "images shard row-wise across the GPUs with a single NCCL all-gather of the packed output".
+ * Band rule = the reference's thread split (win32Threads.cpp:217-230).  Every rank holds its rows of level 0
+ * of an RGBA8 texture on its device; mips are made band-locally while a level's band is a whole number of block
+ * rows, each band is encoded where it lies, ONE ncclAllGather moves the packed bands (plus the few KiB of raw
+ * texels the tiny remaining levels are filtered from), and every rank ends up with the complete packed chain --
+ * byte-identical to the single-GPU encode of the same texture.  NCCL is bound at run time (libnccl.so.2, or the
+ * path in ITW_NCCL_LIB); with no communicator the same call runs on one GPU.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct itw_shard_plan {
+    int32_t  nranks, rank, levels;
+    int32_t  band_levels;         /* leading levels whose row bands are whole block rows on every rank            */
+    int32_t  band_y0, band_y1;    /* rows of level 0 owned by `rank`                                              */
+    uint64_t slot_bytes;          /* per-rank payload of the all-gather (multiple of 16)                          */
+    uint64_t chain_bytes;         /* the complete packed chain, levels 0..levels-1 back to back (= DDS payload)   */
+    uint64_t level_offset[16];    /* of level l in the chain                                                      */
+    uint64_t level_bytes[16];
+    uint64_t send_offset[16];     /* of this rank's band of level l inside its slot (l < band_levels)             */
+    uint64_t band_bytes[16];      /* one rank's band of level l; rank r's band sits at level_offset + r*band_bytes */
+    uint64_t texel_offset;        /* raw texels of level band_levels-1 inside the slot ...                        */
+    uint64_t texel_bytes;         /* ... 0 when every level is band-local                                         */
+} itw_shard_plan;
+/* Pure arithmetic (no CUDA call): the layout used by itw_encode_mip_chain_sharded.  width/height multiples of 4,
+ * levels <= 16, height / nranks a multiple of 4 rows.  Returns 0 on success. */
+int itw_shard_plan_make(int format, int width, int height, int levels, int nranks, int rank, itw_shard_plan* plan);
+/* NCCL bootstrap: rank 0 obtains an id (ncclGetUniqueId), the host passes it to the other ranks by its own means
+ * (MPI, a torch.distributed broadcast, a file), every rank calls itw_shard_init on the thread and device it encodes
+ * with (ncclCommInitRank).  itw_shard_finalize destroys the calling thread's communicator. */
+int itw_shard_unique_id(uint8_t id[128]);
+int itw_shard_init(int rank, int nranks, const uint8_t id[128]);
+void itw_shard_finalize(void);
+/* band0 = this rank's rows [band_y0, band_y1) of level 0 (device memory, any 4-byte aligned stride; width x
+ * (band_y1-band_y0)); chain = device buffer of plan.chain_bytes (16-byte aligned) that receives the COMPLETE packed
+ * chain on every rank.  Everything is enqueued on `cuda_stream` (cudaStream_t as void*), nothing is synchronised;
+ * the scratch belongs to the calling thread, so consecutive calls of one thread must use one stream (or be separated
+ * by a synchronisation).  `settings` as for itw_encode_device.  Returns 0 on success. */
+int itw_encode_mip_chain_sharded(int format, const rgba_surface* band0, int width, int height, int levels,
+                                 const void* settings, uint8_t* chain, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,11 @@ EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "Comp
             "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
             "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file",
             "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture", "itw_decode", "itw_convert_pixels", "itw_encode_pixels",
-            "itw_generate_mips_device_f16", "itw_dds_encode_pixels", "itw_release"]
+            "itw_generate_mips_device_f16", "itw_dds_encode_pixels", "itw_release", "itw_set_devices", "itw_get_devices",
+            "itw_begin_deferred", "itw_flush", "GetProcessorCount", "InitWin32Threads", "DestroyThreads", "GetBytesPerBlock",
+            "CompressImageMT", "CompressImageST", "CompressImageBC1", "CompressImageBC3",
+            "itw_shard_plan_make", "itw_shard_unique_id", "itw_shard_init", "itw_shard_finalize", "itw_encode_mip_chain_sharded"]
+           + ["CompressImageBC7_" + p for p in BC7_PROFILES] + ["CompressImage" + p.replace("bc6h_", "BC6H_") for p in BC6H_PROFILES]
            + ["GetProfile_" + p for p in BC7_PROFILES + BC6H_PROFILES])
 
 
@@ -62,6 +66,13 @@ FRONT_HAS_ALPHA, FRONT_GAMMA, FRONT_FLIP_X, FRONT_FLIP_Y, FRONT_NORMALIZE = 1, 2
 class DdsDesc(ctypes.Structure):              # include/itw_bcn.h section 3
     _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("mip_levels", ctypes.c_uint32),
                 ("array_size", ctypes.c_uint32), ("dxgi_format", ctypes.c_uint32), ("is_cubemap", ctypes.c_uint32)]
+
+
+class ShardPlan(ctypes.Structure):            # include/itw_bcn.h section 7
+    _fields_ = [("nranks", ctypes.c_int32), ("rank", ctypes.c_int32), ("levels", ctypes.c_int32), ("band_levels", ctypes.c_int32),
+                ("band_y0", ctypes.c_int32), ("band_y1", ctypes.c_int32), ("slot_bytes", ctypes.c_uint64), ("chain_bytes", ctypes.c_uint64),
+                ("level_offset", ctypes.c_uint64 * 16), ("level_bytes", ctypes.c_uint64 * 16), ("send_offset", ctypes.c_uint64 * 16),
+                ("band_bytes", ctypes.c_uint64 * 16), ("texel_offset", ctypes.c_uint64), ("texel_bytes", ctypes.c_uint64)]
 
 
 class EncoderApi:
@@ -270,6 +281,24 @@ class ItwBcn(EncoderApi):
     def set_device(self, index):
         if self.lib.itw_set_device(int(index)) != 0:
             self.check()
+
+    def set_devices(self, indices):
+        """itw_set_devices: host -> host calls fan out over these GPUs (one process); [] = single-device behaviour."""
+        arr = (ctypes.c_int * max(len(indices), 1))(*indices)
+        self.lib.itw_set_devices.restype = ctypes.c_int
+        self.lib.itw_set_devices.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        if self.lib.itw_set_devices(arr, len(indices)) != 0:
+            self.check()
+            raise RuntimeError("itw_set_devices failed")
+
+    def begin_deferred(self):
+        if self.lib.itw_begin_deferred() != 0:
+            self.check()
+
+    def flush(self):
+        if self.lib.itw_flush() != 0:
+            self.check()
+            raise RuntimeError("itw_flush failed")
 
     def launch_count(self):
         return int(self.lib.itw_kernel_launch_count())

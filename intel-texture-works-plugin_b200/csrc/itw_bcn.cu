@@ -10,10 +10,14 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/itw_bcn.h"
@@ -29,6 +33,7 @@ using namespace itw;
 namespace {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_default_device{-1};      // itw_set_devices() with ONE device: the process-wide default
 
 struct ThreadCtx {
     int device = -1;             // device the resources below belong to
@@ -52,6 +57,11 @@ struct ThreadCtx {
         uint8_t* d_out = nullptr; size_t d_out_cap = 0;
         bool busy = false;
     } lanes[3];
+    // deferred mode (itw_begin_deferred / itw_flush): host calls are enqueued on the lanes round-robin and drained by itw_flush
+    bool deferred = false;
+    unsigned deferred_next = 0;
+    int deferred_rc = 0;
+    float pool_ms = -1.0f;       // multi-device call: max over the devices of their kernel time
     void release()
     {
         // best effort: at process exit the runtime may already be unloading, errors are ignored
@@ -97,6 +107,9 @@ int ensure_ctx()
     if (c.wanted_device >= 0) {
         ITW_CUDA(cudaSetDevice(c.wanted_device));
         dev = c.wanted_device;
+    } else if (g_default_device.load(std::memory_order_relaxed) >= 0) {
+        dev = g_default_device.load(std::memory_order_relaxed);
+        ITW_CUDA(cudaSetDevice(dev));
     } else {
         ITW_CUDA(cudaGetDevice(&dev));
     }
@@ -142,10 +155,14 @@ bool format_info(int format, FormatInfo& f)
         default: return false;
     }
 }
+// 0 = encode it, 1 = nothing to do, -1 = error.  Zero-height bands are legitimate: CompressImageMT hands them to the
+// threads beyond height/4 (win32Threads.cpp:217-230) and the reference's loops simply do not execute (kernel.ispc:600).
 int check_surface(const rgba_surface* s, const FormatInfo& f)
 {
-    if (!s || !s->ptr) return fail("null surface");
-    if (s->width <= 0 || s->height <= 0 || (s->width & 3) || (s->height & 3))
+    if (!s) return fail("null surface");
+    if (s->height == 0 && s->width >= 0 && (s->width & 3) == 0) return 1;
+    if (!s->ptr) return fail("null surface");
+    if (s->width <= 0 || s->height < 0 || (s->width & 3) || (s->height & 3))
         return fail("surface width/height must be positive multiples of 4 (ispc_texcomp.h:93-95)");
     if ((long long)s->stride < (long long)s->width * f.texel_bytes) return fail("surface stride smaller than a texel row");
     return 0;
@@ -220,7 +237,7 @@ int encode_many(int format, const rgba_surface* srcs, uint8_t* const* dsts, int 
 
 // Host surface -> host blocks for the COMPUTE-bound encoders (BC7, BC6H): the surface is cut into four row bands whose
 // H2D copies, kernels and D2H copies run on three streams, so that all but the first (small) band's input copy and all
-// but the last band's output copy hide behind the kernels.  (For BC1-BC5 the copies ARE the cost -- see encode_any.)
+// but the last band's output copy hide behind the kernels.  (For BC1-BC5 the copies ARE the cost -- see encode_single.)
 // Bands are whole block rows; the kernels see each band as an independent surface, exactly as the reference's own
 // callers do (win32Threads.cpp:217-230), so the output is unchanged.
 int encode_banded(int format, const rgba_surface* src, uint8_t* dst, const void* settings, const FormatInfo& f)
@@ -247,52 +264,94 @@ int encode_banded(int format, const rgba_surface* src, uint8_t* dst, const void*
     first[2] = first[1] + rest / 3;
     first[3] = first[1] + (2 * rest) / 3;
     first[4] = block_rows;
-    for (int b = 0; b < 4; b++) {
+    // Every failure after the first enqueue leaves through `drain`: async copies into the caller's dst and kernels
+    // on the three streams must not stay in flight when the call returns -1 (the caller may free src / dst).
+    int rc = 0;
+    auto step = [&](cudaError_t e, const char* what) { if (rc == 0 && e != cudaSuccess) rc = fail(what, e); return rc == 0; };
+    for (int b = 0; b < 4 && rc == 0; b++) {
         const int r0 = first[b], r1 = first[b + 1];
         if (r1 <= r0) continue;
         const size_t rows = (size_t)(r1 - r0) * 4;
         uint8_t* d_band = c.d_in + (size_t)r0 * 4 * row_bytes;
         const uint8_t* h_band = src->ptr + (size_t)r0 * 4 * (size_t)src->stride;
-        if ((size_t)src->stride == row_bytes)
-            ITW_CUDA(cudaMemcpyAsync(d_band, h_band, row_bytes * rows, cudaMemcpyHostToDevice, c.copy_in));
-        else
-            ITW_CUDA(cudaMemcpy2DAsync(d_band, row_bytes, h_band, (size_t)src->stride, row_bytes, rows, cudaMemcpyHostToDevice, c.copy_in));
-        ITW_CUDA(cudaEventRecord(c.band_in[b], c.copy_in));
-        ITW_CUDA(cudaStreamWaitEvent(c.stream, c.band_in[b], 0));
-        if (b == 0) ITW_CUDA(cudaEventRecord(c.ev0, c.stream));
+        if ((size_t)src->stride == row_bytes) {
+            if (!step(cudaMemcpyAsync(d_band, h_band, row_bytes * rows, cudaMemcpyHostToDevice, c.copy_in), "band H2D")) break;
+        } else {
+            if (!step(cudaMemcpy2DAsync(d_band, row_bytes, h_band, (size_t)src->stride, row_bytes, rows, cudaMemcpyHostToDevice, c.copy_in), "band H2D")) break;
+        }
+        if (!step(cudaEventRecord(c.band_in[b], c.copy_in), "cudaEventRecord")) break;
+        if (!step(cudaStreamWaitEvent(c.stream, c.band_in[b], 0), "cudaStreamWaitEvent")) break;
+        if (b == 0 && !step(cudaEventRecord(c.ev0, c.stream), "cudaEventRecord")) break;
         const SurfaceView v{d_band, src->width, (int)rows, (int)row_bytes};
         uint8_t* d_blocks = c.d_out + (size_t)r0 * block_row_bytes;
-        if (launch(format, v, d_blocks, settings, c.stream)) {          // bad settings: nothing may stay in flight towards dst
-            cudaStreamSynchronize(c.copy_in); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(c.copy_out);
-            return -1;
-        }
-        ITW_CUDA(cudaEventRecord(c.band_done[b], c.stream));
-        ITW_CUDA(cudaStreamWaitEvent(c.copy_out, c.band_done[b], 0));
-        ITW_CUDA(cudaMemcpyAsync(dst + (size_t)r0 * block_row_bytes, d_blocks, (size_t)(r1 - r0) * block_row_bytes, cudaMemcpyDeviceToHost,
-                                 c.copy_out));
+        if (launch(format, v, d_blocks, settings, c.stream)) { rc = -1; break; }           // bad settings or a launch failure
+        if (!step(cudaEventRecord(c.band_done[b], c.stream), "cudaEventRecord")) break;
+        if (!step(cudaStreamWaitEvent(c.copy_out, c.band_done[b], 0), "cudaStreamWaitEvent")) break;
+        if (!step(cudaMemcpyAsync(dst + (size_t)r0 * block_row_bytes, d_blocks, (size_t)(r1 - r0) * block_row_bytes, cudaMemcpyDeviceToHost,
+                                  c.copy_out), "band D2H")) break;
     }
-    ITW_CUDA(cudaEventRecord(c.ev1, c.stream));
-    c.timed = true;
-    ITW_CUDA(cudaStreamSynchronize(c.copy_out));
-    ITW_CUDA(cudaStreamSynchronize(c.stream));
-    return 0;
+    if (rc == 0 && step(cudaEventRecord(c.ev1, c.stream), "cudaEventRecord")) c.timed = true;
+    // drain (also on error): nothing may stay in flight towards dst, and d_in / d_out must be idle for the next call
+    const cudaError_t e0 = cudaStreamSynchronize(c.copy_in), e1 = cudaStreamSynchronize(c.stream), e2 = cudaStreamSynchronize(c.copy_out);
+    if (rc == 0) { step(e0, "cudaStreamSynchronize"); step(e1, "cudaStreamSynchronize"); step(e2, "cudaStreamSynchronize"); }
+    else cudaGetLastError();
+    return rc;
 }
 
-// The CompressBlocks* path: src and dst may each be host or device memory.
-int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* settings)
+// Deferred mode (itw_begin_deferred .. itw_flush): a host -> host encode is enqueued on one of three lanes (stream +
+// staging buffers) and the call returns; the H2D copy of call i+1 overlaps the kernel of call i and the D2H copy of call
+// i-1.  The caller keeps src and dst valid until itw_flush().  This is what makes the reference's unchanged slice loop
+// (IntelPlugin.cpp:851-879: one CompressImageMT per 256 K-texel slice) cheap: no synchronisation per slice.
+int encode_deferred(int format, const rgba_surface* src, uint8_t* dst, const void* settings, const FormatInfo& f)
 {
-    tls.err.clear();
-    FormatInfo f;
-    if (!format_info(format, f)) return fail("unknown format");
-    if (check_surface(src, f)) return -1;
-    if (!dst) return fail("null dst");
+    ThreadCtx& c = tls;
+    ThreadCtx::Lane& L = c.lanes[c.deferred_next++ % 3];
+    if (!L.stream) ITW_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    if (L.busy) {                                      // its buffers are still in flight from three calls ago
+        ITW_CUDA(cudaStreamSynchronize(L.stream));
+        L.busy = false;
+    }
+    const size_t row_bytes = (size_t)src->width * f.texel_bytes;
+    const size_t out_bytes = (size_t)(src->width >> 2) * (src->height >> 2) * f.bpb;
+    if (grow(L.d_in, L.d_in_cap, row_bytes * src->height)) return -1;
+    if (grow(L.d_out, L.d_out_cap, out_bytes)) return -1;
+    if ((size_t)src->stride == row_bytes)
+        ITW_CUDA(cudaMemcpyAsync(L.d_in, src->ptr, row_bytes * src->height, cudaMemcpyHostToDevice, L.stream));
+    else
+        ITW_CUDA(cudaMemcpy2DAsync(L.d_in, row_bytes, src->ptr, (size_t)src->stride, row_bytes, (size_t)src->height, cudaMemcpyHostToDevice, L.stream));
+    L.busy = true;
+    const SurfaceView v{L.d_in, src->width, src->height, (int)row_bytes};
+    if (launch(format, v, L.d_out, settings, L.stream)) return -1;
+    ITW_CUDA(cudaMemcpyAsync(dst, L.d_out, out_bytes, cudaMemcpyDeviceToHost, L.stream));
+    c.timed = false;
+    return 0;
+}
+int drain_lanes(ThreadCtx& c)
+{
+    int rc = 0;
+    for (auto& L : c.lanes)
+        if (L.busy) {
+            if (cudaStreamSynchronize(L.stream) != cudaSuccess && rc == 0) rc = fail("cudaStreamSynchronize");
+            L.busy = false;
+        }
+    return rc;
+}
+
+// One device: src and dst may each be host or device memory.
+int encode_single(int format, const rgba_surface* src, uint8_t* dst, const void* settings, const FormatInfo& f)
+{
     if (ensure_ctx()) return -1;
     ThreadCtx& c = tls;
-    // (Splitting one large host surface into pipelined row bands was measured and rejected: the H2D copy is
+    // (Splitting one large host surface into pipelined row bands was measured and rejected for BC1-BC5: the H2D copy is
     //  >90 % of the BC1 end-to-end time, so overlap buys <0.1 ms while eight smaller copies cost 0.3 ms.)
     const size_t row_bytes = (size_t)src->width * f.texel_bytes;
     const size_t out_bytes = (size_t)(src->width >> 2) * (src->height >> 2) * f.bpb;
     const bool src_dev = is_device_pointer(src->ptr), dst_dev = is_device_pointer(dst);
+    if (!src_dev && !dst_dev && c.deferred) {
+        const int rc = encode_deferred(format, src, dst, settings, f);
+        if (rc && c.deferred_rc == 0) c.deferred_rc = rc;
+        return rc;
+    }
     if (!src_dev && !dst_dev && (format == ITW_FORMAT_BC7 || format == ITW_FORMAT_BC6H) && src->height >= 256)
         return encode_banded(format, src, dst, settings, f);
 
@@ -318,13 +377,154 @@ int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* se
         d_dst = c.d_out;
     }
     ITW_CUDA(cudaEventRecord(c.ev0, s));
-    if (launch(format, v, d_dst, settings, s)) return -1;
+    if (launch(format, v, d_dst, settings, s)) { cudaStreamSynchronize(s); cudaGetLastError(); return -1; }
     ITW_CUDA(cudaEventRecord(c.ev1, s));
     c.timed = true;
     if (!dst_ok)
         ITW_CUDA(cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
     ITW_CUDA(cudaStreamSynchronize(s));
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-device engine (the B200 analogue of the reference's thread pool, win32Threads.cpp:98-274).
+// itw_set_devices() creates one worker thread per selected GPU; every worker owns that device's ThreadCtx (streams,
+// staging buffers).  A host -> host call is then cut into one row band per device (whole block rows, like the
+// reference's per-thread bands, win32Threads.cpp:217-230 -- bands are independent surfaces, so the bytes are those
+// of a single-device encode), every worker runs its band through the single-device path above (H2D, kernels and D2H
+// on its own PCIe link) and writes straight into the caller's dst.  One process, one call, no collective.
+// ---------------------------------------------------------------------------------------------------------------
+class DevicePool {
+public:
+    explicit DevicePool(const std::vector<int>& devices)
+    {
+        for (int d : devices) workers_.emplace_back(new Worker(d));
+    }
+    ~DevicePool()
+    {
+        for (auto& w : workers_) {
+            { std::lock_guard<std::mutex> g(w->m); w->quit = true; }
+            w->cv.notify_all();
+            w->thread.join();
+        }
+    }
+    int size() const { return (int)workers_.size(); }
+    int device(int i) const { return workers_[i]->device; }
+    // Run jobs[i] on worker i (empty functions are skipped); returns 0 or -1 with the first error text in `err`
+    // and the largest kernel time in `ms`.
+    int run(const std::vector<std::function<int()>>& jobs, std::string& err, float& ms)
+    {
+        std::lock_guard<std::mutex> serial(run_mutex_);           // concurrent callers take turns
+        for (size_t i = 0; i < workers_.size() && i < jobs.size(); i++) {
+            Worker& w = *workers_[i];
+            if (!jobs[i]) continue;
+            { std::lock_guard<std::mutex> g(w.m); w.job = &jobs[i]; w.done = false; }
+            w.cv.notify_all();
+        }
+        int rc = 0;
+        ms = -1.0f;
+        for (size_t i = 0; i < workers_.size() && i < jobs.size(); i++) {
+            Worker& w = *workers_[i];
+            if (!jobs[i]) continue;
+            std::unique_lock<std::mutex> g(w.m);
+            w.cv.wait(g, [&] { return w.done; });
+            if (w.rc != 0 && rc == 0) { rc = -1; err = w.err; }
+            if (w.ms > ms) ms = w.ms;
+        }
+        return rc;
+    }
+
+private:
+    struct Worker {
+        int device;
+        std::mutex m;
+        std::condition_variable cv;
+        const std::function<int()>* job = nullptr;
+        bool done = true, quit = false;
+        int rc = 0;
+        float ms = -1.0f;
+        std::string err;
+        std::thread thread;
+        explicit Worker(int dev) : device(dev), thread([this] { loop(); }) {}
+        void loop()
+        {
+            tls.wanted_device = device;                           // this thread's ThreadCtx lives on `device`
+            for (;;) {
+                const std::function<int()>* j;
+                {
+                    std::unique_lock<std::mutex> g(m);
+                    cv.wait(g, [&] { return quit || job; });
+                    if (quit) break;
+                    j = job;
+                }
+                tls.err.clear();
+                const int r = (*j)();
+                float t = -1.0f;
+                if (tls.timed && cudaEventElapsedTime(&t, tls.ev0, tls.ev1) != cudaSuccess) { cudaGetLastError(); t = -1.0f; }
+                {
+                    std::lock_guard<std::mutex> g(m);
+                    rc = r; err = tls.err; ms = t; job = nullptr; done = true;
+                }
+                cv.notify_all();
+            }
+            tls.release();                                        // free this device's buffers on the owning thread
+        }
+    };
+    std::vector<std::unique_ptr<Worker>> workers_;
+    std::mutex run_mutex_;
+};
+std::mutex g_pool_mutex;
+std::shared_ptr<DevicePool> g_pool;                               // null = single-device behaviour
+std::shared_ptr<DevicePool> current_pool()
+{
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    return g_pool;
+}
+// smallest band worth a device of its own: below this the per-device launch + copy latency outweighs the split
+constexpr long long kPoolMinBlocksPerDevice = 4096;
+
+int encode_fanout(DevicePool& pool, int format, const rgba_surface* src, uint8_t* dst, const void* settings, const FormatInfo& f)
+{
+    const int block_rows = src->height >> 2;
+    const long long blocks_per_row = src->width >> 2;
+    int n = pool.size();
+    while (n > 1 && ((long long)block_rows * blocks_per_row) / n < kPoolMinBlocksPerDevice) n--;
+    if (n > block_rows) n = block_rows;
+    const size_t block_row_bytes = (size_t)blocks_per_row * f.bpb;
+    std::vector<rgba_surface> bands((size_t)n);
+    std::vector<std::function<int()>> jobs((size_t)pool.size());
+    for (int i = 0; i < n; i++) {
+        const int r0 = (int)((long long)block_rows * i / n), r1 = (int)((long long)block_rows * (i + 1) / n);
+        bands[i] = rgba_surface{src->ptr + (size_t)r0 * 4 * (size_t)src->stride, src->width, (r1 - r0) * 4, src->stride};
+        uint8_t* out = dst + (size_t)r0 * block_row_bytes;
+        const rgba_surface* band = &bands[i];
+        if (r1 > r0) jobs[i] = [=, &f]() { return encode_single(format, band, out, settings, f); };
+    }
+    std::string err;
+    float ms = -1.0f;
+    const int rc = pool.run(jobs, err, ms);
+    tls.timed = false;
+    tls.pool_ms = ms;
+    if (rc) return fail(err.c_str());
+    return 0;
+}
+
+// The CompressBlocks* path.
+int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* settings)
+{
+    tls.err.clear();
+    tls.pool_ms = -1.0f;
+    FormatInfo f;
+    if (!format_info(format, f)) return fail("unknown format");
+    const int chk = check_surface(src, f);
+    if (chk) return chk < 0 ? -1 : 0;
+    if (!dst) return fail("null dst");
+    if (std::shared_ptr<DevicePool> pool = current_pool()) {
+        if (pool->size() > 1 && !tls.deferred && (long long)(src->width >> 2) * (src->height >> 2) >= 2 * kPoolMinBlocksPerDevice &&
+            !is_device_pointer(src->ptr) && !is_device_pointer(dst))
+            return encode_fanout(*pool, format, src, dst, settings, f);
+    }
+    return encode_single(format, src, dst, settings, f);
 }
 
 
@@ -358,7 +558,7 @@ int decode_any(int format, const uint8_t* blocks, const rgba_surface* dst)
     tls.err.clear();
     FormatInfo f;
     if (!format_info(format, f)) return fail("unknown format");
-    if (check_surface(dst, f)) return -1;
+    if (const int chk = check_surface(dst, f)) return chk < 0 ? -1 : 0;
     if (!blocks) return fail("null blocks");
     if (ensure_ctx()) return -1;
     ThreadCtx& c = tls;
@@ -566,7 +766,7 @@ int itw_encode_device(int format, const rgba_surface* src, uint8_t* dst, const v
     tls.err.clear();
     FormatInfo f;
     if (!format_info(format, f)) return fail("unknown format");
-    if (check_surface(src, f)) return -1;
+    if (const int chk = check_surface(src, f)) return chk < 0 ? -1 : 0;
     if (!dst) return fail("null dst");
     if (reinterpret_cast<uintptr_t>(dst) & 15u) return fail("itw_encode_device: dst must be 16-byte aligned");
     if (ensure_ctx()) return -1;
@@ -591,22 +791,37 @@ int itw_encode_batch(int format, const rgba_surface* srcs, uint8_t* const* dsts,
 }  // extern "C"
 
 namespace {
-int encode_many(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings)
+// Tiles i = first, first+step, ... of the batch on THIS thread's device, pipelined over the three lanes.
+int encode_many_single(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings, int first, int step)
 {
     FormatInfo f;
     if (!format_info(format, f)) return fail("unknown format");
-    if (count < 0 || (count > 0 && (!srcs || !dsts))) return fail("itw_encode_batch: bad arguments");
     if (ensure_ctx()) return -1;
     ThreadCtx& c = tls;
-    int rc = 0;
-    for (int i = 0; i < count && rc == 0; i++) {
+    int rc = drain_lanes(c);
+    // Device-resident operands were produced by the caller's blocking streams: make every lane wait for what is already
+    // enqueued on the legacy default stream (the ordering rule of CompressBlocks*, see itw_bcn.h), once per call.
+    bool any_dev = false;
+    for (int i = first; i < count && !any_dev; i += step) any_dev = is_device_pointer(srcs[i].ptr) || is_device_pointer(dsts[i]);
+    if (any_dev && rc == 0) {
+        if (cudaEventRecord(c.ev0, cudaStreamLegacy) != cudaSuccess) rc = fail("cudaEventRecord");
+        for (auto& L : c.lanes) {
+            if (rc) break;
+            if (!L.stream && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate"); break; }
+            if (cudaStreamWaitEvent(L.stream, c.ev0, 0) != cudaSuccess) rc = fail("cudaStreamWaitEvent");
+        }
+    }
+    unsigned turn = 0;
+    for (int i = first; i < count && rc == 0; i += step) {
         const rgba_surface* src = &srcs[i];
         uint8_t* dst = dsts[i];
-        if (check_surface(src, f)) { rc = -1; break; }
+        const int chk = check_surface(src, f);
+        if (chk < 0) { rc = -1; break; }
+        if (chk > 0) continue;
         if (!dst) { rc = fail("null dst"); break; }
-        ThreadCtx::Lane& L = c.lanes[i % 3];
+        ThreadCtx::Lane& L = c.lanes[turn++ % 3];
         if (!L.stream && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate"); break; }
-        if (L.busy) {                                  // its buffers are still in flight from tile i-3
+        if (L.busy) {                                  // its buffers are still in flight from three tiles ago
             if (cudaStreamSynchronize(L.stream) != cudaSuccess) { rc = fail("cudaStreamSynchronize"); break; }
             L.busy = false;
         }
@@ -632,20 +847,40 @@ int encode_many(int format, const rgba_surface* srcs, uint8_t* const* dsts, int 
             if (grow(L.d_out, L.d_out_cap, out_bytes)) { rc = -1; break; }
             d_dst = L.d_out;
         }
+        L.busy = true;
         if (launch(format, v, d_dst, settings, L.stream)) { rc = -1; break; }
         if (!dst_ok) {
             e = cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, L.stream);
             if (e != cudaSuccess) { rc = fail("itw_encode_batch D2H", e); break; }
         }
-        L.busy = true;
     }
-    for (auto& L : c.lanes)                           // always drain, also on error
-        if (L.busy) {
-            if (cudaStreamSynchronize(L.stream) != cudaSuccess && rc == 0) rc = fail("cudaStreamSynchronize");
-            L.busy = false;
-        }
+    if (drain_lanes(c) && rc == 0) rc = -1;               // always drain, also on error
     tls.timed = false;
     return rc;
+}
+int encode_many(int format, const rgba_surface* srcs, uint8_t* const* dsts, int count, const void* settings)
+{
+    tls.pool_ms = -1.0f;
+    if (count < 0 || (count > 0 && (!srcs || !dsts))) return fail("itw_encode_batch: bad arguments");
+    // tile stream over several devices: host tiles are dealt round-robin, every device runs its
+    // own three-lane pipeline; no collective
+    if (std::shared_ptr<DevicePool> pool = current_pool()) {
+        bool host_only = count >= 2 && pool->size() > 1;
+        for (int i = 0; i < count && host_only; i++)
+            host_only = srcs[i].ptr && dsts[i] && !is_device_pointer(srcs[i].ptr) && !is_device_pointer(dsts[i]);
+        if (host_only) {
+            const int n = pool->size() < count ? pool->size() : count;
+            std::vector<std::function<int()>> jobs((size_t)pool->size());
+            for (int k = 0; k < n; k++) jobs[k] = [=]() { return encode_many_single(format, srcs, dsts, count, settings, k, n); };
+            std::string err;
+            float ms = -1.0f;
+            const int rc = pool->run(jobs, err, ms);
+            tls.timed = false;
+            if (rc) return fail(err.c_str());
+            return 0;
+        }
+    }
+    return encode_many_single(format, srcs, dsts, count, settings, 0, 1);
 }
 }  // namespace
 
@@ -658,6 +893,124 @@ int itw_set_device(int device)
     tls.wanted_device = device;
     return 0;
 }
+
+int itw_set_devices(const int* devices, int count)
+{
+    tls.err.clear();
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail("itw_set_devices: no CUDA device"); }
+    if (count < 0 || (count > 0 && !devices)) return fail("itw_set_devices: bad arguments");
+    std::vector<int> list(devices, devices + count);
+    for (size_t i = 0; i < list.size(); i++) {
+        if (list[i] < 0 || list[i] >= n) return fail("itw_set_devices: no such device");
+        for (size_t j = 0; j < i; j++) if (list[j] == list[i]) return fail("itw_set_devices: duplicate device");
+    }
+    std::shared_ptr<DevicePool> fresh, old;
+    if (list.size() >= 2) fresh = std::make_shared<DevicePool>(list);
+    {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        old.swap(g_pool);
+        g_pool = fresh;
+        g_default_device.store(list.size() == 1 ? list[0] : -1, std::memory_order_relaxed);
+    }
+    old.reset();                                          // joins the previous workers (after in-flight calls released it)
+    return 0;
+}
+int itw_get_devices(int* devices, int capacity)
+{
+    std::shared_ptr<DevicePool> pool = current_pool();
+    if (!pool) {
+        const int d = g_default_device.load(std::memory_order_relaxed);
+        if (d >= 0 && devices && capacity > 0) devices[0] = d;
+        return d >= 0 ? 1 : 0;
+    }
+    for (int i = 0; i < pool->size() && devices && i < capacity; i++) devices[i] = pool->device(i);
+    return pool->size();
+}
+
+int itw_begin_deferred(void)
+{
+    tls.err.clear();
+    if (ensure_ctx()) return -1;
+    tls.deferred = true;
+    tls.deferred_rc = 0;
+    return 0;
+}
+int itw_flush(void)
+{
+    ThreadCtx& c = tls;
+    int rc = c.deferred_rc;
+    const std::string first = c.err;                      // the first failure of a deferred call is the one reported
+    if (drain_lanes(c) && rc == 0) rc = -1;
+    else if (rc) c.err = first;
+    c.deferred = false;
+    c.deferred_rc = 0;
+    return rc;
+}
+
+// ---- the reference's coarse seam (3rdParty/Intel/Source/win32Threads.h:24, :52-80; win32Threads.cpp:192-330) ----
+// CompressImageBC* build the profile on the stack and call CompressBlocks*, exactly like win32Threads.cpp:289-330.
+// CompressImageMT / ST take the same arguments as the reference's; here BOTH hand the whole surface to the encoder in
+// one call: the reference's per-thread row bands (win32Threads.cpp:217-230) exist to occupy CPU cores, while one GPU
+// launch (or one band per selected device, itw_set_devices) already covers the surface -- the bytes are the same
+// because bands are independent surfaces.
+void CompressImageBC1(const rgba_surface* input, uint8_t* output) { CompressBlocksBC1(input, output); }
+void CompressImageBC3(const rgba_surface* input, uint8_t* output) { CompressBlocksBC3(input, output); }
+#define ITW_IMAGE_BC7(profile)                                                             \
+    void CompressImageBC7_##profile(const rgba_surface* input, uint8_t* output)            \
+    {                                                                                      \
+        bc7_enc_settings settings;                                                         \
+        GetProfile_##profile(&settings);                                                   \
+        CompressBlocksBC7(input, output, &settings);                                       \
+    }
+#define ITW_IMAGE_BC6H(profile)                                                            \
+    void CompressImageBC6H_##profile(const rgba_surface* input, uint8_t* output)           \
+    {                                                                                      \
+        bc6h_enc_settings settings;                                                        \
+        GetProfile_bc6h_##profile(&settings);                                              \
+        CompressBlocksBC6H(input, output, &settings);                                      \
+    }
+ITW_IMAGE_BC7(ultrafast) ITW_IMAGE_BC7(veryfast) ITW_IMAGE_BC7(fast) ITW_IMAGE_BC7(basic) ITW_IMAGE_BC7(slow)
+ITW_IMAGE_BC7(alpha_ultrafast) ITW_IMAGE_BC7(alpha_veryfast) ITW_IMAGE_BC7(alpha_fast) ITW_IMAGE_BC7(alpha_basic) ITW_IMAGE_BC7(alpha_slow)
+ITW_IMAGE_BC6H(veryfast) ITW_IMAGE_BC6H(fast) ITW_IMAGE_BC6H(basic) ITW_IMAGE_BC6H(slow) ITW_IMAGE_BC6H(veryslow)
+#undef ITW_IMAGE_BC7
+#undef ITW_IMAGE_BC6H
+
+int GetBytesPerBlock(int format)                          // win32Threads.cpp:192-209: everything but BC3/BC6H/BC7 is 8
+{
+    switch (format) {
+        case 77: case 78: case 98: case 99: case 95: case 96: return 16;
+        default: return 8;
+    }
+}
+bool CompressImageMT(const rgba_surface* input, uint8_t* output, CompressionFunc* cmpFunc, int compformat)
+{
+    (void)compformat;
+    if (!cmpFunc) { fail("CompressImageMT: null compression function"); return false; }
+    (*cmpFunc)(input, output);
+    return true;                                          // like the reference (win32Threads.cpp:248, :281); errors: itw_get_last_error()
+}
+bool CompressImageST(const rgba_surface* input, uint8_t* output, CompressionFunc* cmpFunc, int compformat)
+{
+    return CompressImageMT(input, output, cmpFunc, compformat);
+}
+// The reference's thread-pool life cycle (win32Threads.h:52-55) mapped onto the device pool: InitWin32Threads selects
+// every visible GPU, DestroyThreads returns to the single-device behaviour, GetProcessorCount reports the GPUs.
+int GetProcessorCount(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    return n > 0 ? n : 1;
+}
+void InitWin32Threads(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); fail("InitWin32Threads: no CUDA device"); return; }
+    std::vector<int> all((size_t)n);
+    for (int i = 0; i < n; i++) all[i] = i;
+    if (n >= 2) itw_set_devices(all.data(), n);
+}
+void DestroyThreads(void) { itw_set_devices(nullptr, 0); }
 
 const char* itw_get_last_error(void) { return tls.err.c_str(); }
 
@@ -674,6 +1027,7 @@ uint64_t itw_kernel_launch_count(void) { return g_launches.load(std::memory_orde
 float itw_last_kernel_ms(void)
 {
     float ms = -1.0f;
+    if (tls.pool_ms >= 0.0f) return tls.pool_ms;
     if (tls.timed && cudaEventElapsedTime(&ms, tls.ev0, tls.ev1) != cudaSuccess) { cudaGetLastError(); ms = -1.0f; }
     return ms;
 }
@@ -682,3 +1036,4 @@ float itw_last_kernel_ms(void)
 
 #include "itw_dds.inc"
 #include "itw_mips.inc"
+#include "itw_shard.inc"

@@ -68,6 +68,14 @@ def mixed_rgba8(h, w, seed=0xB2000004):
     return img
 
 
+def c5_tile(t, size=1024):
+    """C5 tile t: even t = the C2 generator with seed 0xB2000005 + t, odd t = the C1 gradient with a
+    per-tile phase."""
+    if t % 2 == 0:
+        return random_rgba8(size, size, seed=0xB2000005 + t)
+    return gradient_rgba8(size, size, phase=37 * t)
+
+
 def box_mip(img):
     """Next mip level: max(1, w>>1) x max(1, h>>1), 2x2 box filter with round-to-nearest ((a+b+c+d+2)>>2);
     a 1-texel-wide/high level degenerates to the 2-tap average; an odd trailing row/column is dropped (floor)."""

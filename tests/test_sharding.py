@@ -1,9 +1,11 @@
-"""Multi-GPU host logic on CPU: world_size-2 gloo processes, the oracle standing in for the kernels.
-The sharded result after the single all-gather must equal the single-process encode byte for byte."""
+"""Multi-GPU host logic.
+
+CPU (gloo, world size 2): the library's own shard plan (itw_shard_plan_make, pure arithmetic in csrc/itw_shard.inc)
+executed with the oracle standing in for the kernels -- the sharded result after the single all-gather must equal the
+single-process encode byte for byte.  GPU (-m gpu, 2+ GPUs): the real thing, itw_encode_mip_chain_sharded over NCCL."""
 import importlib
 import os
 import socket
-import sys
 
 import numpy as np
 import pytest
@@ -27,6 +29,32 @@ def test_band_rule_matches_reference_thread_split():
         assert all(bands[i][1] == bands[i + 1][0] for i in range(n - 1))
 
 
+def test_shardable_levels_rule():
+    assert [sharding.shardable_levels(8192, 14, n) for n in (1, 2, 4, 8)] == [12, 11, 10, 9]
+    assert sharding.shardable_levels(256, 9, 2) == 6 and sharding.shardable_levels(4, 3, 1) == 1
+
+
+def test_plan_layout_c4():
+    """itw_shard_plan_make for config C4 (8192^2 BC3, 14 levels, 8 ranks): the numbers of SURVEY.md 8e."""
+    lib = T.product()
+    plans = [sharding.make_plan(lib, "BC3", 8192, 8192, 14, 8, r) for r in range(8)]
+    p = plans[3]
+    assert p.band_levels == 9 and (p.band_y0, p.band_y1) == (3072, 4096)
+    assert p.chain_bytes == sum(((max(8192 >> l, 1) + 3) // 4) ** 2 * 16 for l in range(14))       # 64 MiB + 21.3 MiB
+    assert p.band_bytes[0] == 8 << 20 and p.level_bytes[0] == 64 << 20
+    assert p.texel_bytes == 32 * 4 * 4                                                              # level 8 is 32x32: 4 rows per rank
+    assert p.slot_bytes % 16 == 0 and p.slot_bytes >= sum(p.band_bytes[l] for l in range(9)) + p.texel_bytes
+    assert all(q.slot_bytes == p.slot_bytes and q.chain_bytes == p.chain_bytes for q in plans)
+    # the rule of sharding.shardable_levels is the library's
+    for h, levels, n in ((8192, 14, 1), (8192, 14, 2), (256, 9, 2), (64, 7, 4), (48, 6, 3)):
+        assert sharding.make_plan(lib, "BC1", 64, h, levels, n, 0).band_levels == sharding.shardable_levels(h, levels, n)
+    # errors are reported, not swallowed
+    with pytest.raises(RuntimeError, match="multiple of 4 rows"):
+        sharding.make_plan(lib, "BC3", 64, 40, 3, 4, 0)
+    with pytest.raises(RuntimeError, match="RGBA8"):
+        sharding.make_plan(lib, "BC6H", 64, 64, 3, 2, 0)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -35,82 +63,81 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, fmt, prof, ret):
+def _worker(rank, world, port, fmt, prof, shape, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        oracle = T.oracle()
+        oracle, lib = T.oracle(), T.product()               # the product library is only asked for the PLAN (no CUDA call)
         settings = oracle.profile(prof) if prof else None
-        base = T.synth.mixed_rgba8(64, 32)
-        chain = T.synth.mip_chain(base)                      # 7 levels, the small ones padded to 4x4
-        bpb = T.binding.FORMATS[fmt][1]
+        h, w = shape
+        base = T.synth.mixed_rgba8(h, w)
+        levels = max(h, w).bit_length()
 
-        def encode_band(li, y0, y1):
-            img = np.ascontiguousarray(chain[li][y0:y1])
-            return torch.from_numpy(oracle.encode(fmt, img, settings))
+        def encode(img):
+            return oracle.encode(fmt, img, settings)
 
-        got = sharding.encode_levels_sharded([(l.shape[1], l.shape[0]) for l in chain], bpb, encode_band)
-        want = [oracle.encode(fmt, np.ascontiguousarray(l), settings) for l in chain]
-        ok = all(np.array_equal(g.numpy(), w) for g, w in zip(got, want))
-        ret[rank] = bool(ok)
+        got, plan = sharding.run_plan_on_cpu(lib, fmt, base, levels, encode, T.synth.mip_chain)
+        want = np.concatenate([encode(np.ascontiguousarray(l)) for l in T.synth.mip_chain(base)])
+        ret[rank] = bool(np.array_equal(got, want)) and plan.band_levels < levels
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fmt,prof", [("BC3", None), ("BC7", "veryfast")])
-def test_row_sharded_mip_chain_equals_single_process(fmt, prof):
+@pytest.mark.parametrize("fmt,prof,shape", [("BC3", None, (64, 32)), ("BC7", "veryfast", (64, 32)), ("BC1", None, (256, 4)), ("BC3", None, (32, 20))],
+                         ids=["BC3-64x32", "BC7-64x32", "BC1-narrow", "BC3-npot-width"])
+def test_row_sharded_mip_chain_equals_single_process(fmt, prof, shape):
+    """World size 2 over gloo; the narrow / non-power-of-two widths cover the padded-width tail (a level whose stored
+    width is pad4(width) but whose valid width is smaller)."""
     world = 2
     ret = mp.get_context("spawn").Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), fmt, prof, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), fmt, prof, shape, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
 def _gpu_worker(rank, world, port, ret):
-    import importlib
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         lib = T.product()
         lib.set_device(rank)
-        fmt, bpb = "BC3", 16
-        chain = T.synth.mip_chain(T.synth.mixed_rgba8(256, 256))
-        dev = [torch.from_numpy(np.ascontiguousarray(l).reshape(-1)).cuda() for l in chain]
-
-        def encode_band(li, y0, y1):
-            h, w = chain[li].shape[:2]
-            out = torch.empty((w // 4) * ((y1 - y0) // 4) * bpb, dtype=torch.uint8, device="cuda")
-            lib.encode_device(fmt, dev[li].data_ptr() + y0 * w * 4, w, y1 - y0, w * 4, out.data_ptr(), None,
-                              torch.cuda.current_stream().cuda_stream)
-            return out
-
-        got = sharding.encode_levels_sharded([(l.shape[1], l.shape[0]) for l in chain], bpb, encode_band, device="cuda")
-        torch.cuda.synchronize()
-        want = [lib.encode(fmt, np.ascontiguousarray(l)) for l in chain]
-        ok = all(np.array_equal(g.cpu().numpy(), w) for g, w in zip(got, want))
-        # config C4 proper: level 0 row-sharded, mips made on the GPUs, one small texel gather + one block gather
-        base = T.synth.mixed_rgba8(256, 256, seed=3)
-        y0, y1 = sharding.band_rows(256, world, rank)
-        band = torch.from_numpy(np.ascontiguousarray(base[y0:y1]).reshape(-1)).cuda()
-        got2 = sharding.encode_mip_chain_sharded(lib, fmt, band, 256, 256, 9)
-        ref_chain = T.synth.mip_chain(base)
-        want2 = [lib.encode(fmt, np.ascontiguousarray(l)) for l in ref_chain]
-        ok = ok and len(got2) == 9 and all(np.array_equal(g.cpu().numpy(), w) for g, w in zip(got2, want2))
+        sharding.shard_init(lib)
+        ok = True
+        for fmt, prof, (h, w) in (("BC3", None, (256, 256)), ("BC1", None, (512, 8)), ("BC7", "veryfast", (128, 64)), ("BC3", None, (64, 20))):
+            settings = lib.profile(prof) if prof else None
+            levels = max(h, w).bit_length()
+            base = T.synth.mixed_rgba8(h, w, seed=3 + h)
+            y0, y1 = sharding.band_rows(h, world, rank)
+            band = torch.from_numpy(np.ascontiguousarray(base[y0:y1]).reshape(-1)).cuda()
+            chain, plan = sharding.encode_mip_chain_sharded(lib, fmt, band, w, h, levels, settings)
+            torch.cuda.synchronize()
+            want = np.concatenate([lib.encode(fmt, np.ascontiguousarray(l), settings) for l in T.synth.mip_chain(base)])
+            ok = ok and np.array_equal(chain.cpu().numpy(), want)
+        sharding.shard_finalize(lib)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
 
 
-def test_shardable_levels_rule():
-    assert [sharding.shardable_levels(8192, 14, n) for n in (1, 2, 4, 8)] == [12, 11, 10, 9]
-    assert sharding.shardable_levels(256, 9, 2) == 6 and sharding.shardable_levels(4, 3, 1) == 1
-
-
 @pytest.mark.gpu
 def test_row_sharded_mip_chain_on_two_gpus_nccl():
-    """Config C4 in small: BC3 + full mip chain, row-sharded over 2 GPUs, one NCCL all-gather."""
+    """Config C4 in small: full mip chains, level 0 row-sharded over 2 GPUs, ONE ncclAllGather issued by the library."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ret = mp.get_context("spawn").Manager().dict()
     mp.spawn(_gpu_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert all(ret.get(r) for r in range(2)), dict(ret)
+
+
+@pytest.mark.gpu
+def test_sharded_entry_on_one_gpu_equals_the_plain_chain():
+    """Without a communicator itw_encode_mip_chain_sharded is the single-GPU chain encode (bands = the whole image)."""
+    lib = T.product()
+    for fmt, (h, w) in (("BC3", (256, 128)), ("BC1", (64, 20)), ("BC5", (128, 128))):
+        base = T.synth.mixed_rgba8(h, w, seed=h)
+        levels = max(h, w).bit_length()
+        band = torch.from_numpy(base.reshape(-1)).cuda()
+        chain, plan = sharding.encode_mip_chain_sharded(lib, fmt, band, w, h, levels)
+        torch.cuda.synchronize()
+        want = np.concatenate([lib.encode(fmt, np.ascontiguousarray(l)) for l in T.synth.mip_chain(base)])
+        assert np.array_equal(chain.cpu().numpy(), want), fmt
