@@ -107,6 +107,8 @@ enum {
     ITW_FORMAT_BC4 = 80,  /* DXGI_FORMAT_BC4_UNORM  */
     ITW_FORMAT_BC5 = 83,  /* DXGI_FORMAT_BC5_UNORM  */
     ITW_FORMAT_BC6H = 95, /* DXGI_FORMAT_BC6H_UF16  */
+    ITW_FORMAT_BC6H_SF16 = 96, /* DXGI_FORMAT_BC6H_SF16: ENCODED by the same unsigned encoder, as the plug-in does
+                                  (IntelPlugin.cpp:840-843); DECODED with the signed rules (DirectXTexCompress.cpp:414) */
     ITW_FORMAT_BC7 = 98   /* DXGI_FORMAT_BC7_UNORM  */
 };
 
@@ -271,7 +273,7 @@ size_t itw_dds_encode_texture(const itw_dds_desc* desc, const rgba_surface* tops
  * D3DXDecodeBC1/3/4U/5U/6HU/7, BC.cpp:897, BC4BC5.cpp:369-400, BC6HBC7.cpp:2879-2900).
  * `blocks` holds (width/4)*(height/4) blocks in raster order; dst->ptr is WRITTEN: RGBA8 texels
  * (4 B) for BC1/BC3/BC4/BC5/BC7 (BC4: r,0,0,255; BC5: r,g,0,255), RGBA16F texels (8 B, half bit
- * patterns, alpha = 1.0) for BC6H_UF16.  width/height multiples of 4; either side may be host or
+ * patterns, alpha = 1.0) for BC6H_UF16 / BC6H_SF16 (signed decode: D3DXDecodeBC6HS).  width/height multiples of 4; either side may be host or
  * device memory; synchronous.  BC7 and BC6H are exact by the format definition; BC1-BC5 equal
  * DirectXTex's float decoders rounded to nearest (csrc/decode.cuh).  Returns 0 on success.
  * ------------------------------------------------------------------------------------------- */

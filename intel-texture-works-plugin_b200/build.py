@@ -38,10 +38,12 @@ def build(force=False, verbose=True, extra=()):
         if all(os.path.getmtime(d) <= t for d in deps()):
             return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + sources() + ["-o", OUT]
+    tmp = OUT + ".tmp"                     # written aside and renamed: a snapshot of the tree never sees a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + sources() + ["-o", tmp]
     if verbose:
         print("[build]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)
     return OUT
 
 

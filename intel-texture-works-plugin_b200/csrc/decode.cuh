@@ -253,6 +253,23 @@ ITW_HD u32 bc6_mode_delta_bits(int mode)
 // reserved mode fields (decoded as opaque black, BC6HBC7.cpp:1088-1106).  The twelve endpoint fields are gathered
 // into three 64-bit registers (per channel: endpoints 0..3, 16 bits each) -- no per-thread arrays, hence no local
 // memory (the array version wrote 349 MB of spills to DRAM for a 128 MB surface, profiles/r1_final2_decode_ncu.txt).
+//
+// kSigned = BC6H_SF16 (D3DXDecodeBC6HS = D3DX_BC6H::Decode(true, ...), what DirectX::Decompress runs for DXGI_FORMAT_BC6H_SF16,
+// DirectXTexCompress.cpp:414): every endpoint is sign-extended at the mode's endpoint width (BC6HBC7.cpp:1141-1157, :582-594),
+// un-quantised symmetrically (:1318-1336), the interpolated value is scaled by 31/32 on its magnitude (:1351-1354) and leaves
+// as sign | magnitude half bits (BC.h INT2F16).
+ITW_HD int bc6_dequant_signed(int v, int bits)                         // BC6HBC7.cpp:1318-1336
+{
+    if (bits >= 16) return v;
+    const bool neg = v < 0;
+    if (neg) v = -v;
+    int unq;
+    if (v == 0) unq = 0;
+    else if (v >= ((1 << (bits - 1)) - 1)) unq = 0x7FFF;
+    else unq = ((v << 15) + 0x4000) >> (bits - 1);
+    return neg ? -unq : unq;
+}
+template <bool kSigned>
 ITW_HD bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
 {
     const u32 m2 = w[0] & 3u;
@@ -291,13 +308,13 @@ ITW_HD bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
     const int epb = bc6_mode_epb(mode);
     const u32 dbits = bc6_mode_delta_bits(mode);
     const u32 mask = (1u << epb) - 1u;
-    u32 lo[2][3], hi[2][3];                                  // decoded endpoints A, B per subset and channel
+    int lo[2][3], hi[2][3];                                  // decoded endpoints A, B per subset and channel
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const unsigned long long chv = (c == 0) ? ch0 : ((c == 1) ? ch1 : ch2);
         const u32 base = (u32)chv & 0xFFFFu;
         const int nb = (int)((dbits >> (4 * c)) & 15u);
-        u32 ep[4];
+        int ep[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             u32 v = (u32)(chv >> (16 * i)) & 0xFFFFu;
@@ -305,7 +322,11 @@ ITW_HD bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
                 if (v & (1u << (nb - 1))) v -= 1u << nb;     // sign-extend the delta (wraps, masked below)
                 v = (base + v) & mask;
             }
-            ep[i] = (u32)bc6_dequant((int)v, epb);
+            if (kSigned) {
+                int sv = (int)v;
+                if (epb < 32 && (v & (1u << (epb - 1)))) sv -= 1 << epb;      // SIGN_EXTEND at the endpoint width
+                ep[i] = bc6_dequant_signed(sv, epb);
+            } else ep[i] = bc6_dequant((int)v, epb);
         }
         lo[0][c] = ep[0]; hi[0][c] = ep[1]; lo[1][c] = ep[2]; hi[1][c] = ep[3];
     }
@@ -322,8 +343,12 @@ ITW_HD bool decode_bc6h(u32 (&px)[16][2], const u32 (&w)[4])
         u32 h[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const int a = (int)(second ? lo[1][c] : lo[0][c]), bb = (int)(second ? hi[1][c] : hi[0][c]);
-            h[c] = (u32)(((((64 - wt) * a + wt * bb + 32) >> 6) * 31) >> 6);
+            const int a = second ? lo[1][c] : lo[0][c], bb = second ? hi[1][c] : hi[0][c];
+            const int v = ((64 - wt) * a + wt * bb + 32) >> 6;           // arithmetic shift of a possibly negative value, as in C++ on x86
+            if (kSigned) {
+                const int m = (v < 0) ? -(((-v) * 31) >> 5) : ((v * 31) >> 5);
+                h[c] = (m < 0) ? (0x8000u | (u32)(-m)) : (u32)m;
+            } else h[c] = (u32)((v * 31) >> 6);
         }
         px[k][0] = h[0] | (h[1] << 16);
         px[k][1] = h[2] | 0x3C000000u;
@@ -375,9 +400,9 @@ __global__ void __launch_bounds__(128) decode_kernel(const uint8_t* __restrict__
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(blocks) + id);
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     }
-    if (kFormat == 95) {
+    if (kFormat == 95 || kFormat == 96) {
         u32 px[16][2];
-        decode_bc6h(px, w);
+        decode_bc6h<kFormat == 96>(px, w);
         uint8_t* row = dst + (long long)(4 * by) * stride + (long long)bx * 32;
         const bool wide = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)stride) & 31u) == 0;
 #pragma unroll

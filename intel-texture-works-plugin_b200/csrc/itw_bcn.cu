@@ -22,6 +22,7 @@
 
 #include "../../include/itw_bcn.h"
 #include "bc4_bc5.cuh"
+#include "bc1_pair.cuh"
 #include "mips.cuh"
 #include "decode.cuh"
 #include "frontend.cuh"
@@ -151,7 +152,7 @@ bool format_info(int format, FormatInfo& f)
     switch (format) {
         case ITW_FORMAT_BC1: case ITW_FORMAT_BC4: f = {8, 4}; return true;
         case ITW_FORMAT_BC3: case ITW_FORMAT_BC5: case ITW_FORMAT_BC7: f = {16, 4}; return true;
-        case ITW_FORMAT_BC6H: f = {16, 8}; return true;
+        case ITW_FORMAT_BC6H: case ITW_FORMAT_BC6H_SF16: f = {16, 8}; return true;
         default: return false;
     }
 }
@@ -171,18 +172,27 @@ int check_surface(const rgba_surface* s, const FormatInfo& f)
 // Enqueue the kernel for one device-resident surface on `stream`.
 int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* settings, cudaStream_t stream)
 {
+    if (format == ITW_FORMAT_BC6H_SF16) format = ITW_FORMAT_BC6H;     // the plug-in encodes SF16 with the unsigned encoder (IntelPlugin.cpp:840-843)
     const long long nblocks = (long long)(v.width >> 2) * (v.height >> 2);
     const bool vec16 = ((reinterpret_cast<uintptr_t>(v.ptr) | (uintptr_t)v.stride) & 15u) == 0;
     const unsigned grid1 = (unsigned)((nblocks + 127) / 128);
     switch (format) {
         case ITW_FORMAT_BC1:
-            if (vec16) bc1_bc3_kernel<false, true><<<grid1, 128, 0, stream>>>(v, d_dst);
-            else       bc1_bc3_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+        case ITW_FORMAT_BC3: {
+            // 16-byte aligned rows: the persistent TMA-staged kernel, two blocks per thread on packed float lanes (bc1_pair.cuh);
+            // anything else: one block per thread with byte-safe loads (bc1_bc3.cuh)
+            const long long tiles = (nblocks + kBc1TileBlocks - 1) / kBc1TileBlocks;
+            const long long cap = (long long)tls.sm_count * kBc1CtasPerSm;
+            const unsigned gridp = (unsigned)(tiles < cap ? tiles : cap);
+            if (format == ITW_FORMAT_BC1) {
+                if (vec16) bc1_bc3_pair_kernel<false><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks);
+                else       bc1_bc3_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+            } else {
+                if (vec16) bc1_bc3_pair_kernel<true><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks);
+                else       bc1_bc3_kernel<true, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+            }
             break;
-        case ITW_FORMAT_BC3:
-            if (vec16) bc1_bc3_kernel<true, true><<<grid1, 128, 0, stream>>>(v, d_dst);
-            else       bc1_bc3_kernel<true, false><<<grid1, 128, 0, stream>>>(v, d_dst);
-            break;
+        }
         case ITW_FORMAT_BC4:
             if (vec16) bc4_bc5_kernel<false, true><<<grid1, 128, 0, stream>>>(v, d_dst);
             else       bc4_bc5_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
@@ -514,6 +524,7 @@ int encode_any(int format, const rgba_surface* src, uint8_t* dst, const void* se
 {
     tls.err.clear();
     tls.pool_ms = -1.0f;
+    if (format == ITW_FORMAT_BC6H_SF16) format = ITW_FORMAT_BC6H;      // one encoder for both (IntelPlugin.cpp:840-843)
     FormatInfo f;
     if (!format_info(format, f)) return fail("unknown format");
     const int chk = check_surface(src, f);
@@ -546,6 +557,7 @@ int launch_decode(int format, const uint8_t* d_blocks, uint8_t* d_dst, int w, in
         case ITW_FORMAT_BC4: launch_decode_as<ITW_FORMAT_BC4>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
         case ITW_FORMAT_BC5: launch_decode_as<ITW_FORMAT_BC5>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
         case ITW_FORMAT_BC6H: launch_decode_as<ITW_FORMAT_BC6H>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
+        case ITW_FORMAT_BC6H_SF16: launch_decode_as<ITW_FORMAT_BC6H_SF16>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
         case ITW_FORMAT_BC7: launch_decode_as<ITW_FORMAT_BC7>(vec16, grid, s, d_blocks, d_dst, w, h, stride); break;
         default: return fail("unknown format");
     }
@@ -607,7 +619,7 @@ int front_params(FrontParams& P, int format, const itw_pixel_source* src, uint32
     const long long row_bytes = src->row_bytes ? src->row_bytes : tight;
     if (row_bytes < tight) return fail("pixel source: row_bytes smaller than a texel row");
     if ((reinterpret_cast<uintptr_t>(src->data) | (uintptr_t)row_bytes) & (uintptr_t)(esize - 1)) return fail("pixel source: misaligned elements");
-    const int family = (format == ITW_FORMAT_BC6H) ? 2 : ((format == ITW_FORMAT_BC4 || format == ITW_FORMAT_BC5) ? 1 : 0);
+    const int family = (format == ITW_FORMAT_BC6H || format == ITW_FORMAT_BC6H_SF16) ? 2 : ((format == ITW_FORMAT_BC4 || format == ITW_FORMAT_BC5) ? 1 : 0);
     if (flags & ITW_FRONT_HAS_ALPHA) {
         // the converters read plane 3 (IntelPlugin.cpp:310, :758 ...); the 32-bit HDR one reads plane 2 (:361)
         const int need = (family == 2 && src->depth == 32) ? 3 : 4;

@@ -8,6 +8,7 @@
 // is loaded only by tests.  The product library never contains or calls this code.
 #include <cstring>
 #include "../../intel-texture-works-plugin_b200/csrc/bc4_bc5.cuh"
+#include "../../intel-texture-works-plugin_b200/csrc/bc1_pair.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/itw_params.h"
 #include "../../intel-texture-works-plugin_b200/csrc/mips.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/decode.cuh"
@@ -41,9 +42,9 @@ static void emu_decode_as(const uint8_t* blocks, uint8_t* dst, int w, int h, int
         for (int bx = 0; bx < bw; bx++) {
             u32 wd[4] = {0, 0, 0, 0};
             memcpy(wd, blocks + ((size_t)by * bw + bx) * bpb, bpb);
-            if (kFormat == 95) {
+            if (kFormat == 95 || kFormat == 96) {
                 u32 px[16][2];
-                decode_bc6h(px, wd);
+                decode_bc6h<kFormat == 96>(px, wd);
                 for (int k = 0; k < 16; k++) memcpy(dst + (size_t)(4 * by + k / 4) * stride + (size_t)(4 * bx + k % 4) * 8, px[k], 8);
             } else {
                 u32 px[16];
@@ -53,7 +54,27 @@ static void emu_decode_as(const uint8_t* blocks, uint8_t* dst, int w, int h, int
         }
 }
 
+// the two-blocks-per-thread form (csrc/bc1_pair.cuh): consecutive blocks are paired as lanes x / y, an odd last block pairs with itself
+template <bool kAlpha>
+static void per_block_pair(const rgba_surface* src, uint8_t* dst, int bpb)
+{
+    SurfaceView s = view_of(src);
+    const int bw = s.width / 4, bh = s.height / 4;
+    const long long n = (long long)bw * bh;
+    for (long long id = 0; id < n; id += 2) {
+        const long long idb = (id + 1 < n) ? id + 1 : id;
+        u32 ta[16], tb[16], oa[4], ob[4];
+        fetch_rows_rgba8<false>(ta, s, (int)(id % bw), (int)(id / bw));
+        fetch_rows_rgba8<false>(tb, s, (int)(idb % bw), (int)(idb / bw));
+        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob);
+        memcpy(dst + (size_t)id * bpb, oa, bpb);
+        memcpy(dst + (size_t)idb * bpb, ob, bpb);
+    }
+}
+
 extern "C" {
+void emu_pair_CompressBlocksBC1(const rgba_surface* src, uint8_t* dst) { per_block_pair<false>(src, dst, 8); }
+void emu_pair_CompressBlocksBC3(const rgba_surface* src, uint8_t* dst) { per_block_pair<true>(src, dst, 16); }
 void emu_CompressBlocksBC1(const rgba_surface* src, uint8_t* dst)
 { per_block(src, dst, 8, [](const u32 (&t)[16], u32 (&o)[4]) { bc1_bc3_encode_block<false>(t, o); }); }
 void emu_CompressBlocksBC3(const rgba_surface* src, uint8_t* dst)
@@ -103,6 +124,7 @@ int emu_itw_decode(int format, const uint8_t* blocks, const rgba_surface* dst)
         case 80: emu_decode_as<80>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 8); return 0;
         case 83: emu_decode_as<83>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
         case 95: emu_decode_as<95>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
+        case 96: emu_decode_as<96>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
         case 98: emu_decode_as<98>(blocks, dst->ptr, dst->width, dst->height, dst->stride, 16); return 0;
         default: return -1;
     }
