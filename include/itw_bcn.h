@@ -238,10 +238,25 @@ size_t itw_dds_encode_file(const itw_dds_desc* desc, const rgba_surface* images,
                            uint8_t* file, size_t capacity);
 
 /* ---------------------------------------------------------------------------------------------
- * Section 4 -- on-GPU pre-pass: mip chain + pad-to-4, RGBA8 only.
- * Level l has max(1,w>>l) x max(1,h>>l) texels, filtered from level l-1 with the 2x2 box
- * (a+b+c+d+2)>>2, and is STORED padded to multiples of 4 by edge replication
+ * Section 4 -- on-GPU pre-pass: mip chain + pad-to-4.
+ * Level l has max(1,w>>l) x max(1,h>>l) texels and is STORED padded to multiples of 4 by edge replication
  * (IntelPlugin.cpp:893-928), rows tightly packed -- ready to be handed to CompressBlocks*.
+ * Filters = DirectXTex's own (non-WIC) generators, which are in the reference tree (DirectXTexMipmaps.cpp:715-905,
+ * Filters.h:33-112): the BOX filter ((p0+p1)+p2+p3)*0.25 when width and height of level 0 are powers of two, the two-tap
+ * LINEAR filter otherwise (GenerateMipMaps' default choice, :2611-2616), every level re-read from the stored previous one.
+ *   itw_generate_mips_device       RGBA8 as R8G8B8A8_UNORM.  For exact 2:1 levels the float box on byte/255 values stored
+ *                                  with round-to-nearest equals the integer (a+b+c+d+2)>>2, which is what runs there.
+ *                                  (The plug-in's default for UNORM encodings is the WIC scaler, which is NOT in the tree:
+ *                                  parity with WIC is unpinned; this is DirectXTex's TEX_FILTER_FORCE_NON_WIC result.)
+ *   itw_generate_mips_device_srgb  RGBA8 as R8G8B8A8_UNORM_SRGB: filtered in linear light (XMColorSRGBToRGB after the load,
+ *                                  XMColorRGBToSRGB before the store, DirectXTexConvert.cpp:2669-2685, :2757-2775) -- what the
+ *                                  plug-in gets for BC1/BC3/BC7 *_SRGB encodings (IntelPlugin.cpp:152-154; WIC is bypassed for
+ *                                  sRGB formats, DirectXTexMipmaps.cpp:389-393).  itw_dds_encode_texture / _pixels use it for
+ *                                  dxgi_format 72 / 78 / 99.
+ *   itw_generate_mips_device_f16   RGBA16F, the BC6H save path (TEX_FILTER_FORCE_NON_WIC, IntelPlugin.cpp:2117-2127).
+ * Bit-exact to those generator bodies (cut and compiled by oracle/build_ref_frontend.py), including their stale fourth tap
+ * on wide power-of-two textures (csrc/mips_f16.cuh).  Outside the tree and therefore assumed: XMLoadUByteN4 = byte*(1/255),
+ * XMStoreUByteN4 = round to nearest, the half conversions of DirectXMath 3.06, the C library's powf.
  * ------------------------------------------------------------------------------------------- */
 /* Bytes of device scratch for the padded levels first_level..levels-1 of a w x h RGBA8 texture. */
 size_t itw_mip_scratch_bytes(int width, int height, int levels, int first_level);
@@ -251,13 +266,9 @@ size_t itw_mip_scratch_bytes(int width, int height, int levels, int first_level)
  * level l (out[0] = *level0 when no padding is needed).  Enqueued on `cuda_stream`; returns 0 on success. */
 int itw_generate_mips_device(const rgba_surface* level0, int levels, rgba_surface* out, uint8_t* scratch,
                              void* cuda_stream);
-/* RGBA16F chain for BC6H textures.  For BC6H the plug-in forces DirectXTex's own (non-WIC) generator
- * (IntelPlugin.cpp:2117-2127), which IS in the reference tree: box filter ((p0+p1)+p2+p3)*0.25 in float
- * when width and height are powers of two, the two-tap linear filter otherwise
- * (DirectXTex/DirectXTexMipmaps.cpp:715-905, Filters.h:33-112), each level re-read from its stored halves.
- * Same conventions as itw_generate_mips_device with 8-byte texels; scratch needs TWICE
- * itw_mip_scratch_bytes(...).  Bit-exact to that code including its stale fourth tap on wide textures
- * (csrc/mips_f16.cuh); half conversions as in section 6. */
+/* Same arguments, sRGB-correct RGBA8 chain / RGBA16F chain (8-byte texels: scratch needs TWICE itw_mip_scratch_bytes(...)). */
+int itw_generate_mips_device_srgb(const rgba_surface* level0, int levels, rgba_surface* out, uint8_t* scratch,
+                                  void* cuda_stream);
 int itw_generate_mips_device_f16(const rgba_surface* level0, int levels, rgba_surface* out, uint8_t* scratch,
                                  void* cuda_stream);
 /* The complete save path of one texture (IntelPlugin.cpp:2117-2171): `tops` = array_size HOST or

@@ -47,7 +47,7 @@ EXPORTS = (["CompressBlocksBC1", "CompressBlocksBC3", "CompressBlocksBC4", "Comp
             "itw_last_kernel_ms", "itw_dds_header_bytes", "itw_dds_image_bytes", "itw_dds_image_offset",
             "itw_dds_file_bytes", "itw_dds_write_header", "itw_dds_read_header", "itw_dds_encode_file",
             "itw_mip_scratch_bytes", "itw_generate_mips_device", "itw_dds_encode_texture", "itw_decode", "itw_convert_pixels", "itw_encode_pixels",
-            "itw_generate_mips_device_f16", "itw_dds_encode_pixels", "itw_release", "itw_set_devices", "itw_get_devices",
+            "itw_generate_mips_device_f16", "itw_generate_mips_device_srgb", "itw_dds_encode_pixels", "itw_release", "itw_set_devices", "itw_get_devices",
             "itw_begin_deferred", "itw_flush", "GetProcessorCount", "InitWin32Threads", "DestroyThreads", "GetBytesPerBlock",
             "CompressImageMT", "CompressImageST", "CompressImageBC1", "CompressImageBC3",
             "itw_shard_plan_make", "itw_shard_unique_id", "itw_shard_init", "itw_shard_finalize", "itw_encode_mip_chain_sharded"]

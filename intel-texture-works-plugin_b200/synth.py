@@ -77,7 +77,9 @@ def c5_tile(t, size=1024):
 
 
 def box_mip(img):
-    """Next mip level: max(1, w>>1) x max(1, h>>1), 2x2 box filter with round-to-nearest ((a+b+c+d+2)>>2);
+    """Next mip level of a SQUARE POWER-OF-TWO texture (config C4): the integer form (a+b+c+d+2)>>2 of DirectXTex's box filter, which
+    is what the library runs on exact 2:1 levels (include/itw_bcn.h section 4; other shapes follow DirectXTex's linear filter / its
+    one-texel-high quirk, see tests/itw_testlib.oracle_mip_chain_rgba8).  max(1, w>>1) x max(1, h>>1);
     a 1-texel-wide/high level degenerates to the 2-tap average; an odd trailing row/column is dropped (floor)."""
     h, w = img.shape[:2]
     a = img.astype(np.uint16)

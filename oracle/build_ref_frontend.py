@@ -62,6 +62,7 @@ PLUGIN_H = os.path.join(REF_ROOT, "IntelCompressionPlugin", "IntelPlugin.h")
 PLUGIN_CPP = os.path.join(REF_ROOT, "IntelCompressionPlugin", "IntelPlugin.cpp")
 MIPMAPS_CPP = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "DirectXTexMipmaps.cpp")
 FILTERS_H = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "Filters.h")
+CONVERT_CPP = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "DirectXTexConvert.cpp")
 BC45_CPP = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "BC4BC5.cpp")
 BC_H = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "BC.h")
 BC_CPP = os.path.join(REF_ROOT, "3rdParty", "DirectXTex", "DirectXTex", "BC.cpp")
@@ -84,7 +85,7 @@ typedef unsigned char unsigned8;
 typedef unsigned short unsigned16;
 typedef uint8_t uint8;
 typedef uint16_t uint16;
-enum DXGI_FORMAT { DXGI_FORMAT_R16G16B16A16_FLOAT = 10, DXGI_FORMAT_R8G8B8A8_UNORM = 28, DXGI_FORMAT_BC6H_UF16 = 95 };
+enum DXGI_FORMAT { DXGI_FORMAT_R16G16B16A16_FLOAT = 10, DXGI_FORMAT_R8G8B8A8_UNORM = 28, DXGI_FORMAT_R8G8B8A8_UNORM_SRGB = 29, DXGI_FORMAT_BC6H_UF16 = 95 };
 struct rgba_surface { uint8_t* ptr; int32_t width, height, stride; };
 namespace DirectX {
 struct Image { size_t width, height; DXGI_FORMAT format; size_t rowPitch, slicePitch; uint8_t* pixels; };
@@ -244,19 +245,61 @@ struct MipChain {                      // stands in for DirectX::ScratchImage in
     const Image* GetImage(size_t level, size_t, size_t) const { return &images[level]; }
 };
 #define ScratchImage MipChain
-// R16G16B16A16_FLOAT scanlines: XMLoadHalf4 / XMStoreHalf4 in the reference (DirectXTexConvert.cpp _LoadScanline / _StoreScanline)
-static bool _LoadScanlineLinear(XMVECTOR* d, size_t count, LPCVOID src, size_t, DXGI_FORMAT, DWORD)
+// ---- what XMColorSRGBToRGB / XMColorRGBToSRGB (cut from DirectXTexConvert.cpp below) need from DirectXMath ----
+typedef const XMVECTOR FXMVECTOR;
+struct XMVECTORU32 { uint32_t u[4]; };
+static const XMVECTORU32 g_XMSelect1110 = {{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u}};
+static inline float xm_mask(bool on) { uint32_t u = on ? 0xFFFFFFFFu : 0u; float f; memcpy(&f, &u, 4); return f; }
+static inline bool xm_on(float f) { uint32_t u; memcpy(&u, &f, 4); return u != 0; }
+inline XMVECTOR XMVectorSaturate(XMVECTOR v) { XMVECTOR r; for (int i = 0; i < 4; i++) { float x = v.f[i]; x = (x > 0.0f) ? x : 0.0f; r.f[i] = (x < 1.0f) ? x : 1.0f; } return r; }
+inline XMVECTOR XMVectorPow(XMVECTOR a, XMVECTOR b) { XMVECTOR r; for (int i = 0; i < 4; i++) r.f[i] = powf(a.f[i], b.f[i]); return r; }   // DirectXMath: powf per component
+inline XMVECTOR XMVectorGreater(XMVECTOR a, XMVECTOR b) { XMVECTOR r; for (int i = 0; i < 4; i++) r.f[i] = xm_mask(a.f[i] > b.f[i]); return r; }
+inline XMVECTOR XMVectorLess(XMVECTOR a, XMVECTOR b) { XMVECTOR r; for (int i = 0; i < 4; i++) r.f[i] = xm_mask(a.f[i] < b.f[i]); return r; }
+inline XMVECTOR XMVectorSelect(XMVECTOR a, XMVECTOR b, XMVECTOR c) { XMVECTOR r; for (int i = 0; i < 4; i++) r.f[i] = xm_on(c.f[i]) ? b.f[i] : a.f[i]; return r; }   // all-or-nothing masks only
+inline XMVECTOR XMVectorSelect(XMVECTOR a, XMVECTOR b, const XMVECTORU32& c) { XMVECTOR r; for (int i = 0; i < 4; i++) r.f[i] = c.u[i] ? b.f[i] : a.f[i]; return r; }
+inline XMVECTOR operator*(XMVECTOR a, XMVECTOR b) { return XMVectorMultiply(a, b); }
+inline XMVECTOR operator-(XMVECTOR a, XMVECTOR b) { return XMVECTOR{{a.f[0] - b.f[0], a.f[1] - b.f[1], a.f[2] - b.f[2], a.f[3] - b.f[3]}}; }
+//@SRGB_FUNCTIONS@
+enum { TEX_FILTER_SRGB_IN = 0x1000000, TEX_FILTER_SRGB_OUT = 0x2000000, TEX_FILTER_SRGB = 0x3000000 };
+// Scanline load / store (DirectXTexConvert.cpp:2688-2830).  The format dispatch is restated; the per-format conversions are
+//   R16G16B16A16_FLOAT  XMLoadHalf4 / XMStoreHalf4            (restated above)
+//   R8G8B8A8_UNORM      XMLoadUByteN4: byte * (1/255)         (rule F7: DirectXMath, not in the tree)
+//                       XMStoreUByteN4: saturate, * 255, round to nearest (x + 0.5 truncated) -- the store rounding of this
+//                       DirectXMath version is outside the tree: ASSUMED, as for the decoders (tests/test_decode.py)
+//   ..._UNORM_SRGB      the same bytes with XMColorSRGBToRGB after the load and XMColorRGBToSRGB before the store -- the
+//                       reference's own definitions (DirectXTexConvert.cpp:2669-2685, :2757-2775), cut above
+static inline float unorm8_load(uint8_t b) { return (float)b * (1.0f / 255.0f); }
+static inline uint8_t unorm8_store(float v) { v = (v > 0.0f) ? v : 0.0f; v = (v < 1.0f) ? v : 1.0f; return (uint8_t)(int)(v * 255.0f + 0.5f); }
+static bool _LoadScanlineLinear(XMVECTOR* d, size_t count, LPCVOID src, size_t, DXGI_FORMAT format, DWORD flags)
 {
-    const unsigned short* s = static_cast<const unsigned short*>(src);
-    for (size_t i = 0; i < count; i++)
-        for (int c = 0; c < 4; c++) d[i].f[c] = PackedVector::XMConvertHalfToFloat(s[4 * i + c]);
+    if (format == DXGI_FORMAT_R16G16B16A16_FLOAT) {
+        const unsigned short* s = static_cast<const unsigned short*>(src);
+        for (size_t i = 0; i < count; i++)
+            for (int c = 0; c < 4; c++) d[i].f[c] = PackedVector::XMConvertHalfToFloat(s[4 * i + c]);
+        return true;
+    }
+    if (format == DXGI_FORMAT_R8G8B8A8_UNORM_SRGB) flags |= TEX_FILTER_SRGB;
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    for (size_t i = 0; i < count; i++) {
+        for (int c = 0; c < 4; c++) d[i].f[c] = unorm8_load(s[4 * i + c]);
+        if (flags & TEX_FILTER_SRGB_IN) d[i] = XMColorSRGBToRGB(d[i]);
+    }
     return true;
 }
-static bool _StoreScanlineLinear(LPVOID dst, size_t, DXGI_FORMAT, XMVECTOR* s, size_t count, DWORD)
+static bool _StoreScanlineLinear(LPVOID dst, size_t, DXGI_FORMAT format, XMVECTOR* s, size_t count, DWORD flags)
 {
-    unsigned short* d = static_cast<unsigned short*>(dst);
-    for (size_t i = 0; i < count; i++)
-        for (int c = 0; c < 4; c++) d[4 * i + c] = PackedVector::XMConvertFloatToHalf(s[i].f[c]);
+    if (format == DXGI_FORMAT_R16G16B16A16_FLOAT) {
+        unsigned short* d = static_cast<unsigned short*>(dst);
+        for (size_t i = 0; i < count; i++)
+            for (int c = 0; c < 4; c++) d[4 * i + c] = PackedVector::XMConvertFloatToHalf(s[i].f[c]);
+        return true;
+    }
+    if (format == DXGI_FORMAT_R8G8B8A8_UNORM_SRGB) flags |= TEX_FILTER_SRGB;
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    for (size_t i = 0; i < count; i++) {
+        if (flags & TEX_FILTER_SRGB_OUT) s[i] = XMColorRGBToSRGB(s[i]);
+        for (int c = 0; c < 4; c++) d[4 * i + c] = unorm8_store(s[i].f[c]);
+    }
     return true;
 }
 inline static bool ispow2(size_t x) { return ((x != 0) && !(x & (x - 1))); }
@@ -281,6 +324,29 @@ extern "C" int ref_mip_chain_f16(const unsigned short* level0, int w, int h, int
     const bool box = ispow2((size_t)w) && ispow2((size_t)h);
     return (int)(box ? _Generate2DMipsBoxFilter((size_t)levels, 0, chain, 0) : _Generate2DMipsLinearFilter((size_t)levels, 0, chain, 0));
 }
+// RGBA8 chain through the SAME two generators: srgb = 0 -> R8G8B8A8_UNORM, 1 -> R8G8B8A8_UNORM_SRGB (what the plug-in's scratch
+// image is for *_SRGB encodings, IntelPlugin.cpp:152-154; _UseWICFiltering then returns false, DirectXTexMipmaps.cpp:389-393)
+extern "C" int ref_mip_chain_rgba8(const uint8_t* level0, int w, int h, int levels, int srgb, uint8_t* out)
+{
+    MipChain chain;
+    chain.meta = MipMeta{(size_t)w, (size_t)h};
+    const DXGI_FORMAT fmt = srgb ? DXGI_FORMAT_R8G8B8A8_UNORM_SRGB : DXGI_FORMAT_R8G8B8A8_UNORM;
+    size_t off = 0;
+    for (int l = 0; l < levels; l++) {
+        const size_t lw = (w >> l) ? (w >> l) : 1, lh = (h >> l) ? (h >> l) : 1;
+        chain.images.push_back(Image{lw, lh, fmt, lw * 4, lw * lh * 4, out + off});
+        off += lw * lh * 4;
+    }
+    memcpy(out, level0, (size_t)w * h * 4);
+    if (levels < 2) return 0;
+    const bool box = ispow2((size_t)w) && ispow2((size_t)h);
+    return (int)(box ? _Generate2DMipsBoxFilter((size_t)levels, 0, chain, 0) : _Generate2DMipsLinearFilter((size_t)levels, 0, chain, 0));
+}
+// the scalar pieces, for the table generator (tools/gen_srgb_tables.py) and the tests
+extern "C" float ref_srgb_to_linear(float v) { return XMColorSRGBToRGB(XMVECTOR{{v, v, v, v}}).f[0]; }
+extern "C" int ref_linear_to_srgb8(float v) { return unorm8_store(XMColorRGBToSRGB(XMVECTOR{{v, v, v, v}}).f[0]); }
+extern "C" float ref_unorm8_load(int b) { return unorm8_load((uint8_t)b); }
+extern "C" int ref_unorm8_store(float v) { return unorm8_store(v); }
 """
 
 
@@ -338,15 +404,9 @@ BC13_SHIM_TOP = r"""
 // ---- DirectXTex BC1 / BC3 decoders: shim -----------------------------------------------------------------
 #define _In_
 struct XMU565 { uint16_t v; };
-struct XMVECTORU32 { uint32_t u[4]; };
-static const XMVECTORF32 g_XMIdentityR3 = {0.0f, 0.0f, 0.0f, 1.0f};
-static const XMVECTORU32 g_XMSelect1110 = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u};
+static const XMVECTORF32 g_XMIdentityR3 = {0.0f, 0.0f, 0.0f, 1.0f};      // XMVECTORU32 / g_XMSelect1110 / XMVectorSelect: the mip shim above
 inline XMVECTOR XMLoadU565(const XMU565* p) { return XMVECTOR{{(float)(p->v & 31), (float)((p->v >> 5) & 63), (float)((p->v >> 11) & 31), 0.0f}}; }
 template <int A, int B, int C, int D> inline XMVECTOR XMVectorSwizzle(XMVECTOR v) { return XMVECTOR{{v.f[A], v.f[B], v.f[C], v.f[D]}}; }
-inline XMVECTOR XMVectorSelect(XMVECTOR a, XMVECTOR b, const XMVECTORU32& c)
-{
-    return XMVECTOR{{c.u[0] ? b.f[0] : a.f[0], c.u[1] ? b.f[1] : a.f[1], c.u[2] ? b.f[2] : a.f[2], c.u[3] ? b.f[3] : a.f[3]}};
-}
 inline XMVECTOR XMVectorLerp(XMVECTOR v0, XMVECTOR v1, float t)          // DirectXMath: Length = V1 - V0; Length * t + V0 (mul, add)
 {
     XMVECTOR r;
@@ -386,6 +446,18 @@ def cut_bc13(cpp, bch):
             raise RuntimeError(pat + " not found in BC.cpp")
         out.append(cut_function(cpp, m.start()))
     return "\n\n".join(out)
+
+
+def cut_srgb(conv):
+    """XMColorRGBToSRGB / XMColorSRGBToRGB as DirectXTexConvert.cpp defines them (its DIRECTX_MATH_VERSION < 306 branch; DirectXMath
+    3.06 ships the same two functions)."""
+    out = []
+    for name in ("XMColorRGBToSRGB", "XMColorSRGBToRGB"):
+        m = re.search(r"^static inline XMVECTOR " + name + r"\s*\(", conv, re.M)
+        if not m:
+            raise RuntimeError(name + " not found in DirectXTexConvert.cpp")
+        out.append(cut_function(conv, m.start()))
+    return "\n".join(out)
 
 
 def cut_static_function(src, name):
@@ -453,7 +525,9 @@ def build(verbose=True):
         cpp = open(PLUGIN_CPP, encoding="utf-8", errors="replace").read()
         mips = open(MIPMAPS_CPP, encoding="utf-8", errors="replace").read()
         filt = open(FILTERS_H, encoding="utf-8", errors="replace").read()
-        unit = (SHIM_TOP + cut_inlines(hdr) + SHIM_CLASS + cut_members(cpp) + SHIM_BOTTOM + MIP_SHIM_TOP + cut_filters(filt)
+        conv = open(CONVERT_CPP, encoding="utf-8", errors="replace").read()
+        unit = (SHIM_TOP + cut_inlines(hdr) + SHIM_CLASS + cut_members(cpp) + SHIM_BOTTOM + MIP_SHIM_TOP.replace("//@SRGB_FUNCTIONS@", cut_srgb(conv))
+                + cut_filters(filt)
                 + cut_static_function(mips, "_Generate2DMipsBoxFilter") + "\n" + cut_static_function(mips, "_Generate2DMipsLinearFilter")
                 + MIP_SHIM_BOTTOM
                 + BC45_SHIM_TOP + cut_bc45(open(BC45_CPP, encoding="utf-8", errors="replace").read(),

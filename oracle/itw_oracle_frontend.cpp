@@ -192,19 +192,61 @@ void linear_taps(size_t source, size_t dest, std::vector<Tap>& lf)              
         lf[u] = Tap{size_t(isrcA), size_t(isrcB), weight, 1.0f - weight};
     }
 }
-void load_row(std::vector<float>& row, const uint16_t* src, size_t width)
+// ---- texel codecs of the three chains ----
+// RGBA16F: XMLoadHalf4 / XMStoreHalf4 (float_from_half / half_from_float above).
+// RGBA8 UNORM: XMLoadUByteN4 = byte * (1/255) (rule F7); XMStoreUByteN4 = saturate, * 255, round to nearest -- ASSUMED, the store's
+//   rounding is DirectXMath's (not in the tree); the decoder tests make the same assumption.
+// RGBA8 UNORM_SRGB: the same bytes with XMColorSRGBToRGB after the load and XMColorRGBToSRGB before the store, restated from
+//   DirectXTexConvert.cpp:2669-2685, :2757-2775 (float constants 1.f/12.92f ..., powf per component, alpha untouched).
+inline float saturate_f(float v) { v = (v > 0.0f) ? v : 0.0f; return (v < 1.0f) ? v : 1.0f; }
+inline float srgb_to_linear(float s)
 {
-    for (size_t i = 0; i < width * 4; i++) row[i] = float_from_half(src[i]);
+    const float v = saturate_f(s);
+    const float v0 = v * (1.f / 12.92f);
+    const float v1 = powf((v + 0.055f) * (1.f / 1.055f), 2.4f);
+    return (v > 0.04045f) ? v1 : v0;
 }
-}  // namespace
-
-extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int levels, uint16_t* out)
+inline float linear_to_srgb(float l)
 {
-    memcpy(out, level0, (size_t)w * h * 8);
+    const float v = saturate_f(l);
+    const float v0 = v * 12.92f;
+    const float v1 = 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+    return (v < 0.0031308f) ? v0 : v1;
+}
+inline uint8_t unorm8_store(float v) { return (uint8_t)(int)(saturate_f(v) * 255.0f + 0.5f); }
+
+struct CodecF16 {
+    typedef uint16_t T;
+    static void load(std::vector<float>& row, const T* src, size_t width) { for (size_t i = 0; i < width * 4; i++) row[i] = float_from_half(src[i]); }
+    static T store(float v, int) { return half_from_float(v); }
+};
+struct CodecUnorm8 {
+    typedef uint8_t T;
+    static void load(std::vector<float>& row, const T* src, size_t width) { for (size_t i = 0; i < width * 4; i++) row[i] = (float)src[i] * (1.0f / 255.0f); }
+    static T store(float v, int) { return unorm8_store(v); }
+};
+struct CodecSrgb8 {
+    typedef uint8_t T;
+    static void load(std::vector<float>& row, const T* src, size_t width)
+    {
+        for (size_t i = 0; i < width * 4; i++) {
+            const float f = (float)src[i] * (1.0f / 255.0f);
+            row[i] = ((i & 3) == 3) ? f : srgb_to_linear(f);
+        }
+    }
+    static T store(float v, int c) { return unorm8_store(c == 3 ? v : linear_to_srgb(v)); }
+};
+
+// The two generators in their scanline form; `out` receives `levels` tightly packed levels one after the other.
+template <class Codec>
+int mip_chain(const typename Codec::T* level0, int w, int h, int levels, typename Codec::T* out)
+{
+    typedef typename Codec::T T;
+    memcpy(out, level0, (size_t)w * h * 4 * sizeof(T));
     const bool box = w > 0 && h > 0 && !(w & (w - 1)) && !(h & (h - 1));
     size_t width = (size_t)w, height = (size_t)h;
-    const uint16_t* src = out;
-    uint16_t* dst = out + width * height * 4;
+    const T* src = out;
+    T* dst = out + width * height * 4;
     // the box loop's scanline buffers live across levels (:730-739); `second` is only reloaded while the source has two rows,
     // and the fourth tap keeps reading it when the height reaches one before the width does (reference behaviour)
     std::vector<float> first((size_t)w * 4, 0.0f), second((size_t)w * 4, 0.0f), r0((size_t)w * 4), r1((size_t)w * 4);
@@ -213,8 +255,8 @@ extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int le
         const size_t nwidth = width > 1 ? width >> 1 : 1, nheight = height > 1 ? height >> 1 : 1;
         if (box) {
             for (size_t y = 0; y < nheight; y++) {
-                load_row(first, src + (height > 1 ? 2 * y : y) * width * 4, width);
-                if (height > 1) load_row(second, src + (2 * y + 1) * width * 4, width);
+                Codec::load(first, src + (height > 1 ? 2 * y : y) * width * 4, width);
+                if (height > 1) Codec::load(second, src + (2 * y + 1) * width * 4, width);
                 const std::vector<float>& u1 = height > 1 ? second : first;        // urow1
                 for (size_t x = 0; x < nwidth; x++) {
                     const size_t x2 = x << 1;
@@ -225,7 +267,7 @@ extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int le
                         float v = p0 + p1;
                         v = v + p2;
                         v = v + p3;
-                        dst[(y * nwidth + x) * 4 + c] = half_from_float(v * 0.25f);
+                        dst[(y * nwidth + x) * 4 + c] = Codec::store(v * 0.25f, c);
                     }
                 }
             }
@@ -233,13 +275,13 @@ extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int le
             linear_taps(width, nwidth, lx);
             linear_taps(height, nheight, ly);
             for (size_t y = 0; y < nheight; y++) {
-                load_row(r0, src + ly[y].u0 * width * 4, width);
-                load_row(r1, src + ly[y].u1 * width * 4, width);
+                Codec::load(r0, src + ly[y].u0 * width * 4, width);
+                Codec::load(r1, src + ly[y].u1 * width * 4, width);
                 for (size_t x = 0; x < nwidth; x++)
                     for (int c = 0; c < 4; c++) {
                         const float a = r0[lx[x].u0 * 4 + c] * lx[x].w0 + r0[lx[x].u1 * 4 + c] * lx[x].w1;
                         const float b = r1[lx[x].u0 * 4 + c] * lx[x].w0 + r1[lx[x].u1 * 4 + c] * lx[x].w1;
-                        dst[(y * nwidth + x) * 4 + c] = half_from_float((ly[y].w0 * a) + (ly[y].w1 * b));
+                        dst[(y * nwidth + x) * 4 + c] = Codec::store((ly[y].w0 * a) + (ly[y].w1 * b), c);
                     }
             }
         }
@@ -250,6 +292,19 @@ extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int le
     }
     return 0;
 }
+}  // namespace
+
+extern "C" int oracle_mip_chain_f16(const uint16_t* level0, int w, int h, int levels, uint16_t* out) { return mip_chain<CodecF16>(level0, w, h, levels, out); }
+// RGBA8 chain of the LDR save path, non-WIC generators: srgb = 1 is what the plug-in gets for *_SRGB encodings (IntelPlugin.cpp:152-154
+// overrides the scratch format, _UseWICFiltering then returns false, DirectXTexMipmaps.cpp:389-393); srgb = 0 is the same code on
+// R8G8B8A8_UNORM (TEX_FILTER_FORCE_NON_WIC) -- the plug-in's default for UNORM encodings is WIC, which is outside the tree.
+extern "C" int oracle_mip_chain_rgba8(const uint8_t* level0, int w, int h, int levels, int srgb, uint8_t* out)
+{
+    return srgb ? mip_chain<CodecSrgb8>(level0, w, h, levels, out) : mip_chain<CodecUnorm8>(level0, w, h, levels, out);
+}
+// scalar pieces for tools/gen_srgb_tables.py (the product's tables are derived from THESE functions, i.e. from the C library's powf)
+extern "C" float oracle_srgb_to_linear(float v) { return srgb_to_linear(v); }
+extern "C" int oracle_linear_to_srgb8(float v) { return unorm8_store(linear_to_srgb(v)); }
 
 // ConvertTo8Bit(double, gammaCorrect = true) of one float, exported for tools/gen_gamma_table.py (which derives the product's
 // threshold table from THIS function, i.e. from the C library's pow) and for tests.

@@ -154,6 +154,17 @@ void emu_mip_level_f16(const uint8_t* src, int sw, int sh, int sstride, uint8_t*
             memcpy(dst + ((size_t)y * pw + x) * 8, out, 8);
         }
 }
+// one padded RGBA8 mip level through the float filter of csrc/mips_f16.cuh: codec 1 = UNORM, 2 = UNORM_SRGB
+void emu_mip_level_rgba8(int codec, const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int pw, int ph, int box, const uint8_t* stale_row)
+{
+    for (int y = 0; y < ph; y++)
+        for (int x = 0; x < pw; x++) {
+            u32 out[2];
+            if (codec == 2) mip_float_texel<2>(out, src, sw, sh, sstride, dw, dh, x, y, box != 0, stale_row);
+            else mip_float_texel<1>(out, src, sw, sh, sstride, dw, dh, x, y, box != 0, stale_row);
+            memcpy(dst + ((size_t)y * pw + x) * 4, out, 4);
+        }
+}
 // the product's profile tables (csrc/itw_params.h), exported so the emulation is self-contained
 #define EMU_BC7(name, row) void emu_GetProfile_##name(bc7_enc_settings* s) { bc7_fill_profile(s, row); }
 EMU_BC7(ultrafast, 0) EMU_BC7(veryfast, 1) EMU_BC7(fast, 2) EMU_BC7(basic, 3) EMU_BC7(slow, 4)

@@ -29,11 +29,22 @@ def main():
         img = M.random_f16(h, w, seed=h * 131 + w)
         chain = M.chain_with(lib.ref_mip_chain_f16, img, M.full_levels(w, h))
         mips[f"{h}x{w}"] = hashlib.sha256(b"".join(l.tobytes() for l in chain)).hexdigest()
+    import ctypes
+    import numpy as np
+    import test_mips as M8
+    lib.ref_mip_chain_rgba8.restype = ctypes.c_int
+    lib.ref_mip_chain_rgba8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    mips8 = {}
+    for h, w in M8.SIZES:
+        img = M8.random_rgba8(h, w)
+        for srgb in (0, 1):
+            chain = M8.chain_with(lib.ref_mip_chain_rgba8, img, srgb)
+            mips8[f"{h}x{w}:{'srgb' if srgb else 'unorm'}"] = hashlib.sha256(b"".join(l.tobytes() for l in chain)).hexdigest()
     out = {"generator": "tests/golden/make_golden_frontend.py", "produced_by": "reference function bodies (oracle/build_ref_frontend.py)",
-           "convert": convert, "mip_chain_f16": mips}
+           "convert": convert, "mip_chain_f16": mips, "mip_chain_rgba8": mips8}
     path = os.path.join(HERE, "frontend_digests.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
-    print("wrote", path, len(convert), "conversion digests,", len(mips), "mip-chain digests")
+    print("wrote", path, len(convert), "conversion digests,", len(mips), "+", len(mips8), "mip-chain digests")
 
 
 if __name__ == "__main__":

@@ -155,3 +155,26 @@ def run(api, fmt, img, prof):
 
 def differing_blocks(a, b, bpb):
     return int((a.reshape(-1, bpb) != b.reshape(-1, bpb)).any(1).sum())
+
+
+def oracle_mip_chain_rgba8(img, srgb=0, levels=None, pad=True):
+    """The RGBA8 mip chain contract (include/itw_bcn.h section 4): DirectXTex's non-WIC generators as restated in
+    oracle/itw_oracle_frontend.cpp (oracle_mip_chain_rgba8; pinned to the reference's own bodies by tests/test_mips.py).
+    Returns the list of levels, each padded to multiples of 4 by edge replication unless pad=False."""
+    import ctypes
+    h, w = img.shape[:2]
+    if levels is None:
+        levels = max(h, w).bit_length()
+    dims = [(max(1, h >> l), max(1, w >> l)) for l in range(levels)]
+    out = np.zeros(sum(a * b * 4 for a, b in dims), np.uint8)
+    src = np.ascontiguousarray(img)
+    f = oracle().lib.oracle_mip_chain_rgba8
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    assert f(src.ctypes.data, w, h, levels, int(srgb), out.ctypes.data) == 0
+    res, off = [], 0
+    for a, b in dims:
+        lvl = out[off:off + a * b * 4].reshape(a, b, 4)
+        res.append(synth.pad_to_4(lvl) if pad else lvl)
+        off += a * b * 4
+    return res

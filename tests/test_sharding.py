@@ -76,8 +76,9 @@ def _worker(rank, world, port, fmt, prof, shape, ret):
         def encode(img):
             return oracle.encode(fmt, img, settings)
 
-        got, plan = sharding.run_plan_on_cpu(lib, fmt, base, levels, encode, T.synth.mip_chain)
-        want = np.concatenate([encode(np.ascontiguousarray(l)) for l in T.synth.mip_chain(base)])
+        chain_of = lambda img: T.oracle_mip_chain_rgba8(img, 0)      # the product's RGBA8 contract (box / linear, DirectXTex non-WIC)
+        got, plan = sharding.run_plan_on_cpu(lib, fmt, base, levels, encode, chain_of)
+        want = np.concatenate([encode(np.ascontiguousarray(l)) for l in chain_of(base)])
         ret[rank] = bool(np.array_equal(got, want)) and plan.band_levels < levels
     finally:
         dist.destroy_process_group()
@@ -111,7 +112,7 @@ def _gpu_worker(rank, world, port, ret):
             band = torch.from_numpy(np.ascontiguousarray(base[y0:y1]).reshape(-1)).cuda()
             chain, plan = sharding.encode_mip_chain_sharded(lib, fmt, band, w, h, levels, settings)
             torch.cuda.synchronize()
-            want = np.concatenate([lib.encode(fmt, np.ascontiguousarray(l), settings) for l in T.synth.mip_chain(base)])
+            want = np.concatenate([lib.encode(fmt, np.ascontiguousarray(l), settings) for l in T.oracle_mip_chain_rgba8(base, 0)])
             ok = ok and np.array_equal(chain.cpu().numpy(), want)
         sharding.shard_finalize(lib)
         ret[rank] = bool(ok)
@@ -139,5 +140,5 @@ def test_sharded_entry_on_one_gpu_equals_the_plain_chain():
         band = torch.from_numpy(base.reshape(-1)).cuda()
         chain, plan = sharding.encode_mip_chain_sharded(lib, fmt, band, w, h, levels)
         torch.cuda.synchronize()
-        want = np.concatenate([lib.encode(fmt, np.ascontiguousarray(l)) for l in T.synth.mip_chain(base)])
+        want = np.concatenate([lib.encode(fmt, np.ascontiguousarray(l)) for l in T.oracle_mip_chain_rgba8(base, 0)])
         assert np.array_equal(chain.cpu().numpy(), want), fmt
