@@ -37,7 +37,7 @@ ITW_HD int pack565_lane(float r, float g, float b) { return pack565(r, g, b); }
 // Linear 2-bit indices of both lanes along p0 -> p1; K:308-344.  kRefine: also accumulate sum_k (3 - q_k) * px_k per
 // channel (K:432-440) while the indices are at hand.
 template <bool kRefine>
-ITW_HD void bc1_indices_pair(const f2 (&px)[3][16], int p0x, int p1x, int p0y, int p1y, u32& bits_x, u32& bits_y, f2 (&atb1)[3])
+ITW_HD void bc1_indices_pair(const f2 (&px)[3][16], int p0x, int p1x, int p0y, int p1y, u32& bits_x, u32& bits_y, f2 (&atb1)[3], const f2 one)
 {
     float ax[3], bx[3], ay[3], by[3];
     unpack565(ax, p0x); unpack565(bx, p1x);
@@ -49,21 +49,21 @@ ITW_HD void bc1_indices_pair(const f2 (&px)[3][16], int p0x, int p1x, int p0y, i
         dir[c] = add2(mk2(bx[c], by[c]), na[c]);                       // b - a, exact small integers
     }
     f2 n2 = mul2(dir[0], dir[0]);                                      // 0 + x dropped: squares are never -0
-    n2 = add2(n2, mul2(dir[1], dir[1]));
-    n2 = add2(n2, mul2(dir[2], dir[2]));
+    n2 = madd2(dir[1], dir[1], n2, one);
+    n2 = madd2(dir[2], dir[2], n2, one);
     const f2 inv3 = mul2(mk2(1.0f / n2.x, 1.0f / n2.y), splat2(3.0f)); // inf when p0 == p1 -> NaN below, as in K
 #pragma unroll
     for (int c = 0; c < 3; c++) dir[c] = mul2(dir[c], inv3);
     f2 bias = splat2(0.5f);
 #pragma unroll
-    for (int c = 0; c < 3; c++) bias = add2(bias, mul2(na[c], dir[c]));    // bias -= a*dir: -(a*dir) == (-a)*dir
+    for (int c = 0; c < 3; c++) bias = madd2(na[c], dir[c], bias, one);    // bias -= a*dir: -(a*dir) == (-a)*dir
     u32 bx_bits = 0u, by_bits = 0u;
     if (kRefine) { atb1[0] = atb1[1] = atb1[2] = splat2(0.0f); }
 #pragma unroll
     for (int k = 15; k >= 0; k--) {                                   // texels are independent: descending order makes
         f2 d = mul2(px[0][k], dir[0]);                                // bits = bits*4 + q one multiply-add per lane
-        d = add2(d, mul2(px[1][k], dir[1]));                          // (0 + first term dropped: d only feeds d + bias,
-        d = add2(d, mul2(px[2][k], dir[2]));                          //  where the sign of a zero vanishes)
+        d = madd2(px[1][k], dir[1], d, one);                          // (0 + first term dropped: d only feeds d + bias,
+        d = madd2(px[2][k], dir[2], d, one);                          //  where the sign of a zero vanishes)
         const f2 t = trunc_clamp_magic(add2(d, bias), 3.5f);          // 2^23 + q
         bx_bits = bx_bits * 4u + (float_bits(t.x) & 3u);
         by_bits = by_bits * 4u + (float_bits(t.y) & 3u);
@@ -109,7 +109,7 @@ ITW_HD void bc1_refine_lane(u32 bits, const float (&mean)[3], const float (&atb1
 }
 
 // The colour half of both lanes; K:494-533.  out = (w0, w1) per lane.
-ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16])
+ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16], const f2 one)
 {
     // mean: sixteen exact integers, any order; K:377-385.  The first "0 + x" is dropped (x >= 0).
     f2 mean[3], nmean[3];
@@ -137,14 +137,14 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16])
     f2 v0 = splat2(1.0f), v1 = v0, v2 = v0;
 #pragma unroll
     for (int it = 0; it < 4; it++) {
-        const f2 a0 = add2(add2(mul2(crr, v0), mul2(crg, v1)), mul2(crb, v2));
-        const f2 a1 = add2(add2(mul2(crg, v0), mul2(cgg, v1)), mul2(cgb, v2));
-        const f2 a2 = add2(add2(mul2(crb, v0), mul2(cgb, v1)), mul2(cbb, v2));
+        const f2 a0 = madd2(crb, v2, madd2(crg, v1, mul2(crr, v0), one), one);      // (crr*v0 + crg*v1) + crb*v2
+        const f2 a1 = madd2(cgb, v2, madd2(cgg, v1, mul2(crg, v0), one), one);
+        const f2 a2 = madd2(cbb, v2, madd2(cgb, v1, mul2(crb, v0), one), one);
         v0 = a0; v1 = a1; v2 = a2;
         if (it & 1) {
             f2 n2 = mul2(a0, a0);                                      // 0 + x dropped (a square is never -0)
-            n2 = add2(n2, mul2(a1, a1));
-            n2 = add2(n2, mul2(a2, a2));
+            n2 = madd2(a1, a1, n2, one);
+            n2 = madd2(a2, a2, n2, one);
             const f2 rn = mk2(1.0f / sqrtf(n2.x), 1.0f / sqrtf(n2.y));
             v0 = mul2(v0, rn); v1 = mul2(v1, rn); v2 = mul2(v2, rn);
         }
@@ -155,16 +155,16 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16])
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         f2 d = mul2(add2(px[0][k], nmean[0]), v0);
-        d = add2(d, mul2(add2(px[1][k], nmean[1]), v1));
-        d = add2(d, mul2(add2(px[2][k], nmean[2]), v2));
+        d = madd2(add2(px[1][k], nmean[1]), v1, d, one);
+        d = madd2(add2(px[2][k], nmean[2]), v2, d, one);
         dmin = min2(dmin, d);                                          // d is finite: fminf == the reference's (a<b)?a:b
         dmax = max2(dmax, d);
     }
     if (dmax.x - dmin.x < 1.0f) { dmin.x -= 0.5f; dmax.x += 0.5f; }
     if (dmax.y - dmin.y < 1.0f) { dmin.y -= 0.5f; dmax.y += 0.5f; }
     f2 n2 = mul2(v0, v0);
-    n2 = add2(n2, mul2(v1, v1));
-    n2 = add2(n2, mul2(v2, v2));
+    n2 = madd2(v1, v1, n2, one);
+    n2 = madd2(v2, v2, n2, one);
     const f2 inv = mk2(1.0f / n2.x, 1.0f / n2.y);
     const f2 tmin = mul2(dmin, inv), tmax = mul2(dmax, inv);
     const f2 ax[3] = {v0, v1, v2};
@@ -173,8 +173,8 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16])
     for (int c = 0; c < 3; c++) {
         // clamp_sse(v, 0, 255) == fminf(fmaxf(v, 0), 255) for every v that can occur (a NaN gives 0 in both forms; -0
         // and +0 truncate alike)
-        lo[c] = min2(max2(add2(mean[c], mul2(tmin, ax[c])), splat2(0.0f)), splat2(255.0f));
-        hi[c] = min2(max2(add2(mean[c], mul2(tmax, ax[c])), splat2(0.0f)), splat2(255.0f));
+        lo[c] = min2(max2(madd2(tmin, ax[c], mean[c], one), splat2(0.0f)), splat2(255.0f));
+        hi[c] = min2(max2(madd2(tmax, ax[c], mean[c], one), splat2(0.0f)), splat2(255.0f));
     }
     int p0x = pack565(lo[0].x, lo[1].x, lo[2].x), p1x = pack565(hi[0].x, hi[1].x, hi[2].x);
     int p0y = pack565(lo[0].y, lo[1].y, lo[2].y), p1y = pack565(hi[0].y, hi[1].y, hi[2].y);
@@ -182,7 +182,7 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16])
     if (p0y < p1y) { const int t = p0y; p0y = p1y; p1y = t; }
     u32 bits_x, bits_y;
     f2 atb1[3];
-    bc1_indices_pair<true>(px, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1);
+    bc1_indices_pair<true>(px, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1, one);
 
     // one least-squares refinement pass; K:419-480, :524-530
     {
@@ -191,7 +191,7 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16])
         bc1_refine_lane(bits_x, mx, sx, p0x, p1x);
         bc1_refine_lane(bits_y, my, sy, p0y, p1y);
     }
-    bc1_indices_pair<false>(px, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1);
+    bc1_indices_pair<false>(px, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1, one);
 
     // linear order 0,1,2,3 -> BC1 codes 0,2,3,1; K:482-492
     PairWords w;
@@ -209,7 +209,7 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16])
 }
 
 // BC3 alpha half of both lanes; K:535-571.  al[k] = alpha of texel k (exact integers as floats).
-ITW_HD PairWords bc3_alpha_pair(const f2 (&al)[16])
+ITW_HD PairWords bc3_alpha_pair(const f2 (&al)[16], const f2 one)
 {
     f2 lo = splat2(255.0f), hi = splat2(0.0f);
 #pragma unroll
@@ -222,7 +222,7 @@ ITW_HD PairWords bc3_alpha_pair(const f2 (&al)[16])
 #pragma unroll
     for (int k = 15; k >= 0; k--) {
         // (a - lo) * scale + 0.5, each step rounded as in K:553; 0.5 <= value <= 255*70 + 0.5, clamped to 0..7 after truncation
-        const f2 proj = add2(mul2(add2(al[k], nlo), scale), splat2(0.5f));
+        const f2 proj = madd2(add2(al[k], nlo), scale, splat2(0.5f), one);
         const f2 t = trunc_clamp_magic(proj, 7.5f);
         int qx = 7 - (int)(float_bits(t.x) & 7u), qy = 7 - (int)(float_bits(t.y) & 7u);
         if (qx > 0) qx++;
@@ -243,13 +243,13 @@ ITW_HD PairWords bc3_alpha_pair(const f2 (&al)[16])
 
 // Two whole blocks: 2 x 16 packed RGBA8 texels in, 2 (BC1) or 4 (BC3) words out per block; K:573-596
 template <bool kAlpha>
-ITW_HD void bc1_bc3_encode_pair(const u32 (&ta)[16], const u32 (&tb)[16], u32 (&oa)[4], u32 (&ob)[4])
+ITW_HD void bc1_bc3_encode_pair(const u32 (&ta)[16], const u32 (&tb)[16], u32 (&oa)[4], u32 (&ob)[4], const f2 one)
 {
     if (kAlpha) {
         f2 al[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) al[k] = bytes_to_f2(ta[k], tb[k], 3);
-        const PairWords w = bc3_alpha_pair(al);
+        const PairWords w = bc3_alpha_pair(al, one);
         oa[0] = w.a0; oa[1] = w.a1; ob[0] = w.b0; ob[1] = w.b1;
     }
     f2 px[3][16];
@@ -257,7 +257,7 @@ ITW_HD void bc1_bc3_encode_pair(const u32 (&ta)[16], const u32 (&tb)[16], u32 (&
     for (int c = 0; c < 3; c++)
 #pragma unroll
         for (int k = 0; k < 16; k++) px[c][k] = bytes_to_f2(ta[k], tb[k], c);
-    const PairWords w = bc1_colour_pair(px);
+    const PairWords w = bc1_colour_pair(px, one);
     if (kAlpha) { oa[2] = w.a0; oa[3] = w.a1; ob[2] = w.b0; ob[3] = w.b1; }
     else { oa[0] = w.a0; oa[1] = w.a1; oa[2] = oa[3] = 0; ob[0] = w.b0; ob[1] = w.b1; ob[2] = ob[3] = 0; }
 }
@@ -275,7 +275,7 @@ constexpr int kBc1CtasPerSm = ITW_BC1_CTAS_PER_SM;
 // threads read consecutive 16-byte pieces of the staged rows and write consecutive output blocks).
 // Needs 16-byte aligned surface rows (ptr and stride multiples of 16); other surfaces take bc1_bc3_kernel.
 template <bool kAlpha>
-__global__ void __launch_bounds__(kBc1PairThreads, kBc1CtasPerSm) bc1_bc3_pair_kernel(SurfaceView s, uint8_t* __restrict__ dst, long long nblocks)
+__global__ void __launch_bounds__(kBc1PairThreads, kBc1CtasPerSm) bc1_bc3_pair_kernel(SurfaceView s, uint8_t* __restrict__ dst, long long nblocks, float one_arg)
 {
     __shared__ __align__(128) unsigned char stage[2][4 * kBc1TileRowBytes];
     __shared__ __align__(8) unsigned long long full[2];
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kBc1PairThreads, kBc1CtasPerSm) bc1_bc3_pair_k
             tb[4 * y + 0] = vb.x; tb[4 * y + 1] = vb.y; tb[4 * y + 2] = vb.z; tb[4 * y + 3] = vb.w;
         }
         // (blocks past the end of the surface read stale shared memory: any bit pattern is a valid input, nothing is stored)
-        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob);
+        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob, splat2(one_arg));       // one_arg == 1.0f, see madd2 (itw_device.cuh)
         if (kAlpha) {
             if (ida < nblocks) reinterpret_cast<uint4*>(dst)[ida] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
             if (idb < nblocks) reinterpret_cast<uint4*>(dst)[idb] = make_uint4(ob[0], ob[1], ob[2], ob[3]);

@@ -185,10 +185,10 @@ int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* setting
             const long long cap = (long long)tls.sm_count * kBc1CtasPerSm;
             const unsigned gridp = (unsigned)(tiles < cap ? tiles : cap);
             if (format == ITW_FORMAT_BC1) {
-                if (vec16) bc1_bc3_pair_kernel<false><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks);
+                if (vec16) bc1_bc3_pair_kernel<false><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks, 1.0f);
                 else       bc1_bc3_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
             } else {
-                if (vec16) bc1_bc3_pair_kernel<true><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks);
+                if (vec16) bc1_bc3_pair_kernel<true><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks, 1.0f);
                 else       bc1_bc3_kernel<true, false><<<grid1, 128, 0, stream>>>(v, d_dst);
             }
             break;

@@ -150,6 +150,14 @@ ITW_HD f2 fma2(f2 a, f2 b, f2 c)
     return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
 #endif
 }
+// RN(RN(a*b) + c) per lane -- multiply, then add, two roundings (the reference's unfused expression).
+// ptxas of CUDA 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into ONE FFMA2 whenever the product has no other use, even with
+// --fmad false and although both instructions carry an explicit .rn (scalar mul.rn / add.rn are never contracted; checked with
+// cuobjdump, see tools/ubench/check_f32x2.cu).  A fused multiply-add rounds once and changes results.  The addition is therefore
+// issued as an FFMA2 whose multiplier `one` is a KERNEL ARGUMENT that only the host knows to be 1.0: p * 1 is exact, so
+// fma(p, one, c) rounds exactly like p + c, and a product that feeds the multiplicand of an FMA cannot be contracted into it.
+// Same instruction count as the packed multiply + packed add it replaces.
+ITW_HD f2 madd2(f2 a, f2 b, f2 c, f2 one) { return fma2(mul2(a, b), one, c); }
 // a + b rounded TOWARDS ZERO per lane (the float->int "magic number" conversion below)
 ITW_HD f2 add2_rz(f2 a, f2 b)
 {
