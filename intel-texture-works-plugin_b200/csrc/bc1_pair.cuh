@@ -266,8 +266,10 @@ ITW_HD void bc1_bc3_encode_pair(const u32 (&ta)[16], const u32 (&tb)[16], u32 (&
 constexpr int kBc1PairThreads = 128;
 constexpr int kBc1TileBlocks = 2 * kBc1PairThreads;            // 256 consecutive blocks per tile
 constexpr int kBc1TileRowBytes = kBc1TileBlocks * 16;          // 4096
+// Two CTAs of four warps per SM: the kernel wants ~250 registers per thread (96 of them hold the 2 x 48 texel values).  Three CTAs
+// (168 registers) spill ~140 words and measured 70 us at 4096^2 against 61 us for two (B200; tools/tune_unroll.sh style variants).
 #ifndef ITW_BC1_CTAS_PER_SM
-#define ITW_BC1_CTAS_PER_SM 3
+#define ITW_BC1_CTAS_PER_SM 2
 #endif
 constexpr int kBc1CtasPerSm = ITW_BC1_CTAS_PER_SM;
 

@@ -200,7 +200,8 @@ def test_gpu_whole_save_path_from_planes(fmt, dxgi, prof, depth, planes, flags, 
     norm = flags & B.FRONT_NORMALIZE
     for item in range(items):
         top = o.convert_pixels(fmt, srcs[item], flags & ~B.FRONT_NORMALIZE, pad=False)
-        chain = HM.oracle_chain(top, levels) if hdr else [lv[:max(1, h >> i), :max(1, w >> i)] for i, lv in enumerate(LM.reference_chain(top, levels))]
+        srgb = 1 if dxgi in (72, 78, 99) else 0                    # *_SRGB encodings take the sRGB-correct chain (IntelPlugin.cpp:152-154)
+        chain = HM.oracle_chain(top, levels) if hdr else T.oracle_mip_chain_rgba8(top, srgb, levels, pad=False)
         for mip in range(levels):
             lv = np.ascontiguousarray(chain[mip])
             if norm:                                               # the oracle's normalise pass through an identity conversion
