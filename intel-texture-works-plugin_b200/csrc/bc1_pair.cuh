@@ -14,7 +14,7 @@
 //   * "0 + x" first additions are dropped (x when x is not -0, and the sign of a zero is shown unobservable).
 //
 // Staging: a persistent CTA fetches tiles of 2 x blockDim consecutive blocks with the TMA engine (cp.async.bulk, mbarrier)
-// into a double-buffered 4-row shared-memory tile while the previous tile is being encoded.
+// into a 4-row shared-memory tile; the next tile streams in while the current one is being encoded from registers.
 #pragma once
 #include "bc1_bc3.cuh"
 
@@ -36,8 +36,19 @@ ITW_HD int pack565_lane(float r, float g, float b) { return pack565(r, g, b); }
 
 // Linear 2-bit indices of both lanes along p0 -> p1; K:308-344.  kRefine: also accumulate sum_k (3 - q_k) * px_k per
 // channel (K:432-440) while the indices are at hand.
+// The 2 x 48 texel values live in SHARED memory on the device -- px[(c*16 + k) * ps], one 8-byte column per thread -- instead
+// of 96 registers: that is what lets 14 warps share an SM instead of 8 (the load/store pipe is idle in this kernel, every
+// pass reads its operands with LDS.64 at constant offsets).  The emulation passes a local array with ps = 1.
+#define ITW_PX(c, k) px[((c) * 16 + (k)) * ps]
+// Between two passes over the texel values: the compiler must not keep the 96 values of one pass in registers for the next
+// (it would, the columns being read-only after the conversion) -- each pass re-reads them from shared memory.
+#if defined(__CUDA_ARCH__)
+#define ITW_PASS_FENCE() asm volatile("" ::: "memory")
+#else
+#define ITW_PASS_FENCE() ((void)0)
+#endif
 template <bool kRefine>
-ITW_HD void bc1_indices_pair(const f2 (&px)[3][16], int p0x, int p1x, int p0y, int p1y, u32& bits_x, u32& bits_y, f2 (&atb1)[3], const f2 one)
+ITW_HD void bc1_indices_pair(const f2* px, const int ps, int p0x, int p1x, int p0y, int p1y, u32& bits_x, u32& bits_y, f2 (&atb1)[3], const f2 one)
 {
     float ax[3], bx[3], ay[3], by[3];
     unpack565(ax, p0x); unpack565(bx, p1x);
@@ -61,9 +72,10 @@ ITW_HD void bc1_indices_pair(const f2 (&px)[3][16], int p0x, int p1x, int p0y, i
     if (kRefine) { atb1[0] = atb1[1] = atb1[2] = splat2(0.0f); }
 #pragma unroll
     for (int k = 15; k >= 0; k--) {                                   // texels are independent: descending order makes
-        f2 d = mul2(px[0][k], dir[0]);                                // bits = bits*4 + q one multiply-add per lane
-        d = madd2(px[1][k], dir[1], d, one);                          // (0 + first term dropped: d only feeds d + bias,
-        d = madd2(px[2][k], dir[2], d, one);                          //  where the sign of a zero vanishes)
+        const f2 pr = ITW_PX(0, k), pg = ITW_PX(1, k), pb = ITW_PX(2, k);
+        f2 d = mul2(pr, dir[0]);                                      // bits = bits*4 + q one multiply-add per lane
+        d = madd2(pg, dir[1], d, one);                                // (0 + first term dropped: d only feeds d + bias,
+        d = madd2(pb, dir[2], d, one);                                //  where the sign of a zero vanishes)
         const f2 t = trunc_clamp_magic(add2(d, bias), 3.5f);          // 2^23 + q
         bx_bits = bx_bits * 4u + (float_bits(t.x) & 3u);
         by_bits = by_bits * 4u + (float_bits(t.y) & 3u);
@@ -71,8 +83,7 @@ ITW_HD void bc1_indices_pair(const f2 (&px)[3][16], int p0x, int p1x, int p0y, i
             // x = 3 - q = (2^23 + 3) - t exactly; x*px (<= 765) and the running sums (<= 12240) are exact integers, so
             // the fused multiply-add is the reference's multiply-then-add, and the order of an exact sum is free
             const f2 x = add2(splat2(8388611.0f), mk2(-t.x, -t.y));
-#pragma unroll
-            for (int c = 0; c < 3; c++) atb1[c] = fma2(x, px[c][k], atb1[c]);
+            atb1[0] = fma2(x, pr, atb1[0]); atb1[1] = fma2(x, pg, atb1[1]); atb1[2] = fma2(x, pb, atb1[2]);
         }
     }
     bits_x = bx_bits; bits_y = by_bits;
@@ -109,27 +120,29 @@ ITW_HD void bc1_refine_lane(u32 bits, const float (&mean)[3], const float (&atb1
 }
 
 // The colour half of both lanes; K:494-533.  out = (w0, w1) per lane.
-ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16], const f2 one)
+ITW_HD PairWords bc1_colour_pair(const f2* px, const int ps, const f2 one)
 {
     // mean: sixteen exact integers, any order; K:377-385.  The first "0 + x" is dropped (x >= 0).
     f2 mean[3], nmean[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        f2 acc = px[c][0];
+        f2 acc = ITW_PX(c, 0);
 #pragma unroll
-        for (int k = 1; k < 16; k++) acc = add2(acc, px[c][k]);
+        for (int k = 1; k < 16; k++) acc = add2(acc, ITW_PX(c, k));
         mean[c] = mul2(acc, splat2(0.0625f));                          // /16, exact
         nmean[c] = mul2(acc, splat2(-0.0625f));
     }
+    ITW_PASS_FENCE();
     // centred covariance in texel order; K:386-417.  px - mean is exact (multiples of 1/16 below 256), the products are
     // exact (24 significant bits at most), so fusing each product into its running sum rounds exactly like multiply-then-add
     f2 crr = splat2(0.0f), crg = crr, crb = crr, cgg = crr, cgb = crr, cbb = crr;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const f2 r = add2(px[0][k], nmean[0]), g = add2(px[1][k], nmean[1]), b = add2(px[2][k], nmean[2]);
+        const f2 r = add2(ITW_PX(0, k), nmean[0]), g = add2(ITW_PX(1, k), nmean[1]), b = add2(ITW_PX(2, k), nmean[2]);
         crr = fma2(r, r, crr); crg = fma2(r, g, crg); crb = fma2(r, b, crb);
         cgg = fma2(g, g, cgg); cgb = fma2(g, b, cgb); cbb = fma2(b, b, cbb);
     }
+    ITW_PASS_FENCE();
     const f2 eps = splat2(0.001f);
     crr = add2(crr, eps); cgg = add2(cgg, eps); cbb = add2(cbb, eps);
 
@@ -154,12 +167,13 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16], const f2 one)
     f2 dmin = splat2(65536.0f), dmax = splat2(0.0f);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        f2 d = mul2(add2(px[0][k], nmean[0]), v0);
-        d = madd2(add2(px[1][k], nmean[1]), v1, d, one);
-        d = madd2(add2(px[2][k], nmean[2]), v2, d, one);
+        f2 d = mul2(add2(ITW_PX(0, k), nmean[0]), v0);
+        d = madd2(add2(ITW_PX(1, k), nmean[1]), v1, d, one);
+        d = madd2(add2(ITW_PX(2, k), nmean[2]), v2, d, one);
         dmin = min2(dmin, d);                                          // d is finite: fminf == the reference's (a<b)?a:b
         dmax = max2(dmax, d);
     }
+    ITW_PASS_FENCE();
     if (dmax.x - dmin.x < 1.0f) { dmin.x -= 0.5f; dmax.x += 0.5f; }
     if (dmax.y - dmin.y < 1.0f) { dmin.y -= 0.5f; dmax.y += 0.5f; }
     f2 n2 = mul2(v0, v0);
@@ -182,8 +196,9 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16], const f2 one)
     if (p0y < p1y) { const int t = p0y; p0y = p1y; p1y = t; }
     u32 bits_x, bits_y;
     f2 atb1[3];
-    bc1_indices_pair<true>(px, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1, one);
+    bc1_indices_pair<true>(px, ps, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1, one);
 
+    ITW_PASS_FENCE();
     // one least-squares refinement pass; K:419-480, :524-530
     {
         const float mx[3] = {mean[0].x, mean[1].x, mean[2].x}, my[3] = {mean[0].y, mean[1].y, mean[2].y};
@@ -191,7 +206,7 @@ ITW_HD PairWords bc1_colour_pair(const f2 (&px)[3][16], const f2 one)
         bc1_refine_lane(bits_x, mx, sx, p0x, p1x);
         bc1_refine_lane(bits_y, my, sy, p0y, p1y);
     }
-    bc1_indices_pair<false>(px, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1, one);
+    bc1_indices_pair<false>(px, ps, p0x, p1x, p0y, p1y, bits_x, bits_y, atb1, one);
 
     // linear order 0,1,2,3 -> BC1 codes 0,2,3,1; K:482-492
     PairWords w;
@@ -241,72 +256,79 @@ ITW_HD PairWords bc3_alpha_pair(const f2 (&al)[16], const f2 one)
     return w;
 }
 
-// Two whole blocks: 2 x 16 packed RGBA8 texels in, 2 (BC1) or 4 (BC3) words out per block; K:573-596
+// Two whole blocks: 2 x 16 packed RGBA8 texels in, 2 (BC1) or 4 (BC3) words out per block; K:573-596.  `px` = storage for the
+// 48 converted texel-value pairs (stride ps, see ITW_PX).
 template <bool kAlpha>
-ITW_HD void bc1_bc3_encode_pair(const u32 (&ta)[16], const u32 (&tb)[16], u32 (&oa)[4], u32 (&ob)[4], const f2 one)
+ITW_HD void bc1_bc3_encode_pair(const u32 (&ta)[16], const u32 (&tb)[16], u32 (&oa)[4], u32 (&ob)[4], f2* px, const int ps, const f2 one)
 {
-    if (kAlpha) {
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) ITW_PX(c, k) = bytes_to_f2(ta[k], tb[k], c);
+    if (kAlpha) {                                   // alpha from the packed texels while they are still in registers
         f2 al[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) al[k] = bytes_to_f2(ta[k], tb[k], 3);
         const PairWords w = bc3_alpha_pair(al, one);
         oa[0] = w.a0; oa[1] = w.a1; ob[0] = w.b0; ob[1] = w.b1;
     }
-    f2 px[3][16];
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int k = 0; k < 16; k++) px[c][k] = bytes_to_f2(ta[k], tb[k], c);
-    const PairWords w = bc1_colour_pair(px, one);
+    const PairWords w = bc1_colour_pair(px, ps, one);
     if (kAlpha) { oa[2] = w.a0; oa[3] = w.a1; ob[2] = w.b0; ob[3] = w.b1; }
     else { oa[0] = w.a0; oa[1] = w.a1; oa[2] = oa[3] = 0; ob[0] = w.b0; ob[1] = w.b1; ob[2] = ob[3] = 0; }
 }
 
 #if defined(__CUDACC__)
-constexpr int kBc1PairThreads = 128;
-constexpr int kBc1TileBlocks = 2 * kBc1PairThreads;            // 256 consecutive blocks per tile
-constexpr int kBc1TileRowBytes = kBc1TileBlocks * 16;          // 4096
-// Two CTAs of four warps per SM: the kernel wants ~250 registers per thread (96 of them hold the 2 x 48 texel values).  Three CTAs
-// (168 registers) spill ~140 words and measured 70 us at 4096^2 against 61 us for two (B200; tools/tune_unroll.sh style variants).
-#ifndef ITW_BC1_CTAS_PER_SM
-#define ITW_BC1_CTAS_PER_SM 2
+// CTA shape: 64 threads, 6 CTAs per SM = 12 warps; per CTA 24 KB of texel-value columns + one 8 KB stage buffer (+1 KB the
+// system reserves per CTA: a seventh CTA does not fit into the 227 KB of an SM).
+#ifndef ITW_BC1_THREADS
+#define ITW_BC1_THREADS 64
 #endif
+#ifndef ITW_BC1_CTAS_PER_SM
+#define ITW_BC1_CTAS_PER_SM 6
+#endif
+constexpr int kBc1PairThreads = ITW_BC1_THREADS;
 constexpr int kBc1CtasPerSm = ITW_BC1_CTAS_PER_SM;
+constexpr int kBc1TileBlocks = 2 * kBc1PairThreads;            // consecutive blocks per tile
+constexpr int kBc1TileRowBytes = kBc1TileBlocks * 16;
 
-// Persistent: CTA b encodes tiles b, b + gridDim.x, ...  Thread t owns blocks t and t + 128 of the tile (consecutive
-// threads read consecutive 16-byte pieces of the staged rows and write consecutive output blocks).
+// Persistent: CTA b encodes tiles b, b + gridDim.x, ...  Thread t owns blocks t and t + blockDim of the tile (consecutive
+// threads read consecutive 16-byte pieces of the staged rows and write consecutive output blocks).  Per tile: wait for the TMA
+// copy (cp.async.bulk, mbarrier) -> every thread takes its 2 x 16 packed texels into registers -> barrier -> thread 0 starts
+// the TMA copy of the CTA's NEXT tile into the same stage buffer, which streams in behind the encode of this one.
 // Needs 16-byte aligned surface rows (ptr and stride multiples of 16); other surfaces take bc1_bc3_kernel.
 template <bool kAlpha>
 __global__ void __launch_bounds__(kBc1PairThreads, kBc1CtasPerSm) bc1_bc3_pair_kernel(SurfaceView s, uint8_t* __restrict__ dst, long long nblocks, float one_arg)
 {
-    __shared__ __align__(128) unsigned char stage[2][4 * kBc1TileRowBytes];
-    __shared__ __align__(8) unsigned long long full[2];
+    __shared__ __align__(128) unsigned char stage[4 * kBc1TileRowBytes];
+    __shared__ __align__(16) f2 columns[48 * kBc1PairThreads];
+    __shared__ __align__(8) unsigned long long full;
     const long long ntiles = (nblocks + kBc1TileBlocks - 1) / kBc1TileBlocks;
-    auto prefetch = [&](long long tile, int buf) {
+    auto prefetch = [&](long long tile) {
         if (tile >= ntiles) return;
         const long long first = tile * kBc1TileBlocks, left = nblocks - first;
-        tma_prefetch_tile(stage[buf], kBc1TileRowBytes, &full[buf], s, first, (int)(left < kBc1TileBlocks ? left : kBc1TileBlocks), 16);
+        tma_prefetch_tile(stage, kBc1TileRowBytes, &full, s, first, (int)(left < kBc1TileBlocks ? left : kBc1TileBlocks), 16);
     };
-    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    if (threadIdx.x == 0) mbar_init(&full, 1);
     __syncthreads();
-    if (threadIdx.x == 0) prefetch(blockIdx.x, 0);
+    if (threadIdx.x == 0) prefetch(blockIdx.x);
+    f2* px = columns + threadIdx.x;
     int it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const int buf = it & 1;
-        if (threadIdx.x == 0) prefetch(tile + gridDim.x, buf ^ 1);      // streams in behind this tile's math
-        mbar_wait(&full[buf], (unsigned)((it >> 1) & 1));
+        mbar_wait(&full, (unsigned)(it & 1));
         const long long first = tile * kBc1TileBlocks;
         const long long ida = first + threadIdx.x, idb = ida + kBc1PairThreads;
         u32 ta[16], tb[16], oa[4], ob[4];
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            const uint4 va = *reinterpret_cast<const uint4*>(stage[buf] + y * kBc1TileRowBytes + threadIdx.x * 16);
-            const uint4 vb = *reinterpret_cast<const uint4*>(stage[buf] + y * kBc1TileRowBytes + (threadIdx.x + kBc1PairThreads) * 16);
+            const uint4 va = *reinterpret_cast<const uint4*>(stage + y * kBc1TileRowBytes + threadIdx.x * 16);
+            const uint4 vb = *reinterpret_cast<const uint4*>(stage + y * kBc1TileRowBytes + (threadIdx.x + kBc1PairThreads) * 16);
             ta[4 * y + 0] = va.x; ta[4 * y + 1] = va.y; ta[4 * y + 2] = va.z; ta[4 * y + 3] = va.w;
             tb[4 * y + 0] = vb.x; tb[4 * y + 1] = vb.y; tb[4 * y + 2] = vb.z; tb[4 * y + 3] = vb.w;
         }
+        __syncthreads();                                               // every thread has read the stage: it may be refilled
+        if (threadIdx.x == 0) prefetch(tile + gridDim.x);
         // (blocks past the end of the surface read stale shared memory: any bit pattern is a valid input, nothing is stored)
-        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob, splat2(one_arg));       // one_arg == 1.0f, see madd2 (itw_device.cuh)
+        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob, px, kBc1PairThreads, splat2(one_arg));       // one_arg == 1.0f, see madd2 (itw_device.cuh)
         if (kAlpha) {
             if (ida < nblocks) reinterpret_cast<uint4*>(dst)[ida] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
             if (idb < nblocks) reinterpret_cast<uint4*>(dst)[idb] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
@@ -314,7 +336,6 @@ __global__ void __launch_bounds__(kBc1PairThreads, kBc1CtasPerSm) bc1_bc3_pair_k
             if (ida < nblocks) reinterpret_cast<uint2*>(dst)[ida] = make_uint2(oa[0], oa[1]);
             if (idb < nblocks) reinterpret_cast<uint2*>(dst)[idb] = make_uint2(ob[0], ob[1]);
         }
-        __syncthreads();                                               // every thread has read stage[buf]: it may be refilled
     }
 }
 #endif

@@ -66,7 +66,8 @@ static void per_block_pair(const rgba_surface* src, uint8_t* dst, int bpb)
         u32 ta[16], tb[16], oa[4], ob[4];
         fetch_rows_rgba8<false>(ta, s, (int)(id % bw), (int)(id / bw));
         fetch_rows_rgba8<false>(tb, s, (int)(idb % bw), (int)(idb / bw));
-        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob, splat2(1.0f));
+        f2 px[48];
+        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob, px, 1, splat2(1.0f));
         memcpy(dst + (size_t)id * bpb, oa, bpb);
         memcpy(dst + (size_t)idb * bpb, ob, bpb);
     }

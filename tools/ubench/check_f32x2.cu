@@ -78,7 +78,8 @@ __global__ void bc1_kernel(const u32* tex, int nblocks, u32* out_scalar, u32* ou
     for (int k = 0; k < 16; k++) { ta[k] = tex[ia * 16 + k]; tb[k] = tex[ib * 16 + k]; }
     bc1_bc3_encode_block<true>(ta, sa);
     bc1_bc3_encode_block<true>(tb, sb);
-    bc1_bc3_encode_pair<true>(ta, tb, oa, ob, splat2(one));
+    f2 px[48];
+    bc1_bc3_encode_pair<true>(ta, tb, oa, ob, px, 1, splat2(one));
     for (int k = 0; k < 4; k++) { out_scalar[ia * 4 + k] = sa[k]; out_scalar[ib * 4 + k] = sb[k]; out_pair[ia * 4 + k] = oa[k]; out_pair[ib * 4 + k] = ob[k]; }
 }
 
