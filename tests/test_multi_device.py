@@ -178,3 +178,21 @@ def test_deferred_mode_reports_the_first_failure_at_flush():
     with pytest.raises(RuntimeError, match="fastSkipTreshold"):
         lib.flush()
     assert np.array_equal(lib.encode("BC7", img, lib.profile("veryfast")), T.run(T.oracle(), "BC7", img, "veryfast"))
+
+
+def test_texture_save_path_over_devices_equals_single_device():
+    """itw_dds_encode_texture (level 0 in host memory -> mips, encode, DDS) fanned over the selected GPUs: the same file."""
+    lib = T.product()
+    n = _devices()
+    cases = [(1024, 1024, 77, None, 1, 0), (2048, 1024, 72, None, 1, 0), (1024, 1024, 99, "veryfast", 1, 0), (1024, 1024, 71, None, 6, 1), (1536, 1024, 78, None, 1, 0)]
+    for (w, h, fmt, prof, items, cube) in cases:
+        tops = [T.synth.mixed_rgba8(h, w, seed=s) for s in range(items)]
+        d = B.DdsDesc(w, h, max(w, h).bit_length(), items, fmt, cube)
+        s = lib.profile(prof) if prof else None
+        want = lib.dds_encode_texture(d, tops, s)
+        try:
+            lib.set_devices(list(range(n)))
+            got = lib.dds_encode_texture(d, tops, s)
+        finally:
+            lib.set_devices([])
+        assert np.array_equal(got, want), (w, h, fmt)
