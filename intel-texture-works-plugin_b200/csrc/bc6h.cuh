@@ -36,7 +36,7 @@ struct Bc6Entry {
 struct Bc6Step;
 struct Bc6Warp {
     const Bc6Step* layout;                        // the 14 header layouts: CTA-shared copy on the device (bc6h_kernel), host table in the emulation
-    float px[kBc6Slots][65];                      // 64 planar floats per block (+1: the same texel of the three slots falls into three banks)
+    float px[kBc6Slots][64];
     float lo[kBc6Slots][3], hi[kBc6Slots][3];
     float max_span[kBc6Slots];
     int max_span_idx[kBc6Slots];

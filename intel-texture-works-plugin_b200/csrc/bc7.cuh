@@ -55,7 +55,6 @@ struct Bc7Params {
     int sel[4];
     int refine[8];
     int skip2, t1, t3, t7, ch0, rch, channels;
-    float one;         // 1.0f, set by the host: the opaque multiplier of madd2 (itw_device.cuh)
 };
 
 constexpr int kBc7Slots = 4;          // blocks per warp batch
@@ -174,225 +173,151 @@ ITW_HD void load_planes(u32 (&P)[4][4], const View& v)
         for (int i = 0; i < 4; i++) P[c][i] = view_plane(v, c, i);
 }
 
+// Power iteration on a packed symmetric matrix [xx xy xz xw yy yz yw zz zw ww]; K:207-229.  The loop is
+// kept rolled on purpose: the kernel is instruction-cache bound and this body runs 8 (or 4) times.
+template <int CH, int kIterations>
+ITW_HD void bc7_power_axis(float (&axis)[4], const float (&m)[10])
+{
+    float v0 = 1.0f, v1 = 1.0f, v2 = 1.0f, v3 = 1.0f;
+    ITW_UNROLL(ITW_BC7_POWER_UNROLL)
+    for (int it = 0; it < kIterations; it++) {
+        float a0, a1, a2, a3 = 0.0f;
+        if (CH == 3) {
+            a0 = m[0] * v0 + m[1] * v1 + m[2] * v2;
+            a1 = m[1] * v0 + m[4] * v1 + m[5] * v2;
+            a2 = m[2] * v0 + m[5] * v1 + m[7] * v2;
+        } else {
+            a0 = m[0] * v0 + m[1] * v1 + m[2] * v2 + m[3] * v3;
+            a1 = m[1] * v0 + m[4] * v1 + m[5] * v2 + m[6] * v3;
+            a2 = m[2] * v0 + m[5] * v1 + m[7] * v2 + m[8] * v3;
+            a3 = m[3] * v0 + m[6] * v1 + m[8] * v2 + m[9] * v3;
+        }
+        v0 = a0; v1 = a1; v2 = a2; v3 = a3;
+        if (it & 1) {                                  // renormalise every other iteration: 1/sqrt, two exact ops
+            float n2 = a0 * a0;
+            n2 += a1 * a1;
+            n2 += a2 * a2;
+            if (CH == 4) n2 += a3 * a3;
+            const float rn = 1.0f / sqrtf(n2);
+            v0 *= rn; v1 *= rn; v2 *= rn; v3 *= rn;
+        }
+    }
+    axis[0] = v0; axis[1] = v1; axis[2] = v2; axis[3] = v3;
+}
+// cov = sum(xy) - sum(x)*sum(y)/n on exact integer moments; K:805-823.  sum(x)*sum(y) < 2^24 is an
+// exact integer, so the division by the count can use the slow-path-free exact quotient.
+template <int CH>
+ITW_HD void bc7_covariance(float (&cov)[10], float (&mean)[4], const int (&st)[15])
+{
+    const float n = (float)st[14], rn = 1.0f / n;
+    float s[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) s[c] = (float)st[10 + c];
+#pragma unroll
+    for (int i = 0; i < 10; i++) cov[i] = 0.0f;
+    cov[0] = (float)st[0] - div_by_rcp(s[0] * s[0], n, rn);
+    cov[1] = (float)st[1] - div_by_rcp(s[0] * s[1], n, rn);
+    cov[2] = (float)st[2] - div_by_rcp(s[0] * s[2], n, rn);
+    cov[4] = (float)st[4] - div_by_rcp(s[1] * s[1], n, rn);
+    cov[5] = (float)st[5] - div_by_rcp(s[1] * s[2], n, rn);
+    cov[7] = (float)st[7] - div_by_rcp(s[2] * s[2], n, rn);
+    if (CH == 4) {
+        cov[3] = (float)st[3] - div_by_rcp(s[0] * s[3], n, rn);
+        cov[6] = (float)st[6] - div_by_rcp(s[1] * s[3], n, rn);
+        cov[8] = (float)st[8] - div_by_rcp(s[2] * s[3], n, rn);
+        cov[9] = (float)st[9] - div_by_rcp(s[3] * s[3], n, rn);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) mean[c] = (c < CH) ? div_by_rcp(s[c], n, rn) : 0.0f;
+}
 // By-value working set of the shape and chain phases: nvcc keeps these small structs in registers across the
 // non-inlined calls, whereas arrays handed over by pointer live in local memory (see bc6h.cuh).
 struct Bc7Seg { float v[8]; };                       // endpoints A (r,g,b,a) and B (r,g,b,a) of one subset
 struct Bc7Packed { u32 dec_a, dec_b, q_a, q_b; };    // decoded A, B and quantised A, B as RGBA bytes
 struct Bc7Search { int err; u32 idx0, idx1; };
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Two subsets per lane on the packed float lanes (FADD2 / FMUL2 / FFMA2): lane x = mask a, lane y = mask b of the SAME
-// block view.  Every lane performs the reference's operations in the reference's order with one rounding each; unfused
-// multiply-adds go through madd2 (itw_device.cuh) because ptxas would contract them.  Integer steps (moments, bit
-// packing) run per lane.  Two fits / quantisations cost ~25 % fewer instructions than two scalar ones.
-// ---------------------------------------------------------------------------------------------------------------------
-struct Bc7SegPair { f2 v[8]; };                       // v[i] = (seg_a.v[i], seg_b.v[i])
-struct Bc7PackedPair { Bc7Packed a, b; };
-
-ITW_HD f2 div_by_rcp2(f2 x, f2 d, f2 nd, f2 rcp_d)     // div_by_rcp per lane; nd = -d
-{
-    const f2 q = mul2(x, rcp_d);
-    return fma2(fma2(q, nd, x), rcp_d, q);             // fma(-q, d, x) == fma(q, -d, x)
-}
-ITW_HD f2 i2f2(int a, int b) { return mk2((float)a, (float)b); }
-
-// cov = sum(xy) - sum(x)*sum(y)/n on exact integer moments, for the moment sets sa (lane x) and sb (lane y); K:805-823.
-// sum(x)*sum(y) < 2^24 is an exact integer, so the division by the count can use the slow-path-free exact quotient.
 template <int CH>
-ITW_HD void bc7_covariance_pair(f2 (&cov)[10], f2 (&mean)[4], const int (&sa)[15], const int (&sb)[15])
-{
-    const f2 n = i2f2(sa[14], sb[14]), nn = mk2(-n.x, -n.y), rn = mk2(1.0f / n.x, 1.0f / n.y);
-    f2 s[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) s[c] = i2f2(sa[10 + c], sb[10 + c]);
-#pragma unroll
-    for (int i = 0; i < 10; i++) cov[i] = splat2(0.0f);
-    // st - sum(x)sum(y)/n: the product is an exact integer below 2^24, the quotient is the FMA-corrected one (bc7_covariance);
-    // the final subtraction is one rounding of st + (-quotient)
-#define ITW_COV2(slot, i, j)                                                                         \
-    {                                                                                                \
-        const f2 quo = div_by_rcp2(mul2(s[i], s[j]), n, nn, rn);                                     \
-        cov[slot] = add2(i2f2(sa[slot], sb[slot]), mk2(-quo.x, -quo.y));                             \
-    }
-    ITW_COV2(0, 0, 0) ITW_COV2(1, 0, 1) ITW_COV2(2, 0, 2) ITW_COV2(4, 1, 1) ITW_COV2(5, 1, 2) ITW_COV2(7, 2, 2)
-    if (CH == 4) { ITW_COV2(3, 0, 3) ITW_COV2(6, 1, 3) ITW_COV2(8, 2, 3) ITW_COV2(9, 3, 3) }
-#undef ITW_COV2
-#pragma unroll
-    for (int c = 0; c < 4; c++) mean[c] = (c < CH) ? div_by_rcp2(s[c], n, nn, rn) : splat2(0.0f);
-}
-// cov * (1/65536) with eps on the diagonal entries selected by diag9 (block_pca_axis: all four, get_pca_bound: not [9])
-ITW_HD void bc7_scale_cov_pair(f2 (&cov)[10], bool diag9, const f2 one)
-{
-    const f2 inv_var = splat2(1.0f / (256.0f * 256.0f)), eps = splat2(0.001f * 0.001f);
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-        const bool diag = (i == 0 || i == 4 || i == 7 || (i == 9 && diag9));
-        cov[i] = diag ? madd2(cov[i], inv_var, eps, one) : mul2(cov[i], inv_var);      // cov *= inv_var; diagonal += eps
-    }
-}
-// Power iteration on a packed symmetric matrix [xx xy xz xw yy yz yw zz zw ww] from (1,1,1,1), renormalised (1/sqrt, two
-// exact ops per lane) every other iteration; K:207-229.  The loop is kept partly rolled: the kernel is instruction-cache bound.
-template <int CH, int kIterations>
-ITW_HD void bc7_power_axis_pair(f2 (&axis)[4], const f2 (&cov)[10], const f2 one)
-{
-    f2 v0 = splat2(1.0f), v1 = v0, v2 = v0, v3 = v0;
-    ITW_UNROLL(ITW_BC7_POWER_UNROLL)
-    for (int it = 0; it < kIterations; it++) {
-        f2 a0, a1, a2, a3 = splat2(0.0f);
-        a0 = madd2(cov[2], v2, madd2(cov[1], v1, mul2(cov[0], v0), one), one);
-        a1 = madd2(cov[5], v2, madd2(cov[4], v1, mul2(cov[1], v0), one), one);
-        a2 = madd2(cov[7], v2, madd2(cov[5], v1, mul2(cov[2], v0), one), one);
-        if (CH == 4) {
-            a0 = madd2(cov[3], v3, a0, one);
-            a1 = madd2(cov[6], v3, a1, one);
-            a2 = madd2(cov[8], v3, a2, one);
-            a3 = madd2(cov[9], v3, madd2(cov[8], v2, madd2(cov[6], v1, mul2(cov[3], v0), one), one), one);
-        }
-        v0 = a0; v1 = a1; v2 = a2; v3 = a3;
-        if (it & 1) {
-            f2 n2 = mul2(a0, a0);
-            n2 = madd2(a1, a1, n2, one);
-            n2 = madd2(a2, a2, n2, one);
-            if (CH == 4) n2 = madd2(a3, a3, n2, one);
-            const f2 r = mk2(1.0f / sqrtf(n2.x), 1.0f / sqrtf(n2.y));
-            v0 = mul2(v0, r); v1 = mul2(v1, r); v2 = mul2(v2, r); v3 = mul2(v3, r);
-        }
-    }
-    axis[0] = v0; axis[1] = v1; axis[2] = v2; axis[3] = v3;
-}
-
-template <int CH>
-ITW_HD void bc7_fit_pair_impl(f2 (&ep)[8], const View& v, u32 mask_a, u32 mask_b, const f2 one)
+ITW_HD void bc7_fit_impl(float (&ep)[8], const View& v, u32 mask)
 {
     u32 P[4][4];
     load_planes(P, v);
-    int sa[15], sb[15];
-    moments_u8(sa, P, mask_a, CH);
-    moments_u8(sb, P, mask_b, CH);
-    f2 cov[10], mean[4], nmean[4], axis[4];
-    bc7_covariance_pair<CH>(cov, mean, sa, sb);
+    int ist[15];
+    moments_u8(ist, P, mask, CH);
+    float cov[10], mean[4], axis[4];
+    bc7_covariance<CH>(cov, mean, ist);
+    const float inv_var = 1.0f / (256.0f * 256.0f);
 #pragma unroll
-    for (int c = 0; c < 4; c++) nmean[c] = mk2(-mean[c].x, -mean[c].y);
-    bc7_scale_cov_pair(cov, true, one);
-    bc7_power_axis_pair<CH, 8>(axis, cov, one);
-    // extreme projections over each lane's own texels; the byte -> float conversion is shared by both lanes
-    f2 lo = splat2(inf_f()), hi = splat2(-inf_f());
+    for (int i = 0; i < 10; i++) cov[i] *= inv_var;
+    const float eps = 0.001f * 0.001f;
+    cov[0] += eps; cov[4] += eps; cov[7] += eps; cov[9] += eps;
+    bc7_power_axis<CH, 8>(axis, cov);
+
+    float lo = inf_f(), hi = -inf_f();
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        f2 d = splat2(0.0f);
+        float d = 0.0f;
 #pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const f2 t = add2(bytes_to_f2(P[c][k >> 2], P[c][k >> 2], k & 3), nmean[c]);     // (float)byte - mean
-            // the reference starts from d = 0 and adds; "0 + x" is x up to the sign of a zero, which min / max and the affine
-            // map below cannot observe.  d is finite (8-bit texels, finite axis), so the reference's (a<b)?a:b equals
-            // fminf / fmaxf: one FMNMX instead of FSETP + FSEL
-            d = (c == 0) ? mul2(axis[0], t) : madd2(axis[c], t, d, one);
+        for (int c = 0; c < CH; c++) d += axis[c] * ((float)((P[c][k >> 2] >> (8 * (k & 3))) & 255u) - mean[c]);
+        // d is finite here (8-bit texels, finite axis), so the reference's (a<b)?a:b equals fminf/fmaxf up to
+        // the sign of a zero, which the affine map below cannot observe: one FMNMX instead of FSETP+FSEL
+        if ((mask >> k) & 1u) {
+            lo = fminf(lo, d);
+            hi = fmaxf(hi, d);
         }
-        if ((mask_a >> k) & 1u) { lo.x = fminf(lo.x, d.x); hi.x = fmaxf(hi.x, d.x); }
-        if ((mask_b >> k) & 1u) { lo.y = fminf(lo.y, d.y); hi.y = fmaxf(hi.y, d.y); }
     }
-    if (hi.x - lo.x < 1.0f) { lo.x -= 0.5f; hi.x += 0.5f; }
-    if (hi.y - lo.y < 1.0f) { lo.y -= 0.5f; hi.y += 0.5f; }
+    if (hi - lo < 1.0f) { lo -= 0.5f; hi += 0.5f; }
 #pragma unroll
     for (int c = 0; c < CH; c++) {
-        const f2 a = madd2(lo, axis[c], mean[c], one), b = madd2(hi, axis[c], mean[c], one);
-        ep[c] = mk2(clamp_sse(a.x, 0.0f, 255.0f), clamp_sse(a.y, 0.0f, 255.0f));
-        ep[4 + c] = mk2(clamp_sse(b.x, 0.0f, 255.0f), clamp_sse(b.y, 0.0f, 255.0f));
+        ep[c] = clamp_sse(lo * axis[c] + mean[c], 0.0f, 255.0f);
+        ep[4 + c] = clamp_sse(hi * axis[c] + mean[c], 0.0f, 255.0f);
     }
 }
-// PCA lines through the texels of mask_a (lane x) and mask_b (lane y); K:834-905.  Components >= channels are zero (F6).
-ITW_HD_NOINLINE Bc7SegPair bc7_fit_pair(const Bc7Block* blk, int rot, int alpha, u32 mask_a, u32 mask_b, int channels, float one)
+// PCA line through the masked texels, clamped to [0,255]; K:834-905.  v[0..3] = A, v[4..7] = B;
+// components >= channels are zero (the reference's never-written slots, rule F6).
+ITW_HD_NOINLINE Bc7Seg bc7_fit(const Bc7Block* blk, int rot, int alpha, u32 mask, int channels)
 {
     const View v{blk, rot, alpha};
-    Bc7SegPair seg;
+    Bc7Seg seg;
 #pragma unroll
-    for (int i = 0; i < 8; i++) seg.v[i] = splat2(0.0f);
-    if (channels == 4) bc7_fit_pair_impl<4>(seg.v, v, mask_a, mask_b, splat2(one));
-    else bc7_fit_pair_impl<3>(seg.v, v, mask_a, mask_b, splat2(one));
+    for (int i = 0; i < 8; i++) seg.v[i] = 0.0f;
+    if (channels == 4) bc7_fit_impl<4>(seg.v, v, mask);
+    else bc7_fit_impl<3>(seg.v, v, mask);
     return seg;
 }
 
-// Quantise two endpoint pairs (lane x / lane y); K:983-1128.  Per lane: dec_a, dec_b = decoded A, B as RGBA bytes, q_a, q_b =
-// quantised A, B as RGBA bytes.  `channels` = components that vote on the p-bit (K:1011-1020); all four components are always
-// produced (a never-written component is quantised from 0, rule F6).  One loop over the 8 components serves all three families:
-//   modes 0,3,6,7  one p-bit per endpoint   K:983-1022   (the vote compares against the RAW quantised value
-//                                                         except in mode 0 -- reference behaviour, K:1003-1009)
-//   mode 1         one p-bit per pair        K:1024-1052  (a single running error sum over both endpoints)
-//   modes 2,4,5    no p-bit                  K:1054-1065
-// Conversions: |ep| < 2^31 always holds here -- the fit clamps to [0,255] and the least-squares solve divides by an exact
-// non-zero INTEGER determinant (bc7_solve), which bounds |ep| by ~1.2e7 -- so the x86 overflow rule of cvt_x86() can never
-// trigger and a plain truncation is identical.  Modes 0-3 never emit a 4th component and their index search ignores it; it only
-// matters when it votes (alpha profiles refining modes 0/3, quirk Q1); otherwise it is skipped (its byte stays 0).  The no-p-bit
-// family is the p-bit formula with scale 1 instead of 1/2 (t*1 + 0.5 rounds once, like t + 0.5) and both candidates equal.
-ITW_HD_NOINLINE Bc7PackedPair bc7_quantise_pair(Bc7SegPair seg, int mode, int channels, float one_arg)
-{
-    const f2 one = splat2(one_arg);
-    const f2 (&ep)[8] = seg.v;
-    const int family = (mode == 1) ? 1 : ((mode == 2 || mode == 4 || mode == 5) ? 2 : 0);
-    const int qbits = (mode == 0 || mode == 2 || mode == 4) ? 5 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 8));
-    const int top = (1 << qbits) - 1;
-    const f2 ftop = splat2((float)top);
-    const int vote_bits = (mode == 0) ? 5 : ((mode == 1) ? 7 : 8);
-    const int votes = (mode == 1) ? 3 : channels;
-    const bool four = !(mode <= 3 && votes <= 3);
-    const bool plain = (family == 2);
-    const f2 half = splat2(plain ? 1.0f : 0.5f);
-    const int step = plain ? 1 : 2, top0 = plain ? top : top - 1;
-    const f2 n255 = splat2(-255.0f), r255 = splat2(1.0f / 255.0f), d255 = splat2(255.0f);
-    u32 cand0[2][2] = {{0u, 0u}, {0u, 0u}}, cand1[2][2] = {{0u, 0u}, {0u, 0u}};         // [endpoint][lane]
-    bool pick1[2][2] = {{false, false}, {false, false}};
-    f2 e0 = splat2(0.0f), e1 = splat2(0.0f);
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        if (family == 0) { e0 = splat2(0.0f); e1 = splat2(0.0f); }
-        u32 c0x = 0u, c1x = 0u, c0y = 0u, c1y = 0u;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            if (c == 3 && !four) continue;
-            const f2 x = ep[4 * i + c];
-            const f2 t = mul2(div_by_rcp2(x, d255, n255, r255), ftop);                 // div255(x) * ftop
-            // trunc(t*half + 0.5) and trunc((t-1)*0.5 + 0.5): the products t*half and (t-1)*0.5 are exact (powers of two), so the
-            // fused form rounds once like the reference's multiply-then-add
-            const f2 y0 = fma2(t, half, splat2(0.5f)), y1 = fma2(add2(t, splat2(-1.0f)), splat2(0.5f), splat2(0.5f));
-            const int v0x = clampi(trunc_i(y0.x) * step, 0, top0), v0y = clampi(trunc_i(y0.y) * step, 0, top0);
-            const int v1px = clampi(trunc_i(y1.x) * 2 + 1, 1, top), v1py = clampi(trunc_i(y1.y) * 2 + 1, 1, top);
-            const int v1x = plain ? v0x : v1px, v1y = plain ? v0y : v1py;
-            c0x |= (u32)v0x << (8 * c); c1x |= (u32)v1x << (8 * c);
-            c0y |= (u32)v0y << (8 * c); c1y |= (u32)v1y << (8 * c);
-            const f2 dv0 = add2(x, i2f2(-expand_bits(v0x, vote_bits), -expand_bits(v0y, vote_bits)));
-            const f2 dv1 = add2(x, i2f2(-expand_bits(v1x, vote_bits), -expand_bits(v1y, vote_bits)));
-            if (c < 3 || votes == 4) { e0 = madd2(dv0, dv0, e0, one); e1 = madd2(dv1, dv1, e1, one); }
-        }
-        pick1[i][0] = !(e0.x < e1.x); pick1[i][1] = !(e0.y < e1.y);
-        cand0[i][0] = c0x; cand1[i][0] = c1x; cand0[i][1] = c0y; cand1[i][1] = c1y;
-    }
-    const int dbits = (mode == 3 || mode == 6) ? 8 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 5));
-    const u32 lowmask = 0x01010101u * (0xFFu >> dbits);
-    Bc7PackedPair out;
-#pragma unroll
-    for (int l = 0; l < 2; l++) {
-        bool p0 = pick1[0][l], p1 = pick1[1][l];
-        if (family == 1) p0 = p1;                                            // decided after both endpoints
-        if (family == 2) p0 = p1 = false;
-        u32 dec[2], qq[2];
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const u32 q = ((i == 0) ? p0 : p1) ? cand1[i][l] : cand0[i][l];
-            const u32 vv = q << (8 - dbits);
-            dec[i] = vv + ((vv >> dbits) & lowmask);
-            qq[i] = q;
-        }
-        const Bc7Packed pk{dec[0], dec[1], qq[0], qq[1]};
-        if (l == 0) out.a = pk; else out.b = pk;
-    }
-    return out;
-}
-
-// Ranking key of a two-subset shape (K:952-971, :1403-1410): sqrt(bound(subset 0) + bound(rest)) * 256, where bound = trace -
-// lambda_max of the subset's covariance after 4 power iterations (K:907-939; eps on three diagonal slots only, K:918-920).
-// The two subsets ride on the packed lanes (x = subset 0, y = full - subset 0).
+// trace - lambda_max of a covariance; K:907-939 (eps on three diagonal slots only, K:918-920)
 template <int CH>
-ITW_HD int bc7_split_key_impl(const Bc7Block* blk, int shape, const f2 one)
+ITW_HD float bc7_residual_bound(float (&cov)[10])
+{
+    const float inv_var = 1.0f / (256.0f * 256.0f);
+#pragma unroll
+    for (int i = 0; i < 10; i++) cov[i] *= inv_var;
+    const float eps = 0.001f * 0.001f;
+    cov[0] += eps; cov[4] += eps; cov[7] += eps;
+    float axis[4];
+    bc7_power_axis<CH, 4>(axis, cov);
+    float mv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (CH == 3) {
+        mv[0] = cov[0] * axis[0] + cov[1] * axis[1] + cov[2] * axis[2];
+        mv[1] = cov[1] * axis[0] + cov[4] * axis[1] + cov[5] * axis[2];
+        mv[2] = cov[2] * axis[0] + cov[5] * axis[1] + cov[7] * axis[2];
+    } else {
+        mv[0] = cov[0] * axis[0] + cov[1] * axis[1] + cov[2] * axis[2] + cov[3] * axis[3];
+        mv[1] = cov[1] * axis[0] + cov[4] * axis[1] + cov[5] * axis[2] + cov[6] * axis[3];
+        mv[2] = cov[2] * axis[0] + cov[5] * axis[1] + cov[7] * axis[2] + cov[8] * axis[3];
+        mv[3] = cov[3] * axis[0] + cov[6] * axis[1] + cov[8] * axis[2] + cov[9] * axis[3];
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CH; c++) sum += sq(mv[c]);
+    float bound = cov[0] + cov[4] + cov[7];
+    if (CH == 4) bound += cov[9];
+    bound -= sqrtf(sum);
+    return max_sse(bound, 0.0f);
+}
+// Ranking key of a two-subset shape (K:952-971, :1403-1410); subset 1 = full - subset 0
+template <int CH>
+ITW_HD int bc7_split_key_impl(const Bc7Block* blk, int shape)
 {
     const View v{blk, 3, 1};
     u32 P[4][4];
@@ -402,34 +327,89 @@ ITW_HD int bc7_split_key_impl(const Bc7Block* blk, int shape, const f2 one)
     moments_u8(part, P, (u32)shape_mask(shape, 0), CH);
 #pragma unroll
     for (int i = 0; i < 15; i++) rest[i] = full[i] - part[i];            // exact: the reference subtracts exact floats
-    f2 cov[10], mean[4], axis[4];
-    bc7_covariance_pair<CH>(cov, mean, part, rest);
-    bc7_scale_cov_pair(cov, false, one);
-    bc7_power_axis_pair<CH, 4>(axis, cov, one);
-    f2 mv[4];
-    mv[0] = madd2(cov[2], axis[2], madd2(cov[1], axis[1], mul2(cov[0], axis[0]), one), one);
-    mv[1] = madd2(cov[5], axis[2], madd2(cov[4], axis[1], mul2(cov[1], axis[0]), one), one);
-    mv[2] = madd2(cov[7], axis[2], madd2(cov[5], axis[1], mul2(cov[2], axis[0]), one), one);
-    mv[3] = splat2(0.0f);
-    if (CH == 4) {
-        mv[0] = madd2(cov[3], axis[3], mv[0], one);
-        mv[1] = madd2(cov[6], axis[3], mv[1], one);
-        mv[2] = madd2(cov[8], axis[3], mv[2], one);
-        mv[3] = madd2(cov[9], axis[3], madd2(cov[8], axis[2], madd2(cov[6], axis[1], mul2(cov[3], axis[0]), one), one), one);
-    }
-    f2 sum = mul2(mv[0], mv[0]);                                         // 0 + x dropped: a square is never -0
-    sum = madd2(mv[1], mv[1], sum, one);
-    sum = madd2(mv[2], mv[2], sum, one);
-    if (CH == 4) sum = madd2(mv[3], mv[3], sum, one);
-    f2 bound = add2(add2(cov[0], cov[4]), cov[7]);
-    if (CH == 4) bound = add2(bound, cov[9]);
-    bound = add2(bound, mk2(-sqrtf(sum.x), -sqrtf(sum.y)));
-    const float b = max_sse(bound.x, 0.0f) + max_sse(bound.y, 0.0f);      // (0 + b1) + b2; b1 is +0 or positive
+    float c1[10], c2[10], mean[4];
+    bc7_covariance<CH>(c1, mean, part);
+    bc7_covariance<CH>(c2, mean, rest);
+    float b = 0.0f;
+    b += bc7_residual_bound<CH>(c1);
+    b += bc7_residual_bound<CH>(c2);
     return shape + (int)((unsigned)cvt_x86(sqrtf(b) * 256.0f) * 64u);
 }
-ITW_HD_NOINLINE int bc7_split_key(const Bc7Block* blk, int shape, int channels, float one)
+ITW_HD_NOINLINE int bc7_split_key(const Bc7Block* blk, int shape, int channels)
 {
-    return (channels == 4) ? bc7_split_key_impl<4>(blk, shape, splat2(one)) : bc7_split_key_impl<3>(blk, shape, splat2(one));
+    return (channels == 4) ? bc7_split_key_impl<4>(blk, shape) : bc7_split_key_impl<3>(blk, shape);
+}
+
+// Quantise one endpoint pair; K:983-1128.  out[0],out[1] = decoded A,B as RGBA bytes, out[2],out[3] =
+// quantised A,B as RGBA bytes.  `channels` = components that vote on the p-bit (K:1011-1020); all four
+// components are always produced (a never-written component is quantised from 0, rule F6).
+// One rolled loop over the 8 components serves all three families:
+//   modes 0,3,6,7  one p-bit per endpoint   K:983-1022   (the vote compares against the RAW quantised value
+//                                                         except in mode 0 -- reference behaviour, K:1003-1009)
+//   mode 1         one p-bit per pair        K:1024-1052  (a single running error sum over both endpoints)
+//   modes 2,4,5    no p-bit                  K:1054-1065
+ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
+{
+    const float (&ep)[8] = seg.v;
+    const int family = (mode == 1) ? 1 : ((mode == 2 || mode == 4 || mode == 5) ? 2 : 0);
+    // stored bits per component including the p-bit: 2^qbits - 1 is K's `levels2` (p-bit modes) or `levels-1`
+    const int qbits = (mode == 0 || mode == 2 || mode == 4) ? 5 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 8));
+    const int top = (1 << qbits) - 1;
+    const float ftop = (float)top;
+    const int vote_bits = (mode == 0) ? 5 : ((mode == 1) ? 7 : 8);       // expand_bits(v, 8) == v
+    const int votes = (mode == 1) ? 3 : channels;
+    // Conversions: |ep| < 2^31 always holds here -- the fit clamps to [0,255] and the least-squares
+    // solve divides by an exact non-zero INTEGER determinant (bc7_solve), which bounds |ep| by ~1.2e7 --
+    // so the x86 overflow rule of cvt_x86() can never trigger and a plain truncation is identical.
+    // t*0.5 and (t-1)*0.5 are exact (power-of-two scaling), so fusing the +0.5 rounds once, exactly like
+    // the reference's separate multiply and add.
+    // Modes 0-3 never emit a 4th component and their index search ignores it; it only matters when it votes
+    // (alpha profiles refining modes 0/3, quirk Q1).  Otherwise it is skipped (its byte stays 0).
+    const bool four = !(mode <= 3 && votes <= 3);
+    // Branch-free per component: the no-p-bit family is the p-bit formula with scale 1 instead of 1/2 (t*1 + 0.5 rounds
+    // once, like t + 0.5) and both candidates equal.  Components 0..2 always take part and always vote (votes >= 3);
+    // only the fourth is conditional.
+    const bool plain = (family == 2);
+    const float half = plain ? 1.0f : 0.5f;
+    const int step = plain ? 1 : 2, top0 = plain ? top : top - 1;
+    u32 cand0[2] = {0u, 0u}, cand1[2] = {0u, 0u};
+    bool pick1[2] = {false, false};
+    float e0 = 0.0f, e1 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        if (family == 0) { e0 = 0.0f; e1 = 0.0f; }
+        u32 c0 = 0u, c1 = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (c == 3 && !four) continue;
+            const float x = ep[4 * i + c];
+            const float t = div255(x) * ftop;
+            const int v0 = clampi(trunc_i(fma_rn(t, half, 0.5f)) * step, 0, top0);
+            const int v1p = clampi(trunc_i(fma_rn(t - 1.0f, 0.5f, 0.5f)) * 2 + 1, 1, top);      // ((t - 1)/2 + 0.5) truncated, *2 + 1
+            const int v1 = plain ? v0 : v1p;
+            c0 |= (u32)v0 << (8 * c);
+            c1 |= (u32)v1 << (8 * c);
+            const float d0 = sq(x - (float)expand_bits(v0, vote_bits)), d1 = sq(x - (float)expand_bits(v1, vote_bits));
+            if (c < 3 || votes == 4) { e0 += d0; e1 += d1; }
+        }
+        const bool p = !(e0 < e1);
+        if (i == 0) { cand0[0] = c0; cand1[0] = c1; pick1[0] = p; }
+        else        { cand0[1] = c0; cand1[1] = c1; pick1[1] = p; }
+    }
+    if (family == 1) pick1[0] = pick1[1];                                // decided after both endpoints
+    if (family == 2) pick1[0] = pick1[1] = false;
+    // decode all four bytes at once (K:1093-1122): v << (8-d) | that >> d, bytewise
+    const int dbits = (mode == 3 || mode == 6) ? 8 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 5));
+    const u32 lowmask = 0x01010101u * (0xFFu >> dbits);
+    u32 dec[2], qq[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const u32 q = pick1[i] ? cand1[i] : cand0[i];
+        const u32 vv = q << (8 - dbits);
+        dec[i] = vv + ((vv >> dbits) & lowmask);
+        qq[i] = q;
+    }
+    return Bc7Packed{dec[0], dec[1], qq[0], qq[1]};
 }
 
 // Integer interpolation of two packed RGBA endpoints with BC7 weight w (K:1172: ((64-w)a+wb+32)/64
@@ -808,29 +788,17 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
         Q[j][0] = Q[j][1] = 0u;
         ends[2 * j] = ends[2 * j + 1] = 0u;
     }
-    // Subsets are handled two at a time on the packed lanes (subsets 0 and 1; a third or an only subset rides alone, its
-    // lane y repeating lane x).  Modes 4-6 have ONE subset: tail_a / tail_b carry its ep[3], ep[7] between iterations (quirk Q5).
-    float tail_a = 0.0f, tail_b = 0.0f;
-    const u32 m0 = (role.kind == 0) ? (u32)shape_mask(role.shape, 0) : 0xFFFFu;
-    const u32 m1 = (role.kind == 0 && pairs >= 2) ? (u32)shape_mask(role.shape, 1) : m0;     // one subset: lane y repeats lane x
-    const u32 m2 = (role.kind == 0 && pairs == 3) ? (u32)shape_mask(role.shape, 2) : m0;
-    {
-        Bc7SegPair seg = bc7_fit_pair(blk, rot, alpha, m0, m1, channels, P.one);             // slots >= channels are zero (F6)
-        if (role.kind == 2 && channels == 3) seg.v[3] = seg.v[7] = splat2(255.0f);           // K:1664-1667
-        const Bc7PackedPair pk = bc7_quantise_pair(seg, mode, channels, P.one);
-        tail_a = (float)(pk.a.dec_a >> 24); tail_b = (float)(pk.a.dec_b >> 24);
-        ends[0] = pk.a.dec_a; ends[1] = pk.a.dec_b;
-        Q[0][0] = pk.a.q_a; Q[0][1] = pk.a.q_b;
-        if (pairs >= 2) {
-            ends[2] = pk.b.dec_a; ends[3] = pk.b.dec_b;
-            Q[1][0] = pk.b.q_a; Q[1][1] = pk.b.q_b;
-        }
-    }
-    if (pairs == 3) {
-        const Bc7SegPair seg = bc7_fit_pair(blk, rot, alpha, m2, m2, channels, P.one);
-        const Bc7PackedPair pk = bc7_quantise_pair(seg, mode, channels, P.one);
-        ends[4] = pk.a.dec_a; ends[5] = pk.a.dec_b;
-        Q[2][0] = pk.a.q_a; Q[2][1] = pk.a.q_b;
+    float tail_a = 0.0f, tail_b = 0.0f;                          // ep[3], ep[7] carried between iterations (quirk Q5)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (j >= pairs) continue;
+        const u32 mask = (role.kind == 0) ? (u32)shape_mask(role.shape, j) : 0xFFFFu;
+        Bc7Seg seg = bc7_fit(blk, rot, alpha, mask, channels);   // slots >= channels are zero (F6)
+        if (role.kind == 2 && channels == 3) seg.v[3] = seg.v[7] = 255.0f;     // K:1664-1667
+        const Bc7Packed pk = bc7_quantise(seg, mode, channels);
+        tail_a = (float)(pk.dec_a >> 24); tail_b = (float)(pk.dec_b >> 24);
+        ends[2 * j] = pk.dec_a; ends[2 * j + 1] = pk.dec_b;
+        Q[j][0] = pk.q_a; Q[j][1] = pk.q_b;
     }
     Bc7Search best = bc7_assign(W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends[0], ends[1], ends[2], ends[3], ends[4],
                                 ends[5], chmask);
@@ -840,36 +808,18 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
         u32 nQ[3][2];
 #pragma unroll
         for (int j = 0; j < 3; j++) nQ[j][0] = nQ[j][1] = 0u;
-        {
-            const Bc7Seg sa = bc7_solve(blk, rot, alpha, bits, best.idx0, best.idx1, m0, channels);
-            Bc7SegPair seg;
 #pragma unroll
-            for (int i = 0; i < 8; i++) seg.v[i] = splat2(sa.v[i]);
-            if (pairs >= 2) {
-                const Bc7Seg sb = bc7_solve(blk, rot, alpha, bits, best.idx0, best.idx1, m1, channels);
-#pragma unroll
-                for (int i = 0; i < 8; i++) seg.v[i].y = sb.v[i];
-            }
+        for (int j = 0; j < 3; j++) {
+            if (j >= pairs) continue;
+            const u32 mask = (role.kind == 0) ? (u32)shape_mask(role.shape, j) : 0xFFFFu;
+            Bc7Seg seg = bc7_solve(blk, rot, alpha, bits, best.idx0, best.idx1, mask, channels);
             // K's arrays live across iterations in modes 4-6: a fourth slot the solve does not write keeps the
             // previous iteration's decoded value
-            if (role.kind != 0 && channels < 4) { seg.v[3] = splat2(tail_a); seg.v[7] = splat2(tail_b); }
-            const Bc7PackedPair pk = bc7_quantise_pair(seg, mode, vote_refine, P.one);
-            tail_a = (float)(pk.a.dec_a >> 24); tail_b = (float)(pk.a.dec_b >> 24);
-            ends[0] = pk.a.dec_a; ends[1] = pk.a.dec_b;
-            nQ[0][0] = pk.a.q_a; nQ[0][1] = pk.a.q_b;
-            if (pairs >= 2) {
-                ends[2] = pk.b.dec_a; ends[3] = pk.b.dec_b;
-                nQ[1][0] = pk.b.q_a; nQ[1][1] = pk.b.q_b;
-            }
-        }
-        if (pairs == 3) {
-            const Bc7Seg sc = bc7_solve(blk, rot, alpha, bits, best.idx0, best.idx1, m2, channels);
-            Bc7SegPair seg;
-#pragma unroll
-            for (int i = 0; i < 8; i++) seg.v[i] = splat2(sc.v[i]);
-            const Bc7PackedPair pk = bc7_quantise_pair(seg, mode, vote_refine, P.one);
-            ends[4] = pk.a.dec_a; ends[5] = pk.a.dec_b;
-            nQ[2][0] = pk.a.q_a; nQ[2][1] = pk.a.q_b;
+            if (role.kind != 0 && channels < 4) { seg.v[3] = tail_a; seg.v[7] = tail_b; }
+            const Bc7Packed pk = bc7_quantise(seg, mode, vote_refine);
+            tail_a = (float)(pk.dec_a >> 24); tail_b = (float)(pk.dec_b >> 24);
+            ends[2 * j] = pk.dec_a; ends[2 * j + 1] = pk.dec_b;
+            nQ[j][0] = pk.q_a; nQ[j][1] = pk.q_b;
         }
         const Bc7Search found = bc7_assign(W.palette, lane, blk, rot, alpha, bits, pairs, pattern, ends[0], ends[1], ends[2], ends[3],
                                            ends[4], ends[5], chmask);
@@ -933,7 +883,7 @@ ITW_HD void bc7_phase_planes(int lane, Bc7Warp& W)
     }
 }
 // One shape, both modes of a mode-slot pair (ma, mb): fits once, quantises and searches per mode.
-ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, int n, int ma, bool do_a, int mb, bool do_b, float one)
+ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, int n, int ma, bool do_a, int mb, bool do_b)
 {
     const Bc7Block* blk = &W.blk[slot];
     const int mode_a = bc7_slot_mode(ma), mode_b = bc7_slot_mode(mb);
@@ -943,15 +893,18 @@ ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, i
     u32 ends_a[6], ends_b[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) ends_a[i] = ends_b[i] = 0u;
-    // two subsets (modes 1, 3, 7): both fitted and quantised side by side on the packed lanes
-    const Bc7SegPair seg = bc7_fit_pair(blk, 3, 1, (u32)shape_mask(shape, 0), (u32)shape_mask(shape, 1), channels, one);
-    if (do_a) {
-        const Bc7PackedPair pk = bc7_quantise_pair(seg, mode_a, channels, one);
-        ends_a[0] = pk.a.dec_a; ends_a[1] = pk.a.dec_b; ends_a[2] = pk.b.dec_a; ends_a[3] = pk.b.dec_b;
-    }
-    if (do_b) {
-        const Bc7PackedPair pk = bc7_quantise_pair(seg, mode_b, channels, one);
-        ends_b[0] = pk.a.dec_a; ends_b[1] = pk.a.dec_b; ends_b[2] = pk.b.dec_a; ends_b[3] = pk.b.dec_b;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (j >= pairs) continue;
+        const Bc7Seg seg = bc7_fit(blk, 3, 1, (u32)shape_mask(shape, j), channels);
+        if (do_a) {
+            const Bc7Packed pk = bc7_quantise(seg, mode_a, channels);
+            ends_a[2 * j] = pk.dec_a; ends_a[2 * j + 1] = pk.dec_b;
+        }
+        if (do_b) {
+            const Bc7Packed pk = bc7_quantise(seg, mode_b, channels);
+            ends_b[2 * j] = pk.dec_a; ends_b[2 * j + 1] = pk.dec_b;
+        }
     }
     const u32 pattern = shape_pattern(shape);
     if (do_a)
@@ -971,21 +924,20 @@ ITW_HD void bc7_phase_masks3(int lane, Bc7Warp& W, const Bc7Params& P, int half)
 {
     const int ca = bc7_slot_count(P, 0), cb = bc7_slot_count(P, 1);
     const int nmask = (cb > 0) ? ITW_MASK3_COUNT : ITW_MASK3_FIRST;
-    const int npair = nmask / 2;                              // both counts are even: masks 2t and 2t+1 share a lane
     const int nslots = mini(maxi(W.nvalid - 2 * half, 0), 2);
-    for (int t = lane; t < nslots * npair; t += 32) {
-        const int s = t / npair, u = 2 * (t - s * npair);
+    for (int t = lane; t < nslots * nmask; t += 32) {
+        const int s = t / nmask, u = t - s * nmask;
         const Bc7Block* blk = &W.blk[2 * half + s];
-        const Bc7SegPair seg = bc7_fit_pair(blk, 3, 1, (u32)ITW_TABLE(mask3_unique)[u], (u32)ITW_TABLE(mask3_unique)[u + 1], 3, P.one);
+        const Bc7Seg seg = bc7_fit(blk, 3, 1, (u32)ITW_TABLE(mask3_unique)[u], 3);
         if (cb > 0) {
-            const Bc7PackedPair pk = bc7_quantise_pair(seg, 2, 3, P.one);
-            W.ends3_mode2[s][u][0] = pk.a.dec_a;     W.ends3_mode2[s][u][1] = pk.a.dec_b;
-            W.ends3_mode2[s][u + 1][0] = pk.b.dec_a; W.ends3_mode2[s][u + 1][1] = pk.b.dec_b;
+            const Bc7Packed pk = bc7_quantise(seg, 2, 3);
+            W.ends3_mode2[s][u][0] = pk.dec_a;
+            W.ends3_mode2[s][u][1] = pk.dec_b;
         }
         if (ca > 0 && u < ITW_MASK3_FIRST) {
-            const Bc7PackedPair pk = bc7_quantise_pair(seg, 0, 3, P.one);
-            W.ends3_mode0[s][u][0] = pk.a.dec_a;     W.ends3_mode0[s][u][1] = pk.a.dec_b;
-            W.ends3_mode0[s][u + 1][0] = pk.b.dec_a; W.ends3_mode0[s][u + 1][1] = pk.b.dec_b;
+            const Bc7Packed pk = bc7_quantise(seg, 0, 3);
+            W.ends3_mode0[s][u][0] = pk.dec_a;
+            W.ends3_mode0[s][u][1] = pk.dec_b;
         }
     }
 }
@@ -1023,7 +975,7 @@ ITW_HD void bc7_phase_shapes(int lane, Bc7Warp& W, const Bc7Params& P, int ma, i
         int slot, n;
         if (t < nboth) { slot = t / both; n = t - slot * both; }
         else { const int u = t - nboth, rest = count - both; slot = u / rest; n = both + (u - slot * rest); }
-        bc7_eval_shape(W, lane, slot, bc7_slot_shape(W, slot, ma, n), n, ma, n < ca, mb, n < cb, P.one);
+        bc7_eval_shape(W, lane, slot, bc7_slot_shape(W, slot, ma, n), n, ma, n < ca, mb, n < cb);
     }
 }
 // split-bound keys of the 64 two-subset shapes; set 0 = RGB (modes 1,3), set 1 = profile channels (mode 7)
@@ -1037,7 +989,7 @@ ITW_HD void bc7_phase_keys(int lane, Bc7Warp& W, const Bc7Params& P, int set)
     const int channels = (set == 0) ? 3 : P.channels;
     for (int t = lane; t < W.nvalid * 64; t += 32) {
         const int slot = t >> 6, shape = t & 63;
-        W.keys[slot][shape] = bc7_split_key(&W.blk[slot], shape, channels, P.one);
+        W.keys[slot][shape] = bc7_split_key(&W.blk[slot], shape, channels);
     }
 }
 ITW_HD void bc7_phase_rank(int lane, Bc7Warp& W, int set)

@@ -22,7 +22,6 @@
 
 #include "../../include/itw_bcn.h"
 #include "bc4_bc5.cuh"
-#include "bc1_pair.cuh"
 #include "mips.cuh"
 #include "decode.cuh"
 #include "frontend.cuh"
@@ -178,21 +177,13 @@ int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* setting
     const unsigned grid1 = (unsigned)((nblocks + 127) / 128);
     switch (format) {
         case ITW_FORMAT_BC1:
-        case ITW_FORMAT_BC3: {
-            // 16-byte aligned rows: the persistent TMA-staged kernel, two blocks per thread on packed float lanes (bc1_pair.cuh);
-            // anything else: one block per thread with byte-safe loads (bc1_bc3.cuh)
-            const long long tiles = (nblocks + kBc1TileBlocks - 1) / kBc1TileBlocks;
-            const long long cap = (long long)tls.sm_count * kBc1CtasPerSm;
-            const unsigned gridp = (unsigned)(tiles < cap ? tiles : cap);
-            if (format == ITW_FORMAT_BC1) {
-                if (vec16) bc1_bc3_pair_kernel<false><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks, 1.0f);
-                else       bc1_bc3_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
-            } else {
-                if (vec16) bc1_bc3_pair_kernel<true><<<gridp, kBc1PairThreads, 0, stream>>>(v, d_dst, nblocks, 1.0f);
-                else       bc1_bc3_kernel<true, false><<<grid1, 128, 0, stream>>>(v, d_dst);
-            }
+            if (vec16) bc1_bc3_kernel<false, true><<<grid1, 128, 0, stream>>>(v, d_dst);
+            else       bc1_bc3_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);
             break;
-        }
+        case ITW_FORMAT_BC3:
+            if (vec16) bc1_bc3_kernel<true, true><<<grid1, 128, 0, stream>>>(v, d_dst);
+            else       bc1_bc3_kernel<true, false><<<grid1, 128, 0, stream>>>(v, d_dst);
+            break;
         case ITW_FORMAT_BC4:
             if (vec16) bc4_bc5_kernel<false, true><<<grid1, 128, 0, stream>>>(v, d_dst);
             else       bc4_bc5_kernel<false, false><<<grid1, 128, 0, stream>>>(v, d_dst);

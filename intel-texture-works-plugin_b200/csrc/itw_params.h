@@ -20,7 +20,6 @@ inline Bc7Params bc7_params_from(const bc7_enc_settings& s)
     p.ch0 = s.mode45_channel0;
     p.rch = s.refineIterations_channel;
     p.channels = s.channels;
-    p.one = 1.0f;
     return p;
 }
 // The reference indexes 64-entry candidate lists with these counts and has undefined behaviour

@@ -8,7 +8,6 @@
 // is loaded only by tests.  The product library never contains or calls this code.
 #include <cstring>
 #include "../../intel-texture-works-plugin_b200/csrc/bc4_bc5.cuh"
-#include "../../intel-texture-works-plugin_b200/csrc/bc1_pair.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/itw_params.h"
 #include "../../intel-texture-works-plugin_b200/csrc/mips.cuh"
 #include "../../intel-texture-works-plugin_b200/csrc/decode.cuh"
@@ -54,28 +53,7 @@ static void emu_decode_as(const uint8_t* blocks, uint8_t* dst, int w, int h, int
         }
 }
 
-// the two-blocks-per-thread form (csrc/bc1_pair.cuh): consecutive blocks are paired as lanes x / y, an odd last block pairs with itself
-template <bool kAlpha>
-static void per_block_pair(const rgba_surface* src, uint8_t* dst, int bpb)
-{
-    SurfaceView s = view_of(src);
-    const int bw = s.width / 4, bh = s.height / 4;
-    const long long n = (long long)bw * bh;
-    for (long long id = 0; id < n; id += 2) {
-        const long long idb = (id + 1 < n) ? id + 1 : id;
-        u32 ta[16], tb[16], oa[4], ob[4];
-        fetch_rows_rgba8<false>(ta, s, (int)(id % bw), (int)(id / bw));
-        fetch_rows_rgba8<false>(tb, s, (int)(idb % bw), (int)(idb / bw));
-        f2 px[48];
-        bc1_bc3_encode_pair<kAlpha>(ta, tb, oa, ob, px, 1, splat2(1.0f));
-        memcpy(dst + (size_t)id * bpb, oa, bpb);
-        memcpy(dst + (size_t)idb * bpb, ob, bpb);
-    }
-}
-
 extern "C" {
-void emu_pair_CompressBlocksBC1(const rgba_surface* src, uint8_t* dst) { per_block_pair<false>(src, dst, 8); }
-void emu_pair_CompressBlocksBC3(const rgba_surface* src, uint8_t* dst) { per_block_pair<true>(src, dst, 16); }
 void emu_CompressBlocksBC1(const rgba_surface* src, uint8_t* dst)
 { per_block(src, dst, 8, [](const u32 (&t)[16], u32 (&o)[4]) { bc1_bc3_encode_block<false>(t, o); }); }
 void emu_CompressBlocksBC3(const rgba_surface* src, uint8_t* dst)

@@ -28,22 +28,3 @@ def test_ragged_batches_and_strides(fmt, prof):
         got = T.run(T.emu(), fmt, img, prof)
         want = T.run(T.oracle(), fmt, np.ascontiguousarray(img), prof)
         assert np.array_equal(got, want), (h, w, pad)
-
-
-@pytest.mark.parametrize("fmt", ["BC1", "BC3"])
-def test_two_blocks_per_thread_form_bit_exact(fmt):
-    """csrc/bc1_pair.cuh (two blocks on the packed float lanes, magic-number conversions, fused exact products) against the
-    oracle: the whole 64x64 corpus, random pairs, and an odd block count."""
-    from itw_testlib import binding
-    T.emu()                                                   # builds the library
-    emu_pair = binding.EncoderApi(T.EMU_SO, "emu_pair_")
-    bpb = binding.FORMATS[fmt][1]
-    for name, img in T.corpus_for(fmt, 64).items():
-        assert T.differing_blocks(T.run(emu_pair, fmt, img, None), T.run(T.oracle(), fmt, img, None), bpb) == 0, name
-    rng = np.random.default_rng(11)
-    img = rng.integers(0, 256, (12, 20, 4), dtype=np.uint8)   # 15 blocks: odd
-    assert np.array_equal(T.run(emu_pair, fmt, img, None), T.run(T.oracle(), fmt, img, None))
-    big = rng.integers(0, 256, (256, 256, 4), dtype=np.uint8)
-    big[:64] = (rng.integers(0, 4, (64, 256, 4)) * 85).astype(np.uint8)          # few levels: index ties, all-equal indices
-    big[64:96, :, :3] = big[64:96, :1, :1]                                         # flat rows: p0 == p1 (NaN path)
-    assert T.differing_blocks(T.run(emu_pair, fmt, big, None), T.run(T.oracle(), fmt, big, None), bpb) == 0

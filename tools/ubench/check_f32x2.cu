@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../../intel-texture-works-plugin_b200/csrc/bc1_pair.cuh"
+#include "experiments/bc1_pair.cuh"
 
 using namespace itw;
 

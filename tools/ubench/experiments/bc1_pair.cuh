@@ -1,4 +1,5 @@
-// bc1_pair.cuh -- BC1 / BC3 encoder, TWO blocks per thread on Blackwell's packed float lanes
+// bc1_pair.cuh -- EXPERIMENT, not part of the product (DESIGN.md section 4 reports the measurements): BC1 / BC3 encoder,
+// TWO blocks per thread on Blackwell's packed float lanes
 // (reference: kernel.ispc:231-614, cited as K:line; the one-block form of the same arithmetic is bc1_bc3.cuh).
 //
 // Why.  One 4x4 block costs ~1.5 k scalar instructions against 72 bytes of traffic, and three quarters of them are
@@ -16,9 +17,91 @@
 // Staging: a persistent CTA fetches tiles of 2 x blockDim consecutive blocks with the TMA engine (cp.async.bulk, mbarrier)
 // into a 4-row shared-memory tile; the next tile streams in while the current one is being encoded from registers.
 #pragma once
-#include "bc1_bc3.cuh"
+#include "../../../intel-texture-works-plugin_b200/csrc/bc1_bc3.cuh"
 
 namespace itw {
+
+// ---- two independent float lanes per instruction (sm_100a: FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.rn.f32x2) ----------
+// Blackwell issues ONE instruction for two IEEE binary32 operations on a 64-bit register pair.  Each lane is an ordinary
+// round-to-nearest-even add / multiply (or fused multiply-add), so a pair op gives exactly the two results the scalar
+// ops would: the float model of this file is unchanged, the issue slots are halved.  The encoders use the lanes for two
+// independent blocks (BC1/BC3) or two independent quantities of one block.  fma2 FUSES: it is used only where the product
+// is proved exact (then fused == multiply-then-add), like fma_rn above.  Host (tests/emu): plain scalar operations.
+#if defined(__CUDACC__)
+typedef float2 f2;
+#else
+struct f2 { float x, y; };
+#endif
+ITW_HD f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+ITW_HD f2 splat2(float a) { return mk2(a, a); }
+ITW_HD f2 add2(f2 a, f2 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    return mk2(a.x + b.x, a.y + b.y);
+#endif
+}
+ITW_HD f2 mul2(f2 a, f2 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    return mk2(a.x * b.x, a.y * b.y);
+#endif
+}
+ITW_HD f2 fma2(f2 a, f2 b, f2 c)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+// RN(RN(a*b) + c) per lane -- multiply, then add, two roundings (the reference's unfused expression).
+// ptxas of CUDA 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into ONE FFMA2 whenever the product has no other use, even with
+// --fmad false and although both instructions carry an explicit .rn (scalar mul.rn / add.rn are never contracted; checked with
+// cuobjdump, see tools/ubench/check_f32x2.cu).  A fused multiply-add rounds once and changes results.  The addition is therefore
+// issued as an FFMA2 whose multiplier `one` is a KERNEL ARGUMENT that only the host knows to be 1.0: p * 1 is exact, so
+// fma(p, one, c) rounds exactly like p + c, and a product that feeds the multiplicand of an FMA cannot be contracted into it.
+// Same instruction count as the packed multiply + packed add it replaces.
+ITW_HD f2 madd2(f2 a, f2 b, f2 c, f2 one) { return fma2(mul2(a, b), one, c); }
+// a + b rounded TOWARDS ZERO per lane (the float->int "magic number" conversion below)
+ITW_HD f2 add2_rz(f2 a, f2 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rz(a, b);
+#else
+    // a, b >= 0 wherever this is used: towards zero == the double sum truncated to 24 bits == nextafter correction of RN
+    f2 r;
+    const float in[2][2] = {{a.x, b.x}, {a.y, b.y}};
+    float out[2];
+    for (int i = 0; i < 2; i++) {
+        const double exact = (double)in[i][0] + (double)in[i][1];       // exact: both operands are floats of similar magnitude
+        float s = (float)exact;
+        if ((double)s > exact) s = nextafterf(s, 0.0f);
+        out[i] = s;
+    }
+    r.x = out[0]; r.y = out[1];
+    return r;
+#endif
+}
+ITW_HD f2 min2(f2 a, f2 b) { return mk2(fminf(a.x, b.x), fminf(a.y, b.y)); }      // finite / NaN-first operands only (see callers)
+ITW_HD f2 max2(f2 a, f2 b) { return mk2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+// byte `c` of each of two packed words as floats, without the conversion pipe: PRMT drops the byte into the mantissa of
+// 2^23 (0x4B000000 | byte == 8388608 + byte exactly), one packed subtraction removes the 2^23 (exact).
+ITW_HD f2 bytes_to_f2(u32 wa, u32 wb, int c)
+{
+#if defined(__CUDA_ARCH__)
+    const u32 sel = 0x7440u | (u32)c;                       // result bytes: [byte c of w, 00, 00, 4B]
+    const float ma = __uint_as_float(__byte_perm(wa, 0x4B000000u, sel)), mb = __uint_as_float(__byte_perm(wb, 0x4B000000u, sel));
+    return __fadd2_rn(make_float2(ma, mb), make_float2(-8388608.0f, -8388608.0f));
+#else
+    return mk2((float)((wa >> (8 * c)) & 255u), (float)((wb >> (8 * c)) & 255u));
+#endif
+}
+
+
 
 // v -> clamp((int)v, 0, top) for both lanes WITHOUT F2I, top = 3 or 7.  (int)v truncates; clamping first to [0, top + 0.5]
 // cannot change the clamped result, NaN (p0 == p1, K:321-336: INT_MIN -> 0) becomes 0 through fmaxf.  Then
