@@ -1,7 +1,10 @@
 // bc7.cuh -- BC7 encoder (reference: kernel.ispc:616-2037, cited as K:line).
 //
-// Mapping.  One WARP owns a batch of kBc7Slots 4x4 blocks; its 32 lanes are spread over the
-// blocks' independent work items instead of over texels:
+// Mapping.  One WARP owns a batch of kBc7Batch = 8 consecutive 4x4 blocks, handled as two GROUPS of kBc7Slots = 4 for
+// the shape / ranking phases (their per-group scratch is reused) and as ONE set of 8 in the chain phase, so that the
+// chain phase -- 15 to 18 roles per block, a quarter of the work -- fills the warp (8 x 15 = 120 tasks in 4 passes
+// instead of 4 x 15 = 60 tasks in 2 passes of mixed kinds: 88 % of the lanes busy instead of 60 %).  The 32 lanes are
+// spread over the blocks' independent work items instead of over texels:
 //   * shape phases: lane <-> (block slot, partition shape).  A lane fits the PCA segments of its
 //     shape ONCE and evaluates both BC7 modes that use that shape (0 and 2 share the three-subset
 //     shapes, 1 and 3 the two-subset shapes; the reference refits per mode, K:1279-1297, with
@@ -57,7 +60,8 @@ struct Bc7Params {
     int skip2, t1, t3, t7, ch0, rch, channels;
 };
 
-constexpr int kBc7Slots = 4;          // blocks per warp batch
+constexpr int kBc7Slots = 4;          // blocks per group (shape / ranking phases)
+constexpr int kBc7Batch = 8;          // blocks per warp batch (chain phase): two groups
 constexpr int kBc7MaxRoles = 18;      // 5 partitioned modes + up to 8 mode-4 + 4 mode-5 + mode 6
 constexpr int kErrNone = 0x7fffffff;  // "no result": loses every strict < comparison
 
@@ -70,13 +74,17 @@ struct Bc7Block {
 };
 // Per-warp scratch in shared memory
 struct Bc7Warp {
-    Bc7Block blk[kBc7Slots];
-    int cand_err[kBc7Slots][2][64];            // errors of the mode-slot pair being evaluated: [first/second][list position]
-    int keys[kBc7Slots][64];                   // split-bound keys of the set being ranked (scratch)
+    Bc7Block blk[kBc7Batch];
+    // per-GROUP scratch (slot = block index inside the group), reused by the second group after the first
+    union {
+        int cand_err[kBc7Slots][2][64];        // errors of the mode-slot pair being evaluated: [first/second][list position]
+        int keys[kBc7Slots][64];               // split-bound keys of the set being ranked: dead once `order` is written, and
+    };                                         // the candidate errors of the previous pair have been consumed by then
     uint8_t order[kBc7Slots][2][64];           // shapes in ascending key order: [0] RGB (modes 1,3), [1] profile channels (mode 7)
-    int win_pos[kBc7Slots][5];                 // winning list position per mode slot, -1 = none
-    int res_err[kBc7Slots][kBc7MaxRoles];
-    u32 res_code[kBc7Slots][kBc7MaxRoles][4];
+    // per-BATCH state handed to the chain phase
+    int win_shape[kBc7Batch][5];               // winning shape id per mode slot, -1 = none
+    int lane_err[32], lane_role[32];           // chain phase: best (error, role) of the roles a lane ran for ITS block (lane % 8) ...
+    u32 lane_code[32][4];                      // ... and the 128 bits of that candidate
     u32 palette[40][32];                       // lane-private scratch of the index search, [entry][lane]: 24 palette
                                                // entries, then 5 per-subset constants x 3 subsets
     // decoded endpoints (A, B as RGBA bytes) of every DISTINCT three-subset mask, for the two blocks being processed:
@@ -749,8 +757,12 @@ struct Role {
 ITW_HD int bc7_rotations(const Bc7Params& P) { return P.sel[2] ? maxi(P.channels - P.ch0, 0) : 0; }
 ITW_HD int bc7_role_count(const Bc7Params& P) { return 5 + 3 * bc7_rotations(P) + (P.sel[3] ? 1 : 0); }
 
-ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slot, int r)
+struct Bc7Result { int err; u32 code[4]; };
+ITW_HD_NOINLINE Bc7Result bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slot, int r)
 {
+    Bc7Result res;
+    res.err = kErrNone;
+    res.code[0] = res.code[1] = res.code[2] = res.code[3] = 0u;
     const Bc7Block* blk = &W.blk[slot];
     const int nrot = bc7_rotations(P);
     Role role;
@@ -758,9 +770,8 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
     if (r < 5) {
         role.kind = 0;
         role.mode = bc7_slot_mode(r);
-        const int pos = W.win_pos[slot][r];
-        if (pos < 0) { W.res_err[slot][r] = kErrNone; return; }
-        role.shape = bc7_slot_shape(W, slot, r, pos);
+        role.shape = W.win_shape[slot][r];
+        if (role.shape < 0) return res;
     } else if (r < 5 + 2 * nrot) {
         role.kind = 1; role.mode = 4; role.rotation = P.ch0 + ((r - 5) >> 1); role.swap = (r - 5) & 1;
     } else if (r < 5 + 3 * nrot) {
@@ -833,7 +844,7 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
     int best_err = best.err;
     const u32 best_idx[2] = {best.idx0, best.idx1};
 
-    u32* out = W.res_code[slot][r];
+    u32* out = res.code;
     if (role.kind == 0) {
         if (mode != 7 && P.channels != 3) {                       // opaque error of the dropped alpha; K:1267-1277, :1356
             int opaque = 0;
@@ -850,13 +861,16 @@ ITW_HD_NOINLINE void bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slo
     } else {
         bc7_write_mode6(out, Q[0][0], Q[0][1], best_idx[0], best_idx[1]);
     }
-    W.res_err[slot][r] = best_err;
+    res.err = best_err;
+    return res;
 }
 
 // =============================================================================================
 // Warp program: per-lane phase functions.  A phase reads what earlier phases wrote to W and
 // writes disjoint locations; the caller separates phases with a warp barrier.
 // =============================================================================================
+ITW_HD int bc7_group_count(const Bc7Warp& W, int g) { return mini(maxi(W.nvalid - kBc7Slots * g, 0), kBc7Slots); }   // valid blocks of group g
+
 ITW_HD void bc7_phase_load(int lane, Bc7Warp& W, const SurfaceView& s, long long first_block, int nvalid)
 {
     const int bw = s.width >> 2;
@@ -868,7 +882,7 @@ ITW_HD void bc7_phase_load(int lane, Bc7Warp& W, const SurfaceView& s, long long
         W.blk[slot].tex[k] = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
     }
     if (lane == 0) W.nvalid = nvalid;
-    for (int t = lane; t < kBc7Slots * 5; t += 32) W.win_pos[t / 5][t % 5] = -1;
+    for (int t = lane; t < kBc7Batch * 5; t += 32) W.win_shape[t / 5][t % 5] = -1;
 }
 // channel planes from the packed texels (a 4x4 byte transpose per group of four texels)
 ITW_HD void bc7_phase_planes(int lane, Bc7Warp& W)
@@ -882,10 +896,10 @@ ITW_HD void bc7_phase_planes(int lane, Bc7Warp& W)
         W.blk[slot].plane[c][i] = v;
     }
 }
-// One shape, both modes of a mode-slot pair (ma, mb): fits once, quantises and searches per mode.
-ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, int n, int ma, bool do_a, int mb, bool do_b)
+// One shape, both modes of a mode-slot pair (ma, mb): fits once, quantises and searches per mode.  `slot` = position inside
+// the group (scratch index), `blk` = the block.
+ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, const Bc7Block* blk, int shape, int n, int ma, bool do_a, int mb, bool do_b)
 {
-    const Bc7Block* blk = &W.blk[slot];
     const int mode_a = bc7_slot_mode(ma), mode_b = bc7_slot_mode(mb);
     const int pairs = bc7_pairs(mode_a);
     const int channels = (mode_a == 7) ? 4 : 3;
@@ -917,17 +931,17 @@ ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, int shape, i
 // ---- three-subset shapes (modes 0 and 2) -------------------------------------------------------------------
 // The 64 shapes x 3 subsets use only 140 distinct texel masks, and the PCA fit and the endpoint quantisation of a subset
 // depend on its mask alone (the reference refits per shape and per mode with identical results, K:1279-1297).  So, two
-// blocks at a time: phase A fits and quantises every distinct mask once (lane <-> (block, mask)); phase B runs the index
-// search of every shape from the stored endpoints (lane <-> (block, shape)).  Same values as evaluating shape by shape,
-// 25 % fewer fits and quantisations.
-ITW_HD void bc7_phase_masks3(int lane, Bc7Warp& W, const Bc7Params& P, int half)
+// blocks at a time (`duo` = 0..3: blocks 2*duo, 2*duo+1 of the batch): phase A fits and quantises every distinct mask once
+// (lane <-> (block, mask)); phase B runs the index search of every shape from the stored endpoints (lane <-> (block, shape)).
+// Same values as evaluating shape by shape, 25 % fewer fits and quantisations.
+ITW_HD void bc7_phase_masks3(int lane, Bc7Warp& W, const Bc7Params& P, int duo)
 {
     const int ca = bc7_slot_count(P, 0), cb = bc7_slot_count(P, 1);
     const int nmask = (cb > 0) ? ITW_MASK3_COUNT : ITW_MASK3_FIRST;
-    const int nslots = mini(maxi(W.nvalid - 2 * half, 0), 2);
+    const int nslots = mini(maxi(W.nvalid - 2 * duo, 0), 2);
     for (int t = lane; t < nslots * nmask; t += 32) {
         const int s = t / nmask, u = t - s * nmask;
-        const Bc7Block* blk = &W.blk[2 * half + s];
+        const Bc7Block* blk = &W.blk[2 * duo + s];
         const Bc7Seg seg = bc7_fit(blk, 3, 1, (u32)ITW_TABLE(mask3_unique)[u], 3);
         if (cb > 0) {
             const Bc7Packed pk = bc7_quantise(seg, 2, 3);
@@ -941,14 +955,15 @@ ITW_HD void bc7_phase_masks3(int lane, Bc7Warp& W, const Bc7Params& P, int half)
         }
     }
 }
-ITW_HD void bc7_phase_shapes3(int lane, Bc7Warp& W, const Bc7Params& P, int half)
+ITW_HD void bc7_phase_shapes3(int lane, Bc7Warp& W, const Bc7Params& P, int duo)
 {
     const int ca = bc7_slot_count(P, 0), cb = bc7_slot_count(P, 1);
     const int count = maxi(ca, cb);
-    const int nslots = mini(maxi(W.nvalid - 2 * half, 0), 2);
+    const int nslots = mini(maxi(W.nvalid - 2 * duo, 0), 2);
     for (int t = lane; t < nslots * count; t += 32) {
-        const int s = t / count, n = t - s * count, slot = 2 * half + s;
-        const Bc7Block* blk = &W.blk[slot];
+        const int s = t / count, n = t - s * count;
+        const int slot = (2 * duo + s) & (kBc7Slots - 1);             // scratch index inside the group
+        const Bc7Block* blk = &W.blk[2 * duo + s];
         const u32 pattern = shape_pattern(64 + n);
         const int u0 = ITW_TABLE(shape3_mask_id)[3 * n], u1 = ITW_TABLE(shape3_mask_id)[3 * n + 1], u2 = ITW_TABLE(shape3_mask_id)[3 * n + 2];
         if (n < ca)
@@ -962,20 +977,20 @@ ITW_HD void bc7_phase_shapes3(int lane, Bc7Warp& W, const Bc7Params& P, int half
     }
 }
 
-// shapes of a pair of mode slots that walk the same list: (0,1) three-subset, (2,3) ranked two-subset,
-// (4,4) mode 7
-ITW_HD void bc7_phase_shapes(int lane, Bc7Warp& W, const Bc7Params& P, int ma, int mb)
+// shapes of a pair of mode slots that walk the same list, for group g: (2,3) ranked two-subset, (4,4) mode 7
+ITW_HD void bc7_phase_shapes(int lane, Bc7Warp& W, const Bc7Params& P, int g, int ma, int mb)
 {
     const int ca = bc7_slot_count(P, ma), cb = (mb != ma) ? bc7_slot_count(P, mb) : 0;
     const int both = mini(ca, cb), count = maxi(ca, cb);
     // list positions [0, both) run both modes, [both, count) only the longer list's mode; tasks are ordered
     // so that the "both" positions of all blocks come first and a warp never mixes the two kinds
-    const int nboth = W.nvalid * both, nall = W.nvalid * count;
+    const int nv = bc7_group_count(W, g);
+    const int nboth = nv * both, nall = nv * count;
     for (int t = lane; t < nall; t += 32) {
         int slot, n;
         if (t < nboth) { slot = t / both; n = t - slot * both; }
         else { const int u = t - nboth, rest = count - both; slot = u / rest; n = both + (u - slot * rest); }
-        bc7_eval_shape(W, lane, slot, bc7_slot_shape(W, slot, ma, n), n, ma, n < ca, mb, n < cb);
+        bc7_eval_shape(W, lane, slot, &W.blk[kBc7Slots * g + slot], bc7_slot_shape(W, slot, ma, n), n, ma, n < ca, mb, n < cb);
     }
 }
 // split-bound keys of the 64 two-subset shapes; set 0 = RGB (modes 1,3), set 1 = profile channels (mode 7)
@@ -984,26 +999,26 @@ ITW_HD bool bc7_needs_keys(const Bc7Params& P, int set)
     if (!P.sel[1]) return false;
     return set == 0 ? !(P.t1 == 0 && P.t3 == 0) : (P.t7 != 0);
 }
-ITW_HD void bc7_phase_keys(int lane, Bc7Warp& W, const Bc7Params& P, int set)
+ITW_HD void bc7_phase_keys(int lane, Bc7Warp& W, const Bc7Params& P, int g, int set)
 {
     const int channels = (set == 0) ? 3 : P.channels;
-    for (int t = lane; t < W.nvalid * 64; t += 32) {
+    for (int t = lane; t < bc7_group_count(W, g) * 64; t += 32) {
         const int slot = t >> 6, shape = t & 63;
-        W.keys[slot][shape] = bc7_split_key(&W.blk[slot], shape, channels);
+        W.keys[slot][shape] = bc7_split_key(&W.blk[kBc7Slots * g + slot], shape, channels);
     }
 }
-ITW_HD void bc7_phase_rank(int lane, Bc7Warp& W, int set)
+ITW_HD void bc7_phase_rank(int lane, Bc7Warp& W, int g, int set)
 {
-    for (int t = lane; t < W.nvalid * 64; t += 32) {
+    for (int t = lane; t < bc7_group_count(W, g) * 64; t += 32) {
         const int slot = t >> 6, i = t & 63;
         W.order[slot][set][rank_of(W.keys[slot], 64, i)] = (uint8_t)(W.keys[slot][i] & 63);
     }
 }
-// first minimum of the candidate lists just evaluated for mode slots (ma, mb); K:1320 (strict <)
-ITW_HD void bc7_phase_winners(int lane, Bc7Warp& W, const Bc7Params& P, int ma, int mb)
+// first minimum of the candidate lists just evaluated for mode slots (ma, mb) of group g, as a SHAPE id; K:1320 (strict <)
+ITW_HD void bc7_phase_winners(int lane, Bc7Warp& W, const Bc7Params& P, int g, int ma, int mb)
 {
     const int nm = (mb != ma) ? 2 : 1;
-    for (int t = lane; t < W.nvalid * nm; t += 32) {
+    for (int t = lane; t < bc7_group_count(W, g) * nm; t += 32) {
         const int slot = t / nm, which = t - slot * nm;
         const int m = which ? mb : ma;
         const int count = bc7_slot_count(P, m);
@@ -1012,34 +1027,46 @@ ITW_HD void bc7_phase_winners(int lane, Bc7Warp& W, const Bc7Params& P, int ma, 
             const int e = W.cand_err[slot][which][n];
             if (e < best_err) { best_err = e; best = n; }
         }
-        W.win_pos[slot][m] = best;
+        W.win_shape[kBc7Slots * g + slot][m] = (best < 0) ? -1 : bc7_slot_shape(W, slot, m, best);
     }
 }
+// Chain phase over the whole batch.  Lane L works for block L % 8 in every pass and runs roles L / 8, L / 8 + 4, ...: a pass
+// holds four consecutive roles for the eight blocks, so its lanes run the same KIND of role (partitioned / mode 4-5 / mode 6)
+// almost everywhere, and a lane can keep the best candidate of ITS block in registers.  The first strict minimum in role
+// order is kept (K:1358, :1638, :1650, :1684): a lane meets its roles in ascending order, the store phase compares (error, role).
 ITW_HD void bc7_phase_chains(int lane, Bc7Warp& W, const Bc7Params& P)
 {
-    // role-major task order: the lanes of a warp pass hold the same KIND of role (partitioned / mode 4-5 / mode 6) for
-    // different blocks, so each kind's code path is walked once per pass instead of once per block
-    const int nroles = bc7_role_count(P), nv = W.nvalid;
-    for (int t = lane; t < nv * nroles; t += 32) bc7_chain(W, P, lane, t % nv, t / nv);
+    const int nroles = bc7_role_count(P);
+    const int slot = lane & (kBc7Batch - 1);
+    int best_err = kErrNone, best_role = 0;
+    u32 code[4] = {0u, 0u, 0u, 0u};
+    if (slot < W.nvalid)
+        for (int r = lane / kBc7Batch; r < nroles; r += 32 / kBc7Batch) {
+            const Bc7Result res = bc7_chain(W, P, lane, slot, r);
+            if (res.err < best_err) {
+                best_err = res.err; best_role = r;
+#pragma unroll
+                for (int i = 0; i < 4; i++) code[i] = res.code[i];
+            }
+        }
+    W.lane_err[lane] = best_err;
+    W.lane_role[lane] = best_role;
+#pragma unroll
+    for (int i = 0; i < 4; i++) W.lane_code[lane][i] = code[i];
 }
-// first strict minimum over the roles in the reference's order, then the 16-byte store; K:2027
+// the block's winner among the four lanes that worked for it, then the 16-byte store; K:2027
 ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* dst, long long first_block)
 {
-    const int nroles = bc7_role_count(P);
+    (void)P;
     for (int t = lane; t < W.nvalid; t += 32) {
-        int best_err = kErrNone;
-        u32 code[4] = {0u, 0u, 0u, 0u};
-        for (int r = 0; r < nroles; r++) {
-            const int e = W.res_err[t][r];
-            if (e < best_err) {
-                best_err = e;
-#pragma unroll
-                for (int i = 0; i < 4; i++) code[i] = W.res_code[t][r][i];
-            }
+        int best = t;
+        for (int j = 1; j < 32 / kBc7Batch; j++) {
+            const int l = t + kBc7Batch * j;
+            if (W.lane_err[l] < W.lane_err[best] || (W.lane_err[l] == W.lane_err[best] && W.lane_role[l] < W.lane_role[best])) best = l;
         }
         u32* out = reinterpret_cast<u32*>(dst + (size_t)(first_block + t) * 16);
 #pragma unroll
-        for (int i = 0; i < 4; i++) out[i] = code[i];
+        for (int i = 0; i < 4; i++) out[i] = W.lane_code[best][i];
     }
 }
 
@@ -1047,27 +1074,30 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
 #define ITW_BC7_PROGRAM(PHASE)                                                         \
     PHASE(bc7_phase_load(lane, W, surf, first_block, nvalid));                         \
     ITW_BC7_PROGRAM_AFTER_LOAD(PHASE)
-#define ITW_BC7_PROGRAM_AFTER_LOAD(PHASE)                                              \
-    PHASE(bc7_phase_planes(lane, W));                                                  \
+#define ITW_BC7_GROUP_PROGRAM(PHASE, g)                                                \
     if (P.sel[0]) {                                                                    \
-        PHASE(bc7_phase_masks3(lane, W, P, 0));                                        \
-        PHASE(bc7_phase_shapes3(lane, W, P, 0));                                       \
-        PHASE(bc7_phase_masks3(lane, W, P, 1));                                        \
-        PHASE(bc7_phase_shapes3(lane, W, P, 1));                                       \
-        PHASE(bc7_phase_winners(lane, W, P, 0, 1));                                    \
+        PHASE(bc7_phase_masks3(lane, W, P, 2 * (g)));                                  \
+        PHASE(bc7_phase_shapes3(lane, W, P, 2 * (g)));                                 \
+        PHASE(bc7_phase_masks3(lane, W, P, 2 * (g) + 1));                              \
+        PHASE(bc7_phase_shapes3(lane, W, P, 2 * (g) + 1));                             \
+        PHASE(bc7_phase_winners(lane, W, P, g, 0, 1));                                 \
     }                                                                                  \
     if (bc7_needs_keys(P, 0)) {                                                        \
-        PHASE(bc7_phase_keys(lane, W, P, 0));                                          \
-        PHASE(bc7_phase_rank(lane, W, 0));                                             \
-        PHASE(bc7_phase_shapes(lane, W, P, 2, 3));                                     \
-        PHASE(bc7_phase_winners(lane, W, P, 2, 3));                                    \
+        PHASE(bc7_phase_keys(lane, W, P, g, 0));                                       \
+        PHASE(bc7_phase_rank(lane, W, g, 0));                                          \
+        PHASE(bc7_phase_shapes(lane, W, P, g, 2, 3));                                  \
+        PHASE(bc7_phase_winners(lane, W, P, g, 2, 3));                                 \
     }                                                                                  \
     if (bc7_needs_keys(P, 1)) {                                                        \
-        PHASE(bc7_phase_keys(lane, W, P, 1));                                          \
-        PHASE(bc7_phase_rank(lane, W, 1));                                             \
-        PHASE(bc7_phase_shapes(lane, W, P, 4, 4));                                     \
-        PHASE(bc7_phase_winners(lane, W, P, 4, 4));                                    \
-    }                                                                                  \
+        PHASE(bc7_phase_keys(lane, W, P, g, 1));                                       \
+        PHASE(bc7_phase_rank(lane, W, g, 1));                                          \
+        PHASE(bc7_phase_shapes(lane, W, P, g, 4, 4));                                  \
+        PHASE(bc7_phase_winners(lane, W, P, g, 4, 4));                                 \
+    }
+#define ITW_BC7_PROGRAM_AFTER_LOAD(PHASE)                                              \
+    PHASE(bc7_phase_planes(lane, W));                                                  \
+    ITW_BC7_GROUP_PROGRAM(PHASE, 0)                                                    \
+    ITW_BC7_GROUP_PROGRAM(PHASE, 1)                                                    \
     PHASE(bc7_phase_chains(lane, W, P));                                               \
     PHASE(bc7_phase_store(lane, W, P, dst, first_block));
 
@@ -1080,12 +1110,12 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
 constexpr int kBc7WarpsPerCta = 16;
 constexpr size_t kBc7SmemBytes = sizeof(Bc7Warp) * kBc7WarpsPerCta;
 
-// kTma: the 64 consecutive blocks a CTA works on in one round are fetched by the TMA engine
+// kTma: the 128 consecutive blocks a CTA works on in one round are fetched by the TMA engine
 // (cp.async.bulk, SASS UBLKCP) into a double-buffered 4-row shared-memory tile while the previous round is
 // being encoded, signalled through an mbarrier; the load phase then reads the tile from shared memory.
 // Needs 16-byte aligned surface rows; other surfaces use the plain global-load variant.
-constexpr int kBc7TileBlocks = kBc7WarpsPerCta * kBc7Slots;              // 64
-constexpr int kBc7TileRowBytes = kBc7TileBlocks * 16;                     // 1024
+constexpr int kBc7TileBlocks = kBc7WarpsPerCta * kBc7Batch;              // 128
+constexpr int kBc7TileRowBytes = kBc7TileBlocks * 16;                     // 2048
 
 template <bool kTma>
 __global__ void __launch_bounds__(kBc7WarpsPerCta * 32, 1)
@@ -1096,11 +1126,11 @@ bc7_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc7Params P, long long 
     __shared__ __align__(8) unsigned long long full[2];
     Bc7Warp& W = reinterpret_cast<Bc7Warp*>(bc7_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nbatches = (nblocks + kBc7Slots - 1) / kBc7Slots;
+    const long long nbatches = (nblocks + kBc7Batch - 1) / kBc7Batch;
     const long long nwarps = (long long)gridDim.x * kBc7WarpsPerCta;
     const long long rounds = (nbatches + nwarps - 1) / nwarps;            // same trip count for every warp of the CTA
 
-    auto tile_first = [&](long long round) { return ((long long)blockIdx.x * kBc7WarpsPerCta + round * nwarps) * kBc7Slots; };
+    auto tile_first = [&](long long round) { return ((long long)blockIdx.x * kBc7WarpsPerCta + round * nwarps) * kBc7Batch; };
     auto prefetch = [&](long long round) {                                // one thread feeds the TMA engine
         const long long fb = tile_first(round);
         if (round >= rounds || fb >= nblocks) return;
@@ -1115,16 +1145,16 @@ bc7_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc7Params P, long long 
     }
     for (long long round = 0; round < rounds; round++) {
         const long long batch = (long long)blockIdx.x * kBc7WarpsPerCta + warp + round * nwarps;
-        long long first_block = batch * kBc7Slots;
+        long long first_block = batch * kBc7Batch;
         const long long left = nblocks - first_block;
-        const int nvalid = (int)(left <= 0 ? 0 : (left < kBc7Slots ? left : kBc7Slots));
+        const int nvalid = (int)(left <= 0 ? 0 : (left < kBc7Batch ? left : kBc7Batch));
         SurfaceView surf = gsurf;
         const long long out_block = first_block;
         if (kTma) {
             if (threadIdx.x == 0) prefetch(round + 1);                   // next tile streams in behind this round's math
             if (tile_first(round) < nblocks) mbar_wait(&full[round & 1], (unsigned)((round >> 1) & 1));
             surf = SurfaceView{stage[round & 1], kBc7TileBlocks * 4, 4, kBc7TileRowBytes};
-            first_block = (long long)warp * kBc7Slots;                   // block index inside the staged tile
+            first_block = (long long)warp * kBc7Batch;                   // block index inside the staged tile
         }
 #define ITW_PHASE_DEVICE(call) call; __syncthreads()
         {

@@ -71,8 +71,8 @@ void emu_CompressBlocksBC7(const rgba_surface* src, uint8_t* dst, bc7_enc_settin
     const Bc7Params P = bc7_params_from(*settings);
     const long long nblocks = (long long)(surf.width / 4) * (surf.height / 4);
     static thread_local Bc7Warp W;
-    for (long long first_block = 0; first_block < nblocks; first_block += kBc7Slots) {
-        const int nvalid = (int)((nblocks - first_block < kBc7Slots) ? (nblocks - first_block) : kBc7Slots);
+    for (long long first_block = 0; first_block < nblocks; first_block += kBc7Batch) {
+        const int nvalid = (int)((nblocks - first_block < kBc7Batch) ? (nblocks - first_block) : kBc7Batch);
         ITW_BC7_PROGRAM(ITW_PHASE_EMU)
     }
 }
