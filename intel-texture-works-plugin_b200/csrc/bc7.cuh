@@ -69,8 +69,9 @@ constexpr int kErrNone = 0x7fffffff;  // "no result": loses every strict < compa
 struct Bc7Block {
     u32 tex[16];       // packed RGBA8 of texel k (R in byte 0)
     u32 plane[4][4];   // plane[c][i] = channel c of texels 4i..4i+3, one byte each
-    u32 pad;           // 33 words: word k of the four slots of a batch lands in four different banks (in the chain phase
-                       // adjacent lanes hold different slots; with 32 words every block read was a 4-way bank conflict)
+    u32 rgb[16];       // tex[k] & 0x00FFFFFF: what the three-channel index searches read (three quarters of all searches)
+    u32 pad;           // 49 words: word k of the eight blocks of a batch lands in eight different banks (in the chain phase
+                       // adjacent lanes hold different blocks; with 32 words every block read was a bank conflict)
 };
 // Per-warp scratch in shared memory
 struct Bc7Warp {
@@ -383,6 +384,20 @@ ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
     u32 cand0[2] = {0u, 0u}, cand1[2] = {0u, 0u};
     bool pick1[2] = {false, false};
     float e0 = 0.0f, e1 = 0.0f;
+    if (plain) {
+        // no p-bit (modes 2, 4, 5; K:1054-1065): one candidate per component, no vote -- a third of all quantisations
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            u32 c0 = 0u;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c == 3 && !four) continue;
+                const float t = div255(ep[4 * i + c]) * ftop;
+                c0 |= (u32)clampi(trunc_i(fma_rn(t, 1.0f, 0.5f)), 0, top) << (8 * c);
+            }
+            cand0[i] = c0;
+        }
+    } else
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         if (family == 0) { e0 = 0.0f; e1 = 0.0f; }
@@ -455,29 +470,52 @@ ITW_HD_NOINLINE Bc7Search bc7_assign(u32 (*pal)[32], int lane, const Bc7Block* b
     const float flevels = (float)levels;
     int total = 0;
     u32 out0 = 0u, out1 = 0u;
-    ITW_UNROLL(ITW_BC7_ASSIGN_UNROLL)
-    for (int k = 0; k < 16; k++) {
-        const u32 t = view_tex(v, k) & chmask;
-        const int j = (int)((pattern >> (2 * k)) & 3u);
-        const u32 ea = pal[24 + 5 * j + 0][lane], eb = pal[24 + 5 * j + 1][lane];
-        const int cj = (int)pal[24 + 5 * j + 2][lane];
-        const float dj = bits_float(pal[24 + 5 * j + 3][lane]), rj = bits_float(pal[24 + 5 * j + 4][lane]);
-        // sum_c (t_c - a_c)(b_c - a_c): integer, |value| < 2^18, so the float it converts to is the
-        // reference's float sum; the division of K:1158 is the exact FMA-corrected quotient (proved
-        // equal to IEEE num/div on this integer domain, tests/test_exact_division.py)
-        const int num = (int)dp4a_u8(t, eb, 0u) - (int)dp4a_u8(t, ea, 0u) - cj;
-        const float proj = div_by_rcp((float)num, dj, rj);
-        // |proj*levels| < 2^23, so truncation never overflows; NaN (coincident endpoints, 0/0) becomes
-        // INT_MIN on x86 and 0 here -- both clamp to 1 (K:1160-1161).  proj*levels is exact, so the fused
-        // form rounds once like the reference's multiply-then-add.
-        const int q1 = clampi(trunc_i(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);
-        const u32 p0 = pal[j * levels + q1 - 1][lane], p1 = pal[j * levels + q1][lane];
-        const u32 d0 = absdiff_u8x4(p0, t), d1 = absdiff_u8x4(p1, t);
-        const int e0 = (int)dp4a_u8(d0, d0, 0u), e1 = (int)dp4a_u8(d1, d1, 0u);
-        const bool first = e0 < e1;
-        total += first ? e0 : e1;
-        const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
-        if (k < 8) out0 += bq; else out1 += bq;
+    if (rot == 3) {
+        // identity view (every shape-phase search, the partitioned and mode-6 chains): the texel words are read as stored
+        const u32* tx = (chmask == 0x00FFFFFFu) ? blk->rgb : blk->tex;
+        ITW_UNROLL(ITW_BC7_ASSIGN_UNROLL)
+        for (int k = 0; k < 16; k++) {
+            const u32 t = tx[k];
+            const int j = (int)((pattern >> (2 * k)) & 3u);
+            const u32 ea = pal[24 + 5 * j + 0][lane], eb = pal[24 + 5 * j + 1][lane];
+            const int cj = (int)pal[24 + 5 * j + 2][lane];
+            const float dj = bits_float(pal[24 + 5 * j + 3][lane]), rj = bits_float(pal[24 + 5 * j + 4][lane]);
+            // sum_c (t_c - a_c)(b_c - a_c): integer, |value| < 2^18, so the float it converts to is the
+            // reference's float sum; the division of K:1158 is the exact FMA-corrected quotient (proved
+            // equal to IEEE num/div on this integer domain, tests/test_exact_division.py)
+            const int num = (int)dp4a_u8(t, eb, 0u) - (int)dp4a_u8(t, ea, 0u) - cj;
+            const float proj = div_by_rcp((float)num, dj, rj);
+            // |proj*levels| < 2^23, so truncation never overflows; NaN (coincident endpoints, 0/0) becomes
+            // INT_MIN on x86 and 0 here -- both clamp to 1 (K:1160-1161).  proj*levels is exact, so the fused
+            // form rounds once like the reference's multiply-then-add.
+            const int q1 = clampi(trunc_i(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);
+            const u32 p0 = pal[j * levels + q1 - 1][lane], p1 = pal[j * levels + q1][lane];
+            const u32 d0 = absdiff_u8x4(p0, t), d1 = absdiff_u8x4(p1, t);
+            const int e0 = (int)dp4a_u8(d0, d0, 0u), e1 = (int)dp4a_u8(d1, d1, 0u);
+            const bool first = e0 < e1;
+            total += first ? e0 : e1;
+            const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
+            if (k < 8) out0 += bq; else out1 += bq;
+        }
+    } else {                                                       // rotated views of modes 4 / 5: same loop, texels through view_tex
+        ITW_UNROLL(ITW_BC7_ASSIGN_UNROLL)
+        for (int k = 0; k < 16; k++) {
+            const u32 t = view_tex(v, k) & chmask;
+            const int j = (int)((pattern >> (2 * k)) & 3u);
+            const u32 ea = pal[24 + 5 * j + 0][lane], eb = pal[24 + 5 * j + 1][lane];
+            const int cj = (int)pal[24 + 5 * j + 2][lane];
+            const float dj = bits_float(pal[24 + 5 * j + 3][lane]), rj = bits_float(pal[24 + 5 * j + 4][lane]);
+            const int num = (int)dp4a_u8(t, eb, 0u) - (int)dp4a_u8(t, ea, 0u) - cj;
+            const float proj = div_by_rcp((float)num, dj, rj);
+            const int q1 = clampi(trunc_i(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);
+            const u32 p0 = pal[j * levels + q1 - 1][lane], p1 = pal[j * levels + q1][lane];
+            const u32 d0 = absdiff_u8x4(p0, t), d1 = absdiff_u8x4(p1, t);
+            const int e0 = (int)dp4a_u8(d0, d0, 0u), e1 = (int)dp4a_u8(d1, d1, 0u);
+            const bool first = e0 < e1;
+            total += first ? e0 : e1;
+            const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
+            if (k < 8) out0 += bq; else out1 += bq;
+        }
     }
     return Bc7Search{total, out0, out1};
 }
@@ -879,7 +917,9 @@ ITW_HD void bc7_phase_load(int lane, Bc7Warp& W, const SurfaceView& s, long long
         const long long id = first_block + slot;
         const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
         const uint8_t* p = s.ptr + (size_t)(by * 4 + (k >> 2)) * (size_t)s.stride + (size_t)(bx * 4 + (k & 3)) * 4;
-        W.blk[slot].tex[k] = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+        const u32 rgb = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16);
+        W.blk[slot].rgb[k] = rgb;
+        W.blk[slot].tex[k] = rgb | ((u32)p[3] << 24);
     }
     if (lane == 0) W.nvalid = nvalid;
     for (int t = lane; t < kBc7Batch * 5; t += 32) W.win_shape[t / 5][t % 5] = -1;
