@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=8192)
 ap.add_argument("--format", default="BC3")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--srgb", action="store_true", help="the sRGB-correct chain of the *_SRGB encodings (itw_generate_mips_device_srgb)")
 a = ap.parse_args()
 lib = pkg.ItwBcn()
 n = a.size
@@ -35,7 +36,8 @@ sp = ctypes.c_void_p(stream.cuda_stream)
 
 
 def mips():
-    assert lib.lib.itw_generate_mips_device(ctypes.byref(top), levels, outs, ctypes.c_void_p(scratch.data_ptr()), sp) == 0
+    f = lib.lib.itw_generate_mips_device_srgb if a.srgb else lib.lib.itw_generate_mips_device
+    assert f(ctypes.byref(top), levels, outs, ctypes.c_void_p(scratch.data_ptr()), sp) == 0
 
 
 def encode():
@@ -59,7 +61,7 @@ t_mip, t_enc = timed(mips), timed(encode)
 texels = sum(max(n >> l, 1) ** 2 for l in range(levels))
 mip_bytes = sum(max(n >> l, 1) ** 2 * 4 for l in range(0, levels - 1)) + sum(o.width * o.height * 4 for o in list(outs)[1:])
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-print(json.dumps({"config": f"C4 {a.format} + {levels}-level mip chain, {n}x{n} RGBA8, 1 GPU, device-resident",
+print(json.dumps({"config": f"C4 {a.format} + {levels}-level {'sRGB-correct ' if a.srgb else ''}mip chain, {n}x{n} RGBA8, 1 GPU, device-resident",
                   "mip_prepass_ms": round(t_mip, 4), "mip_prepass_GBps": round(mip_bytes / t_mip / 1e6, 1),
                   "mip_prepass_frac_of_hbm_peak": round(mip_bytes / t_mip / 1e6 / peak, 3),
                   "encode_ms": round(t_enc, 4), "Mtexels_per_s_encode": round(texels / t_enc / 1e3, 1),
