@@ -22,7 +22,7 @@ many() {  # name, kernel regex, count, command...: --set full without source, ev
 }
 for w in $WHAT; do
   case $w in
-    launches) $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $OUT/${TAG}_launches_default_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/${TAG}_launches_bench_stdout.log 2>&1 ;;
+    launches) $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $OUT/${TAG}_launches_default_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extras > $OUT/${TAG}_launches_bench_stdout.log 2>&1 ;;
     bc7)  full bc7_slow bc7_kernel bc7_kernelILb1 python bench.py --format BC7 --profile slow --steps 1 --warmup 1 --no-cpu --no-extras ;;
     bc6h) full bc6h_slow bc6h_kernel bc6h_kernelILb1 python bench.py --format BC6H --profile bc6h_slow --steps 1 --warmup 1 --no-cpu --no-extras ;;
     bc1)  full bc1 bc1_bc3_kernel bc1_bc3_kernelILb0ELb1 python bench.py --format BC1 --steps 1 --warmup 1 --no-cpu --no-extras ;;
