@@ -52,19 +52,19 @@ ITW_HD MipTap mip_box_tap(int source, int u)
 //           thresholds of the monotone float -> byte store.
 ITW_TABLE_DECL(uint32_t, srgb_to_linear, 256)
 ITW_TABLE_DECL(uint32_t, linear_threshold, 255)
+ITW_TABLE_DECL(uint32_t, linear_base, ITW_SRGB_BASE_WORDS)
 
 ITW_HD float mip_saturate(float v) { v = (v > 0.0f) ? v : 0.0f; return (v < 1.0f) ? v : 1.0f; }
 ITW_HD u32 mip_unorm8_store(float v) { return (u32)trunc_i(mip_saturate(v) * 255.0f + 0.5f); }
 ITW_HD u32 mip_srgb8_store(float v)
 {
-    const u32 bits = float_bits(mip_saturate(v));            // non-negative floats order like their bit patterns
-    int lo = 0, hi = 255;                                    // result = number of thresholds <= v
-#pragma unroll 1
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (ITW_TABLE(linear_threshold)[mid] <= bits) lo = mid + 1; else hi = mid;
-    }
-    return (u32)lo;
+    // result = number of thresholds <= v (non-negative floats order like their bit patterns).  Two table reads: the byte at the
+    // start of v's bucket (top bits of the float), then one threshold comparison -- inside a bucket the byte rises by at most one.
+    const u32 bits = float_bits(mip_saturate(v));
+    if (bits < ((u32)ITW_SRGB_BASE_FIRST_EXP << 23)) return 0u;                 // below 2^-13 every value stores 0
+    const u32 bucket = (bits >> 15) - ((u32)ITW_SRGB_BASE_FIRST_EXP << 8);
+    const u32 base = (ITW_TABLE(linear_base)[bucket >> 2] >> (8 * (bucket & 3u))) & 255u;
+    return base + ((base < 255u && ITW_TABLE(linear_threshold)[base] <= bits) ? 1u : 0u);
 }
 template <int kCodec>
 ITW_HD void mip_load(float (&v)[4], const uint8_t* row, int x)

@@ -136,16 +136,27 @@ def test_srgb_tables_match_the_oracle_functions():
     o.oracle_linear_to_srgb8.restype = ctypes.c_int
     o.oracle_linear_to_srgb8.argtypes = [ctypes.c_float]
     src = open(os.path.join(T.ROOT, "intel-texture-works-plugin_b200", "csrc", "srgb_tables.cuh")).read()
-    to_lin = [int(x, 16) for x in __import__("re").findall(r"0x([0-9A-F]{8})u", src.split("ITW_TABLE_INIT_linear_threshold")[0])]
-    thr = [int(x, 16) for x in __import__("re").findall(r"0x([0-9A-F]{8})u", src.split("ITW_TABLE_INIT_linear_threshold")[1])]
-    assert len(to_lin) == 256 and len(thr) == 255
+    import re
+    hexes = lambda text: [int(x, 16) for x in re.findall(r"0x([0-9A-F]{8})u", text)]
+    to_lin = hexes(src.split("ITW_TABLE_INIT_linear_threshold")[0])
+    thr = hexes(src.split("ITW_TABLE_INIT_linear_threshold")[1].split("ITW_TABLE_INIT_linear_base")[0])
+    base_words = hexes(src.split("ITW_TABLE_INIT_linear_base")[1])
+    first_exp = int(re.search(r"ITW_SRGB_BASE_FIRST_EXP (\d+)", src).group(1))
+    assert len(to_lin) == 256 and len(thr) == 255 and len(base_words) == int(re.search(r"ITW_SRGB_BASE_WORDS (\d+)", src).group(1))
     for b in range(256):
         s = np.float32(b) * np.float32(1.0 / 255.0)
         assert np.float32(o.oracle_srgb_to_linear(float(s))).view(np.uint32) == to_lin[b], b
     thr_arr = np.array(thr, np.uint32)
 
     def table_byte(bits):
-        return int(np.searchsorted(thr_arr, np.uint32(bits), side="right"))
+        """the kernel's two-level lookup (csrc/mips_f16.cuh mip_srgb8_store), restated on the parsed tables"""
+        if bits < (first_exp << 23):
+            return 0
+        bucket = (bits >> 15) - (first_exp << 8)
+        base = (base_words[bucket >> 2] >> (8 * (bucket & 3))) & 255
+        got = base + (1 if base < 255 and thr[base] <= bits else 0)
+        assert got == int(np.searchsorted(thr_arr, np.uint32(bits), side="right"))        # == the plain count of thresholds
+        return got
     probes = set()
     for t in thr:
         probes.update((t - 1, t, t + 1))

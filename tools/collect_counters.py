@@ -29,6 +29,9 @@ def main():
                 cmd += ["--profile", prof]
             res = subprocess.run(cmd, capture_output=True, text=True)
             rows = [r for r in csv.reader(res.stdout.splitlines()) if len(r) > 10]
+            while rows and "Metric Name" not in rows[0]:               # bench.py's own JSON line also parses as a long CSV row
+                rows.pop(0)
+            rows = [r for r in rows if len(r) == len(rows[0])]
             if len(rows) < 2:
                 print("no rows for", fmt, prof, size, res.stderr[-300:], file=sys.stderr)
                 continue
