@@ -208,17 +208,21 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def count(self, t0=0.0):
+        return sum(1 for t, _ in self.lines if t >= t0)
+
+    def stop(self, t0=0.0, t1=float("inf"), window="timed region"):
+        """Summary of the samples that arrived in [t0, t1] (perf_counter times)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for t, line in self.lines:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
+            if len(parts) < 6 or t < t0 or t > t1:
                 continue
             try:
                 sm.append(float(parts[0]))
@@ -229,7 +233,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -533,11 +537,13 @@ def main():
         lib.encode_device(fmt, d_in[i % nrot].data_ptr(), size, size, size * texel_bytes, d_out.data_ptr(), settings,
                           stream.cuda_stream)
 
+    # nvidia-smi needs a second or more before its first line (longer on an 8-GPU box): started before the warm-up, and only the
+    # samples that arrive inside the timed region count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     g.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = lib.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
@@ -546,9 +552,23 @@ def main():
         step(args.warmup + i)
         evs[i][1].record(stream)
     g.barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    launches = lib.launch_count() - launches0
+    wall1 = time.perf_counter()
+    wall = wall1 - wall0
+    launches_timed = lib.launch_count() - launches0
+    if sampler.count(wall0) >= 3 or not sampler.proc:
+        clocks = sampler.stop(wall0, wall1)
+    else:
+        # a timed region shorter than a few 100 ms sampling periods: the same steps keep running (untimed) until three samples
+        # have been taken under that load
+        i, limit = args.warmup + args.steps, time.perf_counter() + 6.0
+        while sampler.count(wall1) < 3 and time.perf_counter() < limit:
+            for _ in range(4):
+                step(i)
+                i += 1
+            stream.synchronize()
+        clocks = sampler.stop(wall0, window="timed region + the same steps continued until 3 samples")
+    g.barrier()
+    launches = launches_timed
     dev_ms = g.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
     ms_per_step = dev_ms / args.steps
     texels_per_step = size * size * world

@@ -60,8 +60,9 @@ struct Bc7Params {
     int skip2, t1, t3, t7, ch0, rch, channels;
 };
 
-constexpr int kBc7Slots = 4;          // blocks per group (shape / ranking phases)
-constexpr int kBc7Batch = 8;          // blocks per warp batch (chain phase): two groups
+constexpr int kBc7Slots = 4;          // blocks per group (ranking / shape phases share per-group scratch)
+constexpr int kBc7Batch = 8;          // blocks per HALF: what the shape phases hold in Bc7Warp::blk at a time (two groups)
+constexpr int kBc7Super = 16;         // blocks per warp and round when the surface is large: two halves, ONE chain phase
 constexpr int kBc7MaxRoles = 18;      // 5 partitioned modes + up to 8 mode-4 + 4 mode-5 + mode 6
 constexpr int kErrNone = 0x7fffffff;  // "no result": loses every strict < comparison
 
@@ -70,29 +71,42 @@ struct Bc7Block {
     u32 tex[16];       // packed RGBA8 of texel k (R in byte 0)
     u32 plane[4][4];   // plane[c][i] = channel c of texels 4i..4i+3, one byte each
     u32 rgb[16];       // tex[k] & 0x00FFFFFF: what the three-channel index searches read (three quarters of all searches)
-    u32 pad;           // 49 words: word k of the eight blocks of a batch lands in eight different banks (in the chain phase
+    u32 pad;           // 49 words: word k of the eight blocks of a half lands in eight different banks (in the chain phase
                        // adjacent lanes hold different blocks; with 32 words every block read was a bank conflict)
 };
 // Per-warp scratch in shared memory
 struct Bc7Warp {
-    Bc7Block blk[kBc7Batch];
-    // per-GROUP scratch (slot = block index inside the group), reused by the second group after the first
+    Bc7Block blk[kBc7Batch];                   // the half the shape phases are working on
     union {
+        // per-GROUP scratch (slot = block index inside the group), reused by every group in turn
         int cand_err[kBc7Slots][2][64];        // errors of the mode-slot pair being evaluated: [first/second][list position]
         int keys[kBc7Slots][64];               // split-bound keys of the set being ranked: dead once `order` is written, and
-    };                                         // the candidate errors of the previous pair have been consumed by then
+                                               // the candidate errors of the previous pair have been consumed by then
+        // end of the chain phase -> store phase (the shape phases are over by then)
+        struct {
+            int err[32], role[32];             // best (error, role) of the roles a lane ran for ITS block ...
+            u32 code[32][4];                   // ... and the 128 bits of that candidate
+        } fin;
+    };
     uint8_t order[kBc7Slots][2][64];           // shapes in ascending key order: [0] RGB (modes 1,3), [1] profile channels (mode 7)
-    // per-BATCH state handed to the chain phase
-    int win_shape[kBc7Batch][5];               // winning shape id per mode slot, -1 = none
-    int lane_err[32], lane_role[32];           // chain phase: best (error, role) of the roles a lane ran for ITS block (lane % 8) ...
-    u32 lane_code[32][4];                      // ... and the 128 bits of that candidate
+    int win_shape[kBc7Super][5];               // winning shape id per block of the round and mode slot, -1 = none
     u32 palette[40][32];                       // lane-private scratch of the index search, [entry][lane]: 24 palette
                                                // entries, then 5 per-subset constants x 3 subsets
-    // decoded endpoints (A, B as RGBA bytes) of every DISTINCT three-subset mask, for the two blocks being processed:
-    // mode 2 for all 140 masks, mode 0 for the 36 masks of shapes 0..15 (bc7_phase_masks3 -> bc7_phase_shapes3)
-    u32 ends3_mode2[2][ITW_MASK3_COUNT][2];
-    u32 ends3_mode0[2][ITW_MASK3_FIRST][2];
-    int nvalid;
+    union {
+        // decoded endpoints (A, B as RGBA bytes) of every DISTINCT three-subset mask, for the two blocks being processed:
+        // mode 2 for all 140 masks, mode 0 for the 36 masks of shapes 0..15 (bc7_phase_masks3 -> bc7_phase_shapes3)
+        struct {
+            u32 mode2[2][ITW_MASK3_COUNT][2];
+            u32 mode0[2][ITW_MASK3_FIRST][2];
+        } ends3;
+        // chain phase of a two-half round: the FIRST half again (re-read from the staged tile once its slot in blk[] has
+        // been taken by the second half; the mask tables are dead by then)
+        Bc7Block parked[kBc7Batch];
+    };
+    int nvalid;                                // valid blocks in blk[]
+    int half;                                  // which half of the round blk[] holds (0 / 1)
+    int ntotal;                                // valid blocks of the round (chain and store phases)
+    int nparked;                               // blocks in parked[]: the round's blocks [0, nparked); blk[] holds the rest
 };
 // mode slots m = 0..4 <-> BC7 modes {0, 2, 1, 3, 7}: the reference's evaluation order
 ITW_HD int bc7_slot_mode(int m) { return (m == 0) ? 0 : ((m == 1) ? 2 : ((m == 2) ? 1 : ((m == 3) ? 3 : 7))); }
@@ -448,28 +462,62 @@ ITW_HD u32 lerp_rgba(u32 a, u32 b, u32 w)
 // Index search; K:1133-1193.  ends[2j], ends[2j+1] = decoded endpoints A,B of subset j (RGBA bytes);
 // chmask zeroes the channels that do not take part (0x00FFFFFF for three-channel modes).
 // Returns the summed error (exact integer) and the sixteen 4-bit indices in idx[0..1].
-ITW_HD_NOINLINE Bc7Search bc7_assign(u32 (*pal)[32], int lane, const Bc7Block* blk, int rot, int alpha, int bits, int pairs,
+// bits_flags = index bits, plus kAssignThresholds when the caller allows the integer-threshold form of the two-bit search.
+// Only the shape phases do: there every lane of the warp searches the same mode at the same time, whereas a chain-phase
+// pass mixes two- and three-bit roles and two texel loops would run one after the other.
+constexpr int kAssignThresholds = 8;
+ITW_HD_NOINLINE Bc7Search bc7_assign(u32 (*pal)[32], int lane, const Bc7Block* blk, int rot, int alpha, int bits_flags, int pairs,
                                      u32 pattern, u32 e0, u32 e1, u32 e2, u32 e3, u32 e4, u32 e5, u32 chmask)
 {
     const View v{blk, rot, alpha};
+    const int bits = bits_flags & 7;
+    const bool thresholds = (bits_flags == (2 | kAssignThresholds)) && rot == 3;
     const int levels = 1 << bits;
     // per-subset constants go to lane-private shared memory too and are fetched by subset id in the texel
     // loop: the load/store pipe is nearly idle in this kernel while the ALU pipe (selects) is the busiest
     for (int j = 0; j < pairs; j++) {
         const u32 a = ((j == 0) ? e0 : ((j == 1) ? e2 : e4)) & chmask, b = ((j == 0) ? e1 : ((j == 1) ? e3 : e5)) & chmask;
         const u32 aa = dp4a_u8(a, a, 0u), ab = dp4a_u8(a, b, 0u), bb = dp4a_u8(b, b, 0u);
-        const float fdiv = (float)(int)(bb - 2u * ab + aa);      // sum of squared differences, exact
+        const int idiv = (int)(bb - 2u * ab + aa);               // sum of squared differences, exact
+        const float fdiv = (float)idiv;
         const float frcp = 1.0f / fdiv;                          // inf when the endpoints coincide (-> NaN below, as 0/0)
         pal[24 + 5 * j + 0][lane] = a;
         pal[24 + 5 * j + 1][lane] = b;
         pal[24 + 5 * j + 2][lane] = ab - aa;
-        pal[24 + 5 * j + 3][lane] = float_bits(fdiv);
-        pal[24 + 5 * j + 4][lane] = float_bits(frcp);
+        // two-bit search by thresholds: q1 >= m  <=>  8 num >= (2m - 1) div  <=>  num >= ceil((2m - 1) div / 8), m = 2, 3
+        // (see the texel loop); coincident endpoints give 0/0 = NaN -> q1 = 1 in the reference: thresholds out of reach
+        pal[24 + 5 * j + 3][lane] = thresholds ? (u32)(idiv ? (3 * idiv + 7) >> 3 : 0x7fffffff) : float_bits(fdiv);
+        pal[24 + 5 * j + 4][lane] = thresholds ? (u32)(idiv ? (5 * idiv + 7) >> 3 : 0x7fffffff) : float_bits(frcp);
         for (int q = 0; q < levels; q++) pal[j * levels + q][lane] = lerp_rgba(a, b, (u32)bc7_weight(bits, q));
     }
     const float flevels = (float)levels;
     int total = 0;
     u32 out0 = 0u, out1 = 0u;
+    if (thresholds) {
+        // The reference's q1 = clamp((int)(RN(RN(num / div) * 4) + 0.5), 1, 3) is a non-decreasing step function of the
+        // integer num; with tau = (2m - 1) / 8 (a float): RN(p * 4 + 0.5) >= m <=> p >= tau (the sum is exact below the next
+        // binade, and the binade boundary itself is an integer m), and RN(num / div) >= tau <=> num / div >= tau because a
+        // quotient below tau stays at least 1 / (8 div) > 2^-21 away from it while half an ulp of tau is below 2^-24
+        // (div <= 4 * 255^2 < 2^18).  tests/test_exact_division.py checks both sides of every step for every possible div.
+        const u32* tx = (chmask == 0x00FFFFFFu) ? blk->rgb : blk->tex;
+        ITW_UNROLL(ITW_BC7_ASSIGN_UNROLL)
+        for (int k = 0; k < 16; k++) {
+            const u32 t = tx[k];
+            const int j = (int)((pattern >> (2 * k)) & 3u);
+            const u32 ea = pal[24 + 5 * j + 0][lane], eb = pal[24 + 5 * j + 1][lane];
+            const int cj = (int)pal[24 + 5 * j + 2][lane];
+            const int t2 = (int)pal[24 + 5 * j + 3][lane], t3 = (int)pal[24 + 5 * j + 4][lane];
+            const int num = (int)dp4a_u8(t, eb, 0u) - (int)dp4a_u8(t, ea, 0u) - cj;
+            const int q1 = 1 + ((num >= t2) ? 1 : 0) + ((num >= t3) ? 1 : 0);
+            const u32 p0 = pal[j * 4 + q1 - 1][lane], p1 = pal[j * 4 + q1][lane];
+            const u32 d0 = absdiff_u8x4(p0, t), d1 = absdiff_u8x4(p1, t);
+            const int e0 = (int)dp4a_u8(d0, d0, 0u), e1 = (int)dp4a_u8(d1, d1, 0u);
+            const bool first = e0 < e1;
+            total += first ? e0 : e1;
+            const u32 bq = (u32)(first ? q1 - 1 : q1) << (4 * (k & 7));
+            if (k < 8) out0 += bq; else out1 += bq;
+        }
+    } else
     if (rot == 3) {
         // identity view (every shape-phase search, the partitioned and mode-6 chains): the texel words are read as stored
         const u32* tx = (chmask == 0x00FFFFFFu) ? blk->rgb : blk->tex;
@@ -794,6 +842,20 @@ struct Role {
 };
 ITW_HD int bc7_rotations(const Bc7Params& P) { return P.sel[2] ? maxi(P.channels - P.ch0, 0) : 0; }
 ITW_HD int bc7_role_count(const Bc7Params& P) { return 5 + 3 * bc7_rotations(P) + (P.sel[3] ? 1 : 0); }
+// The chain phase walks only the roles that can produce a candidate: a partitioned mode whose list is empty under the profile
+// (mode 7 of the RGB profiles, ...) would otherwise idle one lane of every pass.  i-th active role, ascending.
+ITW_HD int bc7_active_roles(const Bc7Params& P)
+{
+    int n = bc7_role_count(P) - 5;
+    for (int m = 0; m < 5; m++) n += (bc7_slot_count(P, m) > 0) ? 1 : 0;
+    return n;
+}
+ITW_HD int bc7_active_role(const Bc7Params& P, int i)
+{
+    for (int m = 0; m < 5; m++)
+        if (bc7_slot_count(P, m) > 0) { if (i == 0) return m; i--; }
+    return 5 + i;
+}
 
 struct Bc7Result { int err; u32 code[4]; };
 ITW_HD_NOINLINE Bc7Result bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, int slot, int r)
@@ -801,7 +863,7 @@ ITW_HD_NOINLINE Bc7Result bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, in
     Bc7Result res;
     res.err = kErrNone;
     res.code[0] = res.code[1] = res.code[2] = res.code[3] = 0u;
-    const Bc7Block* blk = &W.blk[slot];
+    const Bc7Block* blk = (slot < W.nparked) ? &W.parked[slot] : &W.blk[slot - W.nparked];
     const int nrot = bc7_rotations(P);
     Role role;
     role.rotation = 3; role.swap = 0; role.shape = 0;
@@ -909,20 +971,47 @@ ITW_HD_NOINLINE Bc7Result bc7_chain(Bc7Warp& W, const Bc7Params& P, int lane, in
 // =============================================================================================
 ITW_HD int bc7_group_count(const Bc7Warp& W, int g) { return mini(maxi(W.nvalid - kBc7Slots * g, 0), kBc7Slots); }   // valid blocks of group g
 
-ITW_HD void bc7_phase_load(int lane, Bc7Warp& W, const SurfaceView& s, long long first_block, int nvalid)
+// Loads half `half` (blocks 8*half .. 8*half+7 of the round's `ntotal`) into blk[].
+ITW_HD void bc7_phase_load(int lane, Bc7Warp& W, const SurfaceView& s, long long first_block, int ntotal, int half)
 {
     const int bw = s.width >> 2;
+    const int nvalid = mini(maxi(ntotal - kBc7Batch * half, 0), kBc7Batch);
     for (int t = lane; t < nvalid * 16; t += 32) {
         const int slot = t >> 4, k = t & 15;
-        const long long id = first_block + slot;
+        const long long id = first_block + kBc7Batch * half + slot;
         const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
         const uint8_t* p = s.ptr + (size_t)(by * 4 + (k >> 2)) * (size_t)s.stride + (size_t)(bx * 4 + (k & 3)) * 4;
         const u32 rgb = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16);
         W.blk[slot].rgb[k] = rgb;
         W.blk[slot].tex[k] = rgb | ((u32)p[3] << 24);
     }
-    if (lane == 0) W.nvalid = nvalid;
-    for (int t = lane; t < kBc7Batch * 5; t += 32) W.win_shape[t / 5][t % 5] = -1;
+    if (lane == 0) { W.nvalid = nvalid; W.half = half; W.ntotal = ntotal; W.nparked = 0; }
+    for (int t = lane; t < kBc7Batch * 5; t += 32) W.win_shape[kBc7Batch * half + t / 5][t % 5] = -1;
+}
+// After the shape phases of the second half: the first half is read again (texels and channel planes) for the chain phase.
+ITW_HD void bc7_phase_park(int lane, Bc7Warp& W, const SurfaceView& s, long long first_block, int ntotal)
+{
+    if (ntotal <= kBc7Batch) return;                       // single-half round: blk[] still holds it
+    const int bw = s.width >> 2;
+    for (int t = lane; t < kBc7Batch * 16; t += 32) {
+        const int slot = t >> 4, k = t & 15;
+        const long long id = first_block + slot;
+        const int by = (int)(id / bw), bx = (int)(id - (long long)by * bw);
+        const uint8_t* p = s.ptr + (size_t)(by * 4 + (k >> 2)) * (size_t)s.stride + (size_t)(bx * 4 + (k & 3)) * 4;
+        const u32 rgb = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16);
+        W.parked[slot].rgb[k] = rgb;
+        W.parked[slot].tex[k] = rgb | ((u32)p[3] << 24);
+        // plane word (c, i) = channel c of texels 4i..4i+3: here c = k & 3, i = k >> 2 (any bijection of 16 onto (c, i) does)
+        const int c = k & 3, i = k >> 2;
+        u32 v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int kk = 4 * i + j;
+            v |= (u32)s.ptr[(size_t)(by * 4 + (kk >> 2)) * (size_t)s.stride + (size_t)(bx * 4 + (kk & 3)) * 4 + c] << (8 * j);
+        }
+        W.parked[slot].plane[c][i] = v;
+    }
+    if (lane == 0) W.nparked = kBc7Batch;
 }
 // channel planes from the packed texels (a 4x4 byte transpose per group of four texels)
 ITW_HD void bc7_phase_planes(int lane, Bc7Warp& W)
@@ -962,10 +1051,10 @@ ITW_HD_NOINLINE void bc7_eval_shape(Bc7Warp& W, int lane, int slot, const Bc7Blo
     }
     const u32 pattern = shape_pattern(shape);
     if (do_a)
-        W.cand_err[slot][0][n] = bc7_assign(W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_a), pairs, pattern, ends_a[0], ends_a[1], ends_a[2],
+        W.cand_err[slot][0][n] = bc7_assign(W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_a) | kAssignThresholds, pairs, pattern, ends_a[0], ends_a[1], ends_a[2],
                                             ends_a[3], ends_a[4], ends_a[5], chmask).err;
     if (do_b)
-        W.cand_err[slot][1][n] = bc7_assign(W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_b), pairs, pattern, ends_b[0], ends_b[1], ends_b[2],
+        W.cand_err[slot][1][n] = bc7_assign(W.palette, lane, blk, 3, 1, bc7_mode_bits(mode_b) | kAssignThresholds, pairs, pattern, ends_b[0], ends_b[1], ends_b[2],
                                             ends_b[3], ends_b[4], ends_b[5], chmask).err;
 }
 // ---- three-subset shapes (modes 0 and 2) -------------------------------------------------------------------
@@ -985,13 +1074,13 @@ ITW_HD void bc7_phase_masks3(int lane, Bc7Warp& W, const Bc7Params& P, int duo)
         const Bc7Seg seg = bc7_fit(blk, 3, 1, (u32)ITW_TABLE(mask3_unique)[u], 3);
         if (cb > 0) {
             const Bc7Packed pk = bc7_quantise(seg, 2, 3);
-            W.ends3_mode2[s][u][0] = pk.dec_a;
-            W.ends3_mode2[s][u][1] = pk.dec_b;
+            W.ends3.mode2[s][u][0] = pk.dec_a;
+            W.ends3.mode2[s][u][1] = pk.dec_b;
         }
         if (ca > 0 && u < ITW_MASK3_FIRST) {
             const Bc7Packed pk = bc7_quantise(seg, 0, 3);
-            W.ends3_mode0[s][u][0] = pk.dec_a;
-            W.ends3_mode0[s][u][1] = pk.dec_b;
+            W.ends3.mode0[s][u][0] = pk.dec_a;
+            W.ends3.mode0[s][u][1] = pk.dec_b;
         }
     }
 }
@@ -1007,13 +1096,13 @@ ITW_HD void bc7_phase_shapes3(int lane, Bc7Warp& W, const Bc7Params& P, int duo)
         const u32 pattern = shape_pattern(64 + n);
         const int u0 = ITW_TABLE(shape3_mask_id)[3 * n], u1 = ITW_TABLE(shape3_mask_id)[3 * n + 1], u2 = ITW_TABLE(shape3_mask_id)[3 * n + 2];
         if (n < ca)
-            W.cand_err[slot][0][n] = bc7_assign(W.palette, lane, blk, 3, 1, 3, 3, pattern, W.ends3_mode0[s][u0][0], W.ends3_mode0[s][u0][1],
-                                                W.ends3_mode0[s][u1][0], W.ends3_mode0[s][u1][1], W.ends3_mode0[s][u2][0],
-                                                W.ends3_mode0[s][u2][1], 0x00FFFFFFu).err;
+            W.cand_err[slot][0][n] = bc7_assign(W.palette, lane, blk, 3, 1, 3, 3, pattern, W.ends3.mode0[s][u0][0], W.ends3.mode0[s][u0][1],
+                                                W.ends3.mode0[s][u1][0], W.ends3.mode0[s][u1][1], W.ends3.mode0[s][u2][0],
+                                                W.ends3.mode0[s][u2][1], 0x00FFFFFFu).err;
         if (n < cb)
-            W.cand_err[slot][1][n] = bc7_assign(W.palette, lane, blk, 3, 1, 2, 3, pattern, W.ends3_mode2[s][u0][0], W.ends3_mode2[s][u0][1],
-                                                W.ends3_mode2[s][u1][0], W.ends3_mode2[s][u1][1], W.ends3_mode2[s][u2][0],
-                                                W.ends3_mode2[s][u2][1], 0x00FFFFFFu).err;
+            W.cand_err[slot][1][n] = bc7_assign(W.palette, lane, blk, 3, 1, 2 | kAssignThresholds, 3, pattern, W.ends3.mode2[s][u0][0], W.ends3.mode2[s][u0][1],
+                                                W.ends3.mode2[s][u1][0], W.ends3.mode2[s][u1][1], W.ends3.mode2[s][u2][0],
+                                                W.ends3.mode2[s][u2][1], 0x00FFFFFFu).err;
     }
 }
 
@@ -1067,53 +1156,57 @@ ITW_HD void bc7_phase_winners(int lane, Bc7Warp& W, const Bc7Params& P, int g, i
             const int e = W.cand_err[slot][which][n];
             if (e < best_err) { best_err = e; best = n; }
         }
-        W.win_shape[kBc7Slots * g + slot][m] = (best < 0) ? -1 : bc7_slot_shape(W, slot, m, best);
+        W.win_shape[kBc7Batch * W.half + kBc7Slots * g + slot][m] = (best < 0) ? -1 : bc7_slot_shape(W, slot, m, best);
     }
 }
-// Chain phase over the whole batch.  Lane L works for block L % 8 in every pass and runs roles L / 8, L / 8 + 4, ...: a pass
-// holds four consecutive roles for the eight blocks, so its lanes run the same KIND of role (partitioned / mode 4-5 / mode 6)
-// almost everywhere, and a lane can keep the best candidate of ITS block in registers.  The first strict minimum in role
-// order is kept (K:1358, :1638, :1650, :1684): a lane meets its roles in ascending order, the store phase compares (error, role).
+// Chain phase over the whole round.  With nb = 16 (two halves) or 8 blocks, lane L works for block L % nb in every pass and
+// runs the active roles L / nb, L / nb + 32 / nb, ...: a pass holds 32 / nb consecutive roles for all blocks, so its lanes run
+// the same KIND of role (partitioned / mode 4-5 / mode 6) almost everywhere, and a lane keeps the best candidate of ITS block
+// in registers.  Sixteen blocks make a pass two roles wide: (mode 0, mode 2), (mode 1, mode 3), (rotation, rotation), ... are
+// equally long, where four-wide passes pair three-subset with two-subset chains and leave the last pass half empty.
+// The first strict minimum in role order is kept (K:1358, :1638, :1650, :1684): a lane meets its roles in ascending order,
+// the store phase compares (error, role).
 ITW_HD void bc7_phase_chains(int lane, Bc7Warp& W, const Bc7Params& P)
 {
-    const int nroles = bc7_role_count(P);
-    const int slot = lane & (kBc7Batch - 1);
+    const int nactive = bc7_active_roles(P);
+    const int nb = (W.ntotal > kBc7Batch) ? kBc7Super : kBc7Batch;
+    const int slot = lane & (nb - 1);
     int best_err = kErrNone, best_role = 0;
     u32 code[4] = {0u, 0u, 0u, 0u};
-    if (slot < W.nvalid)
-        for (int r = lane / kBc7Batch; r < nroles; r += 32 / kBc7Batch) {
+    if (slot < W.ntotal)
+        for (int i = lane / nb; i < nactive; i += 32 / nb) {
+            const int r = bc7_active_role(P, i);
             const Bc7Result res = bc7_chain(W, P, lane, slot, r);
             if (res.err < best_err) {
                 best_err = res.err; best_role = r;
 #pragma unroll
-                for (int i = 0; i < 4; i++) code[i] = res.code[i];
+                for (int j = 0; j < 4; j++) code[j] = res.code[j];
             }
         }
-    W.lane_err[lane] = best_err;
-    W.lane_role[lane] = best_role;
+    W.fin.err[lane] = best_err;
+    W.fin.role[lane] = best_role;
 #pragma unroll
-    for (int i = 0; i < 4; i++) W.lane_code[lane][i] = code[i];
+    for (int i = 0; i < 4; i++) W.fin.code[lane][i] = code[i];
 }
-// the block's winner among the four lanes that worked for it, then the 16-byte store; K:2027
+// the block's winner among the lanes that worked for it, then the 16-byte store; K:2027
 ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* dst, long long first_block)
 {
     (void)P;
-    for (int t = lane; t < W.nvalid; t += 32) {
+    const int nb = (W.ntotal > kBc7Batch) ? kBc7Super : kBc7Batch;
+    for (int t = lane; t < W.ntotal; t += 32) {
         int best = t;
-        for (int j = 1; j < 32 / kBc7Batch; j++) {
-            const int l = t + kBc7Batch * j;
-            if (W.lane_err[l] < W.lane_err[best] || (W.lane_err[l] == W.lane_err[best] && W.lane_role[l] < W.lane_role[best])) best = l;
+        for (int j = 1; j < 32 / nb; j++) {
+            const int l = t + nb * j;
+            if (W.fin.err[l] < W.fin.err[best] || (W.fin.err[l] == W.fin.err[best] && W.fin.role[l] < W.fin.role[best])) best = l;
         }
         u32* out = reinterpret_cast<u32*>(dst + (size_t)(first_block + t) * 16);
 #pragma unroll
-        for (int i = 0; i < 4; i++) out[i] = W.lane_code[best][i];
+        for (int i = 0; i < 4; i++) out[i] = W.fin.code[best][i];
     }
 }
 
-// The whole program for one batch, as a list of (phase, barrier) pairs.
-#define ITW_BC7_PROGRAM(PHASE)                                                         \
-    PHASE(bc7_phase_load(lane, W, surf, first_block, nvalid));                         \
-    ITW_BC7_PROGRAM_AFTER_LOAD(PHASE)
+// The program of one round (up to kBc7Super blocks: `nvalid` of them from `first_block` of `surf`, results to block
+// `out_block` of `dst`), as a list of (phase, barrier) pairs.
 #define ITW_BC7_GROUP_PROGRAM(PHASE, g)                                                \
     if (P.sel[0]) {                                                                    \
         PHASE(bc7_phase_masks3(lane, W, P, 2 * (g)));                                  \
@@ -1134,12 +1227,23 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
         PHASE(bc7_phase_shapes(lane, W, P, g, 4, 4));                                  \
         PHASE(bc7_phase_winners(lane, W, P, g, 4, 4));                                 \
     }
-#define ITW_BC7_PROGRAM_AFTER_LOAD(PHASE)                                              \
+#define ITW_BC7_HALF_PROGRAM(PHASE, h)                                                 \
+    PHASE(bc7_phase_load(lane, W, surf, first_block, nvalid, h));                      \
     PHASE(bc7_phase_planes(lane, W));                                                  \
     ITW_BC7_GROUP_PROGRAM(PHASE, 0)                                                    \
-    ITW_BC7_GROUP_PROGRAM(PHASE, 1)                                                    \
+    ITW_BC7_GROUP_PROGRAM(PHASE, 1)
+#define ITW_BC7_SHAPE_PROGRAM(PHASE)                                                   \
+    ITW_BC7_HALF_PROGRAM(PHASE, 0)                                                     \
+    if (per_warp > kBc7Batch) {                                                        \
+        ITW_BC7_HALF_PROGRAM(PHASE, 1)                                                 \
+        PHASE(bc7_phase_park(lane, W, surf, first_block, nvalid));                     \
+    }
+#define ITW_BC7_CHAIN_PROGRAM(PHASE)                                                   \
     PHASE(bc7_phase_chains(lane, W, P));                                               \
-    PHASE(bc7_phase_store(lane, W, P, dst, first_block));
+    PHASE(bc7_phase_store(lane, W, P, dst, out_block));
+#define ITW_BC7_PROGRAM(PHASE)                                                         \
+    ITW_BC7_SHAPE_PROGRAM(PHASE)                                                       \
+    ITW_BC7_CHAIN_PROGRAM(PHASE)
 
 #if defined(__CUDACC__)
 // All warps of a CTA walk the phases in lock step (block barrier between phases) and one CTA fills an
@@ -1150,58 +1254,58 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
 constexpr int kBc7WarpsPerCta = 16;
 constexpr size_t kBc7SmemBytes = sizeof(Bc7Warp) * kBc7WarpsPerCta;
 
-// kTma: the 128 consecutive blocks a CTA works on in one round are fetched by the TMA engine
-// (cp.async.bulk, SASS UBLKCP) into a double-buffered 4-row shared-memory tile while the previous round is
-// being encoded, signalled through an mbarrier; the load phase then reads the tile from shared memory.
-// Needs 16-byte aligned surface rows; other surfaces use the plain global-load variant.
-constexpr int kBc7TileBlocks = kBc7WarpsPerCta * kBc7Batch;              // 128
-constexpr int kBc7TileRowBytes = kBc7TileBlocks * 16;                     // 2048
+// kTma: the consecutive blocks a CTA works on in one round (16 warps x per_warp blocks) are fetched by the TMA engine
+// (cp.async.bulk, SASS UBLKCP) into a 4-row shared-memory tile, signalled through an mbarrier; the load phases read the tile
+// from shared memory.  One tile buffer is enough: it is free again once the last load phase of a round is over, and the next
+// tile then streams in behind the whole chain phase.  Needs 16-byte aligned surface rows; other surfaces use the plain
+// global-load variant.
+// per_warp = kBc7Super for surfaces large enough to give every warp of the grid 16 blocks, kBc7Batch for small ones (more warps
+// busy; the chain phase then runs four roles wide).
+constexpr int kBc7TileBlocks = kBc7WarpsPerCta * kBc7Super;              // 256
+constexpr int kBc7TileRowBytes = kBc7TileBlocks * 16;                     // 4096
 
 template <bool kTma>
 __global__ void __launch_bounds__(kBc7WarpsPerCta * 32, 1)
-bc7_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc7Params P, long long nblocks)
+bc7_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc7Params P, long long nblocks, int per_warp)
 {
     extern __shared__ __align__(16) unsigned char bc7_smem[];
-    __shared__ __align__(128) unsigned char stage[kTma ? 2 : 1][kTma ? 4 * kBc7TileRowBytes : 16];
-    __shared__ __align__(8) unsigned long long full[2];
+    __shared__ __align__(128) unsigned char stage[kTma ? 4 * kBc7TileRowBytes : 16];
+    __shared__ __align__(8) unsigned long long full;
     Bc7Warp& W = reinterpret_cast<Bc7Warp*>(bc7_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nbatches = (nblocks + kBc7Batch - 1) / kBc7Batch;
+    const long long nbatches = (nblocks + per_warp - 1) / per_warp;
     const long long nwarps = (long long)gridDim.x * kBc7WarpsPerCta;
     const long long rounds = (nbatches + nwarps - 1) / nwarps;            // same trip count for every warp of the CTA
+    const int tile_blocks = kBc7WarpsPerCta * per_warp;
 
-    auto tile_first = [&](long long round) { return ((long long)blockIdx.x * kBc7WarpsPerCta + round * nwarps) * kBc7Batch; };
+    auto tile_first = [&](long long round) { return ((long long)blockIdx.x * kBc7WarpsPerCta + round * nwarps) * per_warp; };
     auto prefetch = [&](long long round) {                                // one thread feeds the TMA engine
         const long long fb = tile_first(round);
         if (round >= rounds || fb >= nblocks) return;
         const long long left = nblocks - fb;
-        tma_prefetch_tile(stage[round & 1], kBc7TileRowBytes, &full[round & 1], gsurf, fb,
-                          (int)(left < kBc7TileBlocks ? left : kBc7TileBlocks), 16);
+        tma_prefetch_tile(stage, kBc7TileRowBytes, &full, gsurf, fb, (int)(left < tile_blocks ? left : tile_blocks), 16);
     };
     if (kTma) {
-        if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+        if (threadIdx.x == 0) mbar_init(&full, 1);
         __syncthreads();
         if (threadIdx.x == 0) prefetch(0);
     }
     for (long long round = 0; round < rounds; round++) {
         const long long batch = (long long)blockIdx.x * kBc7WarpsPerCta + warp + round * nwarps;
-        long long first_block = batch * kBc7Batch;
-        const long long left = nblocks - first_block;
-        const int nvalid = (int)(left <= 0 ? 0 : (left < kBc7Batch ? left : kBc7Batch));
+        const long long out_block = batch * per_warp;
+        const long long left = nblocks - out_block;
+        const int nvalid = (int)(left <= 0 ? 0 : (left < per_warp ? left : per_warp));
         SurfaceView surf = gsurf;
-        const long long out_block = first_block;
+        long long first_block = out_block;
         if (kTma) {
-            if (threadIdx.x == 0) prefetch(round + 1);                   // next tile streams in behind this round's math
-            if (tile_first(round) < nblocks) mbar_wait(&full[round & 1], (unsigned)((round >> 1) & 1));
-            surf = SurfaceView{stage[round & 1], kBc7TileBlocks * 4, 4, kBc7TileRowBytes};
-            first_block = (long long)warp * kBc7Batch;                   // block index inside the staged tile
+            if (tile_first(round) < nblocks) mbar_wait(&full, (unsigned)(round & 1));
+            surf = SurfaceView{stage, kBc7TileBlocks * 4, 4, kBc7TileRowBytes};
+            first_block = (long long)warp * per_warp;                    // block index inside the staged tile
         }
 #define ITW_PHASE_DEVICE(call) call; __syncthreads()
-        {
-            ITW_PHASE_DEVICE(bc7_phase_load(lane, W, surf, first_block, nvalid));
-            first_block = out_block;
-            ITW_BC7_PROGRAM_AFTER_LOAD(ITW_PHASE_DEVICE)
-        }
+        ITW_BC7_SHAPE_PROGRAM(ITW_PHASE_DEVICE)
+        if (kTma && threadIdx.x == 0) prefetch(round + 1);               // every load phase of this round is behind a barrier
+        ITW_BC7_CHAIN_PROGRAM(ITW_PHASE_DEVICE)
 #undef ITW_PHASE_DEVICE
     }
 }

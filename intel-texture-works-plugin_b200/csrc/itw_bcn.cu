@@ -196,18 +196,21 @@ int launch(int format, const SurfaceView& v, uint8_t* d_dst, const void* setting
             if (!settings) return fail("CompressBlocksBC7: null settings");
             const Bc7Params P = bc7_params_from(*static_cast<const bc7_enc_settings*>(settings));
             if (const char* why = bc7_params_check(P)) return fail(why);
-            // one 16-warp CTA per SM, persistent over the batches; TMA-staged variant when the surface allows it
+            // one 16-warp CTA per SM, persistent over the rounds; TMA-staged variant when the surface allows it.  A warp takes 16
+            // blocks per round when that still gives every SM a full CTA, else 8 (small surfaces / row bands: more warps busy)
             const bool tma = vec16;                                       // 16-byte aligned rows
-            const long long want = (nblocks + kBc7TileBlocks - 1) / kBc7TileBlocks;
             const long long cap = (long long)tls.sm_count;
+            const int per_warp = (nblocks >= cap * kBc7WarpsPerCta * kBc7Super) ? kBc7Super : kBc7Batch;
+            const long long tile = (long long)kBc7WarpsPerCta * per_warp;
+            const long long want = (nblocks + tile - 1) / tile;
             const unsigned grid = (unsigned)(want < cap ? want : cap);
             // per-device attribute; cheap enough to set on every (millisecond-scale) launch
             if (tma) {
                 ITW_CUDA(cudaFuncSetAttribute(bc7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc7SmemBytes));
-                bc7_kernel<true><<<grid, kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks);
+                bc7_kernel<true><<<grid, kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks, per_warp);
             } else {
                 ITW_CUDA(cudaFuncSetAttribute(bc7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBc7SmemBytes));
-                bc7_kernel<false><<<grid, kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks);
+                bc7_kernel<false><<<grid, kBc7WarpsPerCta * 32, kBc7SmemBytes, stream>>>(v, d_dst, P, nblocks, per_warp);
             }
             break;
         }

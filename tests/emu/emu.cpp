@@ -65,14 +65,18 @@ void emu_CompressBlocksBC5(const rgba_surface* src, uint8_t* dst)
 
 #define ITW_PHASE_EMU(call) for (int lane = 0; lane < 32; lane++) { call; }
 
+static int g_bc7_per_warp = kBc7Super;
+void emu_set_bc7_per_warp(int n) { g_bc7_per_warp = (n == kBc7Batch) ? kBc7Batch : kBc7Super; }   // what the host picks by surface size
 void emu_CompressBlocksBC7(const rgba_surface* src, uint8_t* dst, bc7_enc_settings* settings)
 {
     SurfaceView surf = view_of(src);
     const Bc7Params P = bc7_params_from(*settings);
     const long long nblocks = (long long)(surf.width / 4) * (surf.height / 4);
+    const int per_warp = g_bc7_per_warp;
     static thread_local Bc7Warp W;
-    for (long long first_block = 0; first_block < nblocks; first_block += kBc7Batch) {
-        const int nvalid = (int)((nblocks - first_block < kBc7Batch) ? (nblocks - first_block) : kBc7Batch);
+    for (long long first_block = 0; first_block < nblocks; first_block += per_warp) {
+        const int nvalid = (int)((nblocks - first_block < per_warp) ? (nblocks - first_block) : per_warp);
+        const long long out_block = first_block;
         ITW_BC7_PROGRAM(ITW_PHASE_EMU)
     }
 }

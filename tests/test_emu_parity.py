@@ -28,3 +28,26 @@ def test_ragged_batches_and_strides(fmt, prof):
         got = T.run(T.emu(), fmt, img, prof)
         want = T.run(T.oracle(), fmt, np.ascontiguousarray(img), prof)
         assert np.array_equal(got, want), (h, w, pad)
+
+
+@pytest.mark.parametrize("per_warp", [8, 16])
+@pytest.mark.parametrize("prof", ["slow", "alpha_slow", "alpha_fast", "veryfast"])
+def test_bc7_round_sizes(prof, per_warp):
+    """The BC7 warp program runs rounds of 16 blocks (two halves, one chain phase; large surfaces) or of 8 (small ones): both
+    forms, with every ragged remainder 1..17 of the last round, equal the oracle."""
+    import ctypes
+    emu = T.emu()
+    setter = emu.lib.emu_set_bc7_per_warp
+    setter.argtypes = [ctypes.c_int]
+    setter.restype = None
+    rng = np.random.default_rng(11)
+    try:
+        setter(per_warp)
+        for nblocks in (1, 7, 8, 9, 15, 16, 17, 33):
+            img = rng.integers(0, 256, (4, 4 * nblocks, 4)).astype(np.uint8)
+            img[:, : 4 * (nblocks // 2), 3] = 255                # opaque and translucent blocks side by side
+            got = T.run(emu, "BC7", img, prof)
+            want = T.run(T.oracle(), "BC7", img, prof)
+            assert np.array_equal(got, want), (prof, per_warp, nblocks)
+    finally:
+        setter(16)

@@ -1,6 +1,7 @@
 """The kernels replace IEEE divisions by the FMA-corrected quotient q' = q + (x - q*d)*rcp(d) wherever
 the operands come from a small known domain (itw_device.cuh: div_by_rcp).  That quotient is NOT
-correctly rounded in general, so every domain it is used on is checked exhaustively here (C, OpenMP)."""
+correctly rounded in general, so every domain it is used on is checked exhaustively here (C, OpenMP).
+The integer-threshold form of the two-bit index search (bc7.cuh) is checked against the float formula here too."""
 import os
 import subprocess
 import tempfile
@@ -54,6 +55,26 @@ int main(void) {
     for (int d = 5; d <= 7; d += 2)
         for (int x = 0; x <= 7; x++) bad += ((float)x / (float)d != dq((float)x, (float)d, 1.0f / (float)d));
     printf("ramp %lld\n", bad);
+    /* (6) two-bit index search by integer thresholds (bc7_assign): q1 = clamp((int)(x / d * 4 + 0.5), 1, 3) against
+       1 + [x >= ceil(3d/8)] + [x >= ceil(5d/8)], d in [1, 2^18] (the sum of <= 4 squared byte differences is < 2^18).
+       Both are non-decreasing step functions of the integer x, so they are equal everywhere iff they are equal on both sides of
+       every step and at the ends of the domain; small d are also swept exhaustively. */
+    bad = 0;
+    #pragma omp parallel for reduction(+:bad) schedule(dynamic, 64)
+    for (int d = 1; d <= (1 << 18); d++) {
+        const float fd = (float)d;
+        const int t2 = (3 * d + 7) >> 3, t3 = (5 * d + 7) >> 3;
+        const int probe[8] = {-(1 << 18), -1, 0, t2 - 1, t2, t3 - 1, t3, 1 << 18};
+        const int lo = (d <= 4096) ? -d - 8 : 0, hi = (d <= 4096) ? 2 * d + 8 : 7;
+        for (int i = lo; i <= hi; i++) {
+            const int x = (d <= 4096) ? i : probe[i];
+            volatile float p = (float)x / fd; volatile float p4 = p * 4.0f; volatile float y = p4 + 0.5f;
+            int q = (int)y; q = q < 1 ? 1 : (q > 3 ? 3 : q);
+            const int want = 1 + (x >= t2) + (x >= t3);
+            bad += (q != want);
+        }
+    }
+    printf("thresholds %lld\n", bad);
     return 0;
 }
 """
@@ -66,4 +87,4 @@ def test_fma_corrected_quotient_is_exact_on_every_domain_it_is_used_on():
         open(c, "w").write(SRC)
         subprocess.check_call(["gcc", "-O3", "-fopenmp", "-mavx2", "-mfma", "-ffp-contract=off", c, "-o", exe, "-lm"])
         out = subprocess.check_output([exe], text=True).split()
-    assert out == ["div255", "0", "count", "0", "proj", "0", "scalar", "0", "ramp", "0"], out
+    assert out == ["div255", "0", "count", "0", "proj", "0", "scalar", "0", "ramp", "0", "thresholds", "0"], out

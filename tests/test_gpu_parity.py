@@ -104,6 +104,25 @@ def test_unaligned_source_pointer():
         assert np.array_equal(T.run(lib, fmt, img, None), T.run(oracle, fmt, np.ascontiguousarray(img), None)), fmt
 
 
+@pytest.mark.parametrize("prof", ["veryfast", "alpha_fast"])
+def test_bc7_sixteen_block_rounds_ragged_and_unaligned(prof):
+    """Surfaces with at least 148 x 16 x 16 blocks run BC7 in rounds of sixteen blocks per warp (two halves, one chain phase;
+    smaller ones keep eight): a block count that fills neither the last round nor the last CTA tile, through the TMA-staged
+    kernel and -- from a source address that is not 16-byte aligned -- through the plain-load kernel, against the oracle."""
+    lib, oracle = T.product(), T.oracle()
+    h, w = 1020, 1028                                        # 255 x 257 = 65535 blocks
+    raw = np.random.default_rng(17).integers(0, 256, h * (w + 4) * 4 + 64, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 16
+    raw[off + 3::4][: raw.size // 8] = 255                   # first half opaque
+    aligned = raw[off:off + h * (w + 4) * 4].reshape(h, w + 4, 4)[:, :w]
+    shifted = raw[off + 4:off + 4 + h * (w + 4) * 4].reshape(h, w + 4, 4)[:, :w]
+    assert aligned.ctypes.data % 16 == 0 and shifted.ctypes.data % 16 == 4
+    for img in (aligned, shifted):
+        got = T.run(lib, "BC7", img, prof)
+        want = T.run(oracle, "BC7", np.ascontiguousarray(img), prof)
+        assert T.differing_blocks(got, want, 16) == 0
+
+
 def test_errors_are_reported_not_swallowed():
     lib = T.product()
     img = np.zeros((6, 8, 4), np.uint8)                                # height not a multiple of 4

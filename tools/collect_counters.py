@@ -6,7 +6,8 @@ roofline.traffic / the issue-rate roofline).
     gpurun -- 'python tools/collect_counters.py gpurun_out/counters.json'       (then copy into profiles/dram_traffic.json)
 
 One `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum` pass per config over
-`bench.py --format F --profile P --size S --steps 1 --warmup 1 --no-cpu --no-extras`; the LAST launch of the kernel is taken."""
+`bench.py --format F --profile P --size S --steps 1 --warmup 1 --no-cpu --no-extras`; the last WHOLE-SURFACE launch of the kernel is taken (most executed
+instructions; the end-to-end leg's row-band launches are smaller)."""
 import csv
 import json
 import subprocess
@@ -19,7 +20,7 @@ METRICS = "dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum"
 def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/counters.json"
     out = {"_comment": "per launch of the dominant kernel at the named workload (tools/collect_counters.py: ncu --metrics " + METRICS +
-                       " --clock-control none, last launch of `bench.py --steps 1 --warmup 1`): dram = read + write bytes, warp_inst = smsp__inst_executed.sum",
+                       " --clock-control none, last whole-surface launch of `bench.py --steps 1 --warmup 1`): dram = read + write bytes, warp_inst = smsp__inst_executed.sum",
            "warp_inst": {}, "_kernel": {}}
     for size in (4096, 8192):
         for fmt, prof, kern in SWEEP:
@@ -37,7 +38,8 @@ def main():
                 continue
             hdr = rows[0]
             im, iv, ik, iid = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name"), hdr.index("ID")
-            last = max(int(r[iid]) for r in rows[1:])
+            inst = {int(r[iid]): float(r[iv].replace(",", "")) for r in rows[1:] if r[im] == "smsp__inst_executed.sum"}
+            last = max(inst, key=lambda i: (inst[i], i))               # the whole-surface launch (the end-to-end leg encodes in row bands): most instructions, latest
             vals = {r[im]: float(r[iv].replace(",", "")) for r in rows[1:] if int(r[iid]) == last}
             unit = {r[im]: r[hdr.index("Metric Unit")] for r in rows[1:] if int(r[iid]) == last}
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
