@@ -278,9 +278,11 @@ ITW_HD void bc7_fit_impl(float (&ep)[8], const View& v, u32 mask)
     float lo = inf_f(), hi = -inf_f();
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        float d = 0.0f;
+        // the reference starts the sum from 0.0f; 0 + x differs from x only in the sign of a zero, which nothing below can
+        // observe (see the next comment), so the sum starts from the first product
+        float d = axis[0] * ((float)((P[0][k >> 2] >> (8 * (k & 3))) & 255u) - mean[0]);
 #pragma unroll
-        for (int c = 0; c < CH; c++) d += axis[c] * ((float)((P[c][k >> 2] >> (8 * (k & 3))) & 255u) - mean[c]);
+        for (int c = 1; c < CH; c++) d += axis[c] * ((float)((P[c][k >> 2] >> (8 * (k & 3))) & 255u) - mean[c]);
         // d is finite here (8-bit texels, finite axis), so the reference's (a<b)?a:b equals fminf/fmaxf up to
         // the sign of a zero, which the affine map below cannot observe: one FMNMX instead of FSETP+FSEL
         if ((mask >> k) & 1u) {
@@ -374,12 +376,14 @@ ITW_HD_NOINLINE int bc7_split_key(const Bc7Block* blk, int shape, int channels)
 ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
 {
     const float (&ep)[8] = seg.v;
-    const int family = (mode == 1) ? 1 : ((mode == 2 || mode == 4 || mode == 5) ? 2 : 0);
+    // per-mode constants from nibble tables (mode 0 in the low nibble): nested conditionals on `mode` compile to a jump table
+    // that cost more than a tenth of this routine
+    const int family = (int)((0x00220210u >> (4 * mode)) & 3u);           // 1: mode 1; 2: modes 2, 4, 5; else 0
     // stored bits per component including the p-bit: 2^qbits - 1 is K's `levels2` (p-bit modes) or `levels-1`
-    const int qbits = (mode == 0 || mode == 2 || mode == 4) ? 5 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 8));
+    const int qbits = (int)((0x68758575u >> (4 * mode)) & 15u);           // modes 0,2,4: 5; 1,5: 7; 7: 6; 3,6: 8
     const int top = (1 << qbits) - 1;
     const float ftop = (float)top;
-    const int vote_bits = (mode == 0) ? 5 : ((mode == 1) ? 7 : 8);       // expand_bits(v, 8) == v
+    const int vote_bits = (int)((0x88888875u >> (4 * mode)) & 15u);       // mode 0: 5; mode 1: 7; else 8 (expand_bits(v, 8) == v)
     const int votes = (mode == 1) ? 3 : channels;
     // Conversions: |ep| < 2^31 always holds here -- the fit clamps to [0,255] and the least-squares
     // solve divides by an exact non-zero INTEGER determinant (bc7_solve), which bounds |ep| by ~1.2e7 --
@@ -436,7 +440,7 @@ ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
     if (family == 1) pick1[0] = pick1[1];                                // decided after both endpoints
     if (family == 2) pick1[0] = pick1[1] = false;
     // decode all four bytes at once (K:1093-1122): v << (8-d) | that >> d, bytewise
-    const int dbits = (mode == 3 || mode == 6) ? 8 : ((mode == 1 || mode == 5) ? 7 : ((mode == 7) ? 6 : 5));
+    const int dbits = qbits;                                             // every mode decodes the bits it stores
     const u32 lowmask = 0x01010101u * (0xFFu >> dbits);
     u32 dec[2], qq[2];
 #pragma unroll
@@ -447,16 +451,6 @@ ITW_HD_NOINLINE Bc7Packed bc7_quantise(Bc7Seg seg, int mode, int channels)
         qq[i] = q;
     }
     return Bc7Packed{dec[0], dec[1], qq[0], qq[1]};
-}
-
-// Integer interpolation of two packed RGBA endpoints with BC7 weight w (K:1172: ((64-w)a+wb+32)/64
-// truncated), two channels per multiply.
-ITW_HD u32 lerp_rgba(u32 a, u32 b, u32 w)
-{
-    const u32 m = 0x00FF00FFu;
-    u32 rb = (((64u - w) * (a & m) + w * (b & m) + 0x00200020u) >> 6) & m;
-    u32 ga = (((64u - w) * ((a >> 8) & m) + w * ((b >> 8) & m) + 0x00200020u) >> 6) & m;
-    return rb | (ga << 8);
 }
 
 // Index search; K:1133-1193.  ends[2j], ends[2j+1] = decoded endpoints A,B of subset j (RGBA bytes);
@@ -475,20 +469,38 @@ ITW_HD_NOINLINE Bc7Search bc7_assign(u32 (*pal)[32], int lane, const Bc7Block* b
     const int levels = 1 << bits;
     // per-subset constants go to lane-private shared memory too and are fetched by subset id in the texel
     // loop: the load/store pipe is nearly idle in this kernel while the ALU pipe (selects) is the busiest
+    u32 cur_a = e0, cur_b = e1, next_a = e2, next_b = e3;        // endpoints walk through two register pairs: no select by j
     for (int j = 0; j < pairs; j++) {
-        const u32 a = ((j == 0) ? e0 : ((j == 1) ? e2 : e4)) & chmask, b = ((j == 0) ? e1 : ((j == 1) ? e3 : e5)) & chmask;
+        const u32 a = cur_a & chmask, b = cur_b & chmask;
+        cur_a = next_a; cur_b = next_b; next_a = e4; next_b = e5;
         const u32 aa = dp4a_u8(a, a, 0u), ab = dp4a_u8(a, b, 0u), bb = dp4a_u8(b, b, 0u);
         const int idiv = (int)(bb - 2u * ab + aa);               // sum of squared differences, exact
-        const float fdiv = (float)idiv;
-        const float frcp = 1.0f / fdiv;                          // inf when the endpoints coincide (-> NaN below, as 0/0)
         pal[24 + 5 * j + 0][lane] = a;
         pal[24 + 5 * j + 1][lane] = b;
         pal[24 + 5 * j + 2][lane] = ab - aa;
-        // two-bit search by thresholds: q1 >= m  <=>  8 num >= (2m - 1) div  <=>  num >= ceil((2m - 1) div / 8), m = 2, 3
-        // (see the texel loop); coincident endpoints give 0/0 = NaN -> q1 = 1 in the reference: thresholds out of reach
-        pal[24 + 5 * j + 3][lane] = thresholds ? (u32)(idiv ? (3 * idiv + 7) >> 3 : 0x7fffffff) : float_bits(fdiv);
-        pal[24 + 5 * j + 4][lane] = thresholds ? (u32)(idiv ? (5 * idiv + 7) >> 3 : 0x7fffffff) : float_bits(frcp);
-        for (int q = 0; q < levels; q++) pal[j * levels + q][lane] = lerp_rgba(a, b, (u32)bc7_weight(bits, q));
+        if (thresholds) {
+            // two-bit search by thresholds: q1 >= m  <=>  8 num >= (2m - 1) div  <=>  num >= ceil((2m - 1) div / 8), m = 2, 3
+            // (see the texel loop); coincident endpoints give 0/0 = NaN -> q1 = 1 in the reference: thresholds out of reach
+            pal[24 + 5 * j + 3][lane] = (u32)(idiv ? (3 * idiv + 7) >> 3 : 0x7fffffff);
+            pal[24 + 5 * j + 4][lane] = (u32)(idiv ? (5 * idiv + 7) >> 3 : 0x7fffffff);
+        } else {
+            const float fdiv = (float)idiv;
+            pal[24 + 5 * j + 3][lane] = float_bits(fdiv);
+            pal[24 + 5 * j + 4][lane] = float_bits(1.0f / fdiv);  // inf when the endpoints coincide (-> NaN below, as 0/0)
+        }
+        // Palette, K:1172: ((64 - w) a + w b + 32) >> 6 per channel, two channels per 32-bit word.  Written as
+        // (64 a + 32) + w (b - a): the packed difference may borrow across the 16-bit lanes, but every lane of the SUM is the
+        // non-negative 14-bit value above, so the word arithmetic is exact.  Entries 0 and levels-1 are the endpoints.
+        const u32 m = 0x00FF00FFu;
+        const u32 a_rb = a & m, a_ga = (a >> 8) & m;
+        const u32 base_rb = (a_rb << 6) + 0x00200020u, base_ga = (a_ga << 6) + 0x00200020u;
+        const u32 d_rb = (b & m) - a_rb, d_ga = ((b >> 8) & m) - a_ga;
+        pal[j * levels][lane] = a;
+        pal[j * levels + levels - 1][lane] = b;
+        for (int q = 1; q < levels - 1; q++) {
+            const u32 w = (u32)bc7_weight(bits, q);
+            pal[j * levels + q][lane] = (((base_rb + w * d_rb) >> 6) & m) | (((base_ga + w * d_ga) << 2) & 0xFF00FF00u);
+        }
     }
     const float flevels = (float)levels;
     int total = 0;
@@ -1227,15 +1239,19 @@ ITW_HD void bc7_phase_store(int lane, Bc7Warp& W, const Bc7Params& P, uint8_t* d
         PHASE(bc7_phase_shapes(lane, W, P, g, 4, 4));                                  \
         PHASE(bc7_phase_winners(lane, W, P, g, 4, 4));                                 \
     }
-#define ITW_BC7_HALF_PROGRAM(PHASE, h)                                                 \
-    PHASE(bc7_phase_load(lane, W, surf, first_block, nvalid, h));                      \
-    PHASE(bc7_phase_planes(lane, W));                                                  \
-    ITW_BC7_GROUP_PROGRAM(PHASE, 0)                                                    \
-    ITW_BC7_GROUP_PROGRAM(PHASE, 1)
+// The halves and the groups are LOOPS, not copies: four inlined copies of every shape phase made the kernel body 6.6 k
+// instructions (105 KB) -- the phases of one copy are what the instruction cache should hold.
 #define ITW_BC7_SHAPE_PROGRAM(PHASE)                                                   \
-    ITW_BC7_HALF_PROGRAM(PHASE, 0)                                                     \
+    ITW_UNROLL(1)                                                                      \
+    for (int half = 0; half < ((per_warp > kBc7Batch) ? 2 : 1); half++) {              \
+        PHASE(bc7_phase_load(lane, W, surf, first_block, nvalid, half));               \
+        PHASE(bc7_phase_planes(lane, W));                                              \
+        ITW_UNROLL(1)                                                                  \
+        for (int g = 0; g < kBc7Batch / kBc7Slots; g++) {                              \
+            ITW_BC7_GROUP_PROGRAM(PHASE, g)                                            \
+        }                                                                              \
+    }                                                                                  \
     if (per_warp > kBc7Batch) {                                                        \
-        ITW_BC7_HALF_PROGRAM(PHASE, 1)                                                 \
         PHASE(bc7_phase_park(lane, W, surf, first_block, nvalid));                     \
     }
 #define ITW_BC7_CHAIN_PROGRAM(PHASE)                                                   \
