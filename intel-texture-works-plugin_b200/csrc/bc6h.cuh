@@ -235,15 +235,17 @@ ITW_HD_NOINLINE BitSink bc6_put_header(unsigned long long ch0, unsigned long lon
 }
 
 // ---- index search, three channels, decoded endpoints are integers 0..65535; K:1133-1193 ----
-// D[j][c] = decoded endpoints A | B << 16 of subset j.  The two palette entries are computed with
-// integer arithmetic: (64-w)*a + w*b + 32 < 2^23 is exact in the reference's float evaluation and its
-// (int) cast is a floor, so the integer shift gives the same value.  Everything that involves the
-// (non-integer) texels stays in float, in the reference's order, with the x86 conversion rule.
+// D[j][c] = decoded endpoints A | B << 16 of subset j.  Per subset and channel the loop keeps A and B - A as floats (both
+// exact).  A palette entry is ((64-w) a + w b + 32) / 64 cast to int in the reference, every intermediate an exact integer
+// below 2^23; here it is floor((64 a + 32 + w (b - a)) / 64) in float -- the same integer, exact at every step, without a
+// conversion per texel.  Everything that involves the (non-integer) texels stays in float, in the reference's order, with
+// the x86 conversion rule.  Sums the reference starts from 0.0f start from their first term: 0 + x differs from x only in
+// the sign of a zero, which the quotient below (0 / d -> index 1 either way) and the squared errors (never negative) hide.
 ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32 d00, u32 d01, u32 d02, u32 d10, u32 d11, u32 d12)
 {
     const int levels = 1 << bits;
     const float flevels = (float)levels;
-    int ea[2][3], eb[2][3];
+    float fa[2][3], fd[2][3];
     float div[2], rdiv[2];
     const u32 D[2][3] = {{d00, d01, d02}, {d10, d11, d12}};
 #pragma unroll
@@ -251,9 +253,10 @@ ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32
         float d2 = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            ea[j][c] = (int)(D[j][c] & 0xFFFFu);
-            eb[j][c] = (int)(D[j][c] >> 16);
-            d2 += sq((float)(eb[j][c] - ea[j][c]));          // K:1155; the difference of two exact integers is exact
+            const int a = (int)(D[j][c] & 0xFFFFu), b = (int)(D[j][c] >> 16);
+            fa[j][c] = (float)a;
+            fd[j][c] = (float)(b - a);                       // K:1155; the difference of two exact integers is exact
+            d2 += sq(fd[j][c]);
         }
         div[j] = d2;
         rdiv[j] = 1.0f / d2;                                 // inf when the endpoints coincide: 0 * inf = NaN below, as 0 / 0
@@ -263,27 +266,29 @@ ITW_HD_NOINLINE Bc6Search bc6_assign(const float* px, int bits, u32 pattern, u32
     ITW_UNROLL(ITW_BC6_ASSIGN_UNROLL)
     for (int k = 0; k < 16; k++) {
         const bool second = ((pattern >> (2 * k)) & 3u) != 0u;
-        int a[3], b[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { a[c] = second ? ea[1][c] : ea[0][c]; b[c] = second ? eb[1][c] : eb[0][c]; }
-        float t[3], proj = 0.0f;
+        float a[3], d[3], t[3], proj = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
+            a[c] = second ? fa[1][c] : fa[0][c];
+            d[c] = second ? fd[1][c] : fd[0][c];
             t[c] = px[16 * c + k];
-            proj += (t[c] - (float)a[c]) * (float)(b[c] - a[c]);
+            const float term = (t[c] - a[c]) * d[c];
+            proj = (c == 0) ? term : proj + term;
         }
         // the FMA-corrected quotient equals the IEEE quotient for every pair of normal floats (proved by exhaustion over
         // all 2^46 significand pairs, tests/test_gpu_division.py); proj is 0 or >= 2^-22 in magnitude and div >= 1
         proj = div_by_rcp(proj, second ? div[1] : div[0], second ? rdiv[1] : rdiv[0]);
         const int q1 = clampi(cvt_x86(fma_rn(proj, flevels, 0.5f)), 1, levels - 1);   // proj*levels is exact
-        const int w0 = bc7_weight(bits, q1 - 1), w1 = bc7_weight(bits, q1);
+        const float w0 = (float)bc7_weight(bits, q1 - 1), w1 = (float)bc7_weight(bits, q1);
         float err0 = 0.0f, err1 = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const float d0 = (float)(((64 - w0) * a[c] + w0 * b[c] + 32) >> 6);
-            const float d1 = (float)(((64 - w1) * a[c] + w1 * b[c] + 32) >> 6);
-            err0 += sq(d0 - t[c]);
-            err1 += sq(d1 - t[c]);
+            const float base = fma_rn(a[c], 64.0f, 32.0f);                             // exact
+            const float d0 = floorf(fma_rn(w0, d[c], base) * 0.015625f);
+            const float d1 = floorf(fma_rn(w1, d[c], base) * 0.015625f);
+            const float s0 = sq(d0 - t[c]), s1 = sq(d1 - t[c]);
+            err0 = (c == 0) ? s0 : err0 + s0;
+            err1 = (c == 0) ? s1 : err1 + s1;
         }
         const bool first = err0 < err1;
         const int best_err = cvt_x86(first ? err0 : err1);                             // K:1178-1183 (quirk Q3)

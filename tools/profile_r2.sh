@@ -12,7 +12,7 @@ full() {  # name, kernel regex, mangled-section, command...
     local name=$1 kern=$2 section=$3; shift 3
     $NCU --set full --import-source on -k regex:$kern -c 1 -f -o $OUT/${TAG}_$name "$@" > $OUT/${TAG}_$name.log 2>&1
     python profiles/summarise.py $OUT/${TAG}_$name.ncu-rep $kern $LIB $section > $OUT/${TAG}_${name}_ncu.txt 2>> $OUT/${TAG}_$name.log
-    [ "$name" = bc7_slow ] || rm -f $OUT/${TAG}_$name.ncu-rep
+    [ "$name" = bc7_slow ] || [ "$name" = bc6h_slow ] || rm -f $OUT/${TAG}_$name.ncu-rep
 }
 many() {  # name, kernel regex, count, command...: --set full without source, every matching launch summarised
     local name=$1 kern=$2 count=$3; shift 3
