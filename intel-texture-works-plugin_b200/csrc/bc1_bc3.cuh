@@ -37,9 +37,13 @@ ITW_HD u32 bc1_linear_indices(const float (&px)[3][16], int p0, int p1)
     unpack565(b, p1);
 #pragma unroll
     for (int c = 0; c < 3; c++) dir[c] = b[c] - a[c];
-    float n2 = 0.0f;
+    // Sums the reference starts from 0.0f start from their first term throughout this file: 0 + x differs from x only when x is
+    // -0, and no consumer can see the sign of a zero here -- squares and sums of bytes are never -0; a projection d only meets
+    // min/max, a difference, or d + bias with bias != -0; a covariance cross term is -0 only if every product is, which the
+    // deviations from an exact mean (never all negative, never -0) rule out.
+    float n2 = sq(dir[0]);
 #pragma unroll
-    for (int c = 0; c < 3; c++) n2 += sq(dir[c]);
+    for (int c = 1; c < 3; c++) n2 += sq(dir[c]);
     float inv = 1.0f / n2;
 #pragma unroll
     for (int c = 0; c < 3; c++) dir[c] *= inv * 3.0f;
@@ -49,9 +53,9 @@ ITW_HD u32 bc1_linear_indices(const float (&px)[3][16], int p0, int p1)
     u32 bits = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        float d = 0.0f;
+        float d = px[0][k] * dir[0];
 #pragma unroll
-        for (int c = 0; c < 3; c++) d += px[c][k] * dir[c];
+        for (int c = 1; c < 3; c++) d += px[c][k] * dir[c];
         // |d + bias| < 2^31; the only special value is NaN (p0 == p1), INT_MIN on x86 and 0 here: both clamp to 0
         int q = clampi(trunc_i(d + bias), 0, 3);
         bits |= (u32)q << (2 * k);      // == K's bits += q*4^k: the fields never overlap
@@ -66,17 +70,20 @@ ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
     float mean[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        float acc = 0.0f;
+        float acc = px[c][0];
 #pragma unroll
-        for (int k = 0; k < 16; k++) acc += px[c][k];
+        for (int k = 1; k < 16; k++) acc += px[c][k];
         mean[c] = acc / 16.0f;
     }
     float crr = 0.0f, crg = 0.0f, crb = 0.0f, cgg = 0.0f, cgb = 0.0f, cbb = 0.0f;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         float r = px[0][k] - mean[0], g = px[1][k] - mean[1], b = px[2][k] - mean[2];
-        crr += r * r; crg += r * g; crb += r * b;
-        cgg += g * g; cgb += g * b; cbb += b * b;
+        if (k == 0) { crr = r * r; crg = r * g; crb = r * b; cgg = g * g; cgb = g * b; cbb = b * b; }
+        else {
+            crr += r * r; crg += r * g; crb += r * b;
+            cgg += g * g; cgb += g * b; cbb += b * b;
+        }
     }
     const float eps = 0.001f;
     crr += eps; cgg += eps; cbb += eps;
@@ -90,8 +97,8 @@ ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
         float a2 = crb * v0 + cgb * v1 + cbb * v2;
         v0 = a0; v1 = a1; v2 = a2;
         if (it & 1) {
-            float n2 = 0.0f;
-            n2 += a0 * a0; n2 += a1 * a1; n2 += a2 * a2;
+            float n2 = a0 * a0;
+            n2 += a1 * a1; n2 += a2 * a2;
             float rn = 1.0f / sqrtf(n2);
             v0 *= rn; v1 *= rn; v2 *= rn;
         }
@@ -102,16 +109,16 @@ ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
     float dmin = 65536.0f, dmax = 0.0f;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        float d = 0.0f;
+        float d = (px[0][k] - mean[0]) * axis[0];
 #pragma unroll
-        for (int c = 0; c < 3; c++) d += (px[c][k] - mean[c]) * axis[c];
+        for (int c = 1; c < 3; c++) d += (px[c][k] - mean[c]) * axis[c];
         dmin = fminf(dmin, d);            // d is finite: identical to the reference's (a<b)?a:b, one FMNMX
         dmax = fmaxf(dmax, d);
     }
     if (dmax - dmin < 1.0f) { dmin -= 0.5f; dmax += 0.5f; }
-    float n2 = 0.0f;
+    float n2 = axis[0] * axis[0];
 #pragma unroll
-    for (int c = 0; c < 3; c++) n2 += axis[c] * axis[c];
+    for (int c = 1; c < 3; c++) n2 += axis[c] * axis[c];
     float inv = 1.0f / n2;
     float lo[3], hi[3];
 #pragma unroll
