@@ -398,14 +398,19 @@ int encode_single(int format, const rgba_surface* src, uint8_t* dst, const void*
         if (grow(c.d_out, c.d_out_cap, out_bytes)) return -1;
         d_dst = c.d_out;
     }
-    ITW_CUDA(cudaEventRecord(c.ev0, s));
-    if (launch(format, v, d_dst, settings, s)) { cudaStreamSynchronize(s); cudaGetLastError(); return -1; }
-    ITW_CUDA(cudaEventRecord(c.ev1, s));
-    c.timed = true;
-    if (!dst_ok)
-        ITW_CUDA(cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-    ITW_CUDA(cudaStreamSynchronize(s));
-    return 0;
+    // From here on work is in flight on `s`: every failure still leaves through the synchronisation below (the caller may free
+    // src / dst as soon as the call returns), like encode_banded.
+    int rc = 0;
+    auto step = [&](cudaError_t e, const char* what) { if (rc == 0 && e != cudaSuccess) rc = fail(what, e); return rc == 0; };
+    step(cudaEventRecord(c.ev0, s), "cudaEventRecord");
+    if (rc == 0 && launch(format, v, d_dst, settings, s)) rc = -1;                       // bad settings or a launch failure
+    if (rc == 0 && step(cudaEventRecord(c.ev1, s), "cudaEventRecord")) c.timed = true;
+    if (rc == 0 && !dst_ok)
+        step(cudaMemcpyAsync(dst, d_dst, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync");
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == 0) step(e, "cudaStreamSynchronize");
+    else cudaGetLastError();
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -604,15 +609,18 @@ int decode_any(int format, const uint8_t* blocks, const rgba_surface* dst)
         d_dst = c.d_out;
         stride = (long long)row_bytes;
     }
-    ITW_CUDA(cudaEventRecord(c.ev0, s));
-    if (launch_decode(format, d_blocks, d_dst, dst->width, dst->height, stride, s)) return -1;
-    ITW_CUDA(cudaEventRecord(c.ev1, s));
-    c.timed = true;
-    if (!dst_ok)
-        ITW_CUDA(cudaMemcpy2DAsync(dst->ptr, (size_t)dst->stride, d_dst, row_bytes, row_bytes, (size_t)dst->height,
-                                   dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-    ITW_CUDA(cudaStreamSynchronize(s));
-    return 0;
+    int rc = 0;                                        // work is in flight from here on: every exit synchronises (see encode_single)
+    auto step = [&](cudaError_t e, const char* what) { if (rc == 0 && e != cudaSuccess) rc = fail(what, e); return rc == 0; };
+    step(cudaEventRecord(c.ev0, s), "cudaEventRecord");
+    if (rc == 0 && launch_decode(format, d_blocks, d_dst, dst->width, dst->height, stride, s)) rc = -1;
+    if (rc == 0 && step(cudaEventRecord(c.ev1, s), "cudaEventRecord")) c.timed = true;
+    if (rc == 0 && !dst_ok)
+        step(cudaMemcpy2DAsync(dst->ptr, (size_t)dst->stride, d_dst, row_bytes, row_bytes, (size_t)dst->height,
+                               dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s), "cudaMemcpy2DAsync");
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == 0) step(e, "cudaStreamSynchronize");
+    else cudaGetLastError();
+    return rc;
 }
 
 
