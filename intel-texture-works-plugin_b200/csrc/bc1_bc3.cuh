@@ -64,16 +64,18 @@ ITW_HD u32 bc1_linear_indices(const float (&px)[3][16], int p0, int p1)
 }
 
 // The colour half shared by BC1 and BC3; K:494-533
-ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
+// plane[c][i] = channel c of texels 4i..4i+3, one byte each: the two sums of the reference that are exact integers (the
+// channel sums behind the mean, and the index-weighted sums of the refinement) are taken with IDP.4A on these words.
+ITW_HD void bc1_colour_block(const float (&px)[3][16], const u32 (&plane)[3][4], u32& w0, u32& w1)
 {
     // mean, then centred covariance accumulated in texel order; K:377-417
     float mean[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        float acc = px[c][0];
+        u32 acc = 0u;                                            // sum of sixteen bytes: the reference's float sum is this integer
 #pragma unroll
-        for (int k = 1; k < 16; k++) acc += px[c][k];
-        mean[c] = acc / 16.0f;
+        for (int i = 0; i < 4; i++) acc = dp4a_u8(plane[c][i], 0x01010101u, acc);
+        mean[c] = (float)(int)acc / 16.0f;
     }
     float crr = 0.0f, crg = 0.0f, crb = 0.0f, cgg = 0.0f, cgb = 0.0f, cbb = 0.0f;
 #pragma unroll
@@ -142,13 +144,18 @@ ITW_HD void bc1_colour_block(const float (&px)[3][16], u32& w0, u32& w1)
         const u32 lo_b = bits & 0x55555555u, hi_b = (bits >> 1) & 0x55555555u;
         const float sq1 = (float)(popcount32(lo_b) + 2 * popcount32(hi_b));
         const float sqq = (float)(popcount32(lo_b) + 4 * popcount32(hi_b) + 4 * popcount32(lo_b & hi_b));
-        float atb1[3] = {0.0f, 0.0f, 0.0f};
+        // sum of (3 - q) * texel: products and running sums (<= 12240) are exact integers in the reference's floats
+        u32 isum[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const float x = (float)(3 - (int)((bits >> (2 * k)) & 3u));
+        for (int i = 0; i < 4; i++) {
+            u32 t = (bits >> (8 * i)) & 255u;                    // four 2-bit indices ...
+            t = (t | (t << 12)) & 0x000F000Fu;
+            t = (t | (t << 6)) & 0x03030303u;                    // ... one per byte
+            const u32 x = 0x03030303u - t;                       // 3 - q, bytewise, no borrows
 #pragma unroll
-            for (int c = 0; c < 3; c++) atb1[c] = fma_rn(x, px[c][k], atb1[c]);
+            for (int c = 0; c < 3; c++) isum[c] = dp4a_u8(x, plane[c][i], isum[c]);
         }
+        const float atb1[3] = {(float)(int)isum[0], (float)(int)isum[1], (float)(int)isum[2]};
         float cxx = 16.0f * 9.0f - 6.0f * sq1 + sqq;
         float cyy = sqq;
         float cxy = 3.0f * sq1 - sqq;
@@ -234,21 +241,36 @@ ITW_HD void bc1_bc3_encode_block(const u32 (&tex)[16], u32 (&out)[4])
         px[1][k] = (float)((tex[k] >> 8) & 255u);
         px[2][k] = (float)((tex[k] >> 16) & 255u);
     }
+    u32 plane[3][4];                                             // 4x4 byte transposes: two PRMT stages per four texels
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u32 rg01 = byte_perm(tex[4 * i], tex[4 * i + 1], 0x5140u), rg23 = byte_perm(tex[4 * i + 2], tex[4 * i + 3], 0x5140u);
+        const u32 ba01 = byte_perm(tex[4 * i], tex[4 * i + 1], 0x7362u), ba23 = byte_perm(tex[4 * i + 2], tex[4 * i + 3], 0x7362u);
+        plane[0][i] = byte_perm(rg01, rg23, 0x5410u);
+        plane[1][i] = byte_perm(rg01, rg23, 0x7632u);
+        plane[2][i] = byte_perm(ba01, ba23, 0x5410u);
+    }
     if (kAlpha) {
         float al[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) al[k] = (float)(tex[k] >> 24);
         bc3_alpha_block(al, out[0], out[1]);
-        bc1_colour_block(px, out[2], out[3]);
+        bc1_colour_block(px, plane, out[2], out[3]);
     } else {
-        bc1_colour_block(px, out[0], out[1]);
+        bc1_colour_block(px, plane, out[0], out[1]);
         out[2] = out[3] = 0;
     }
 }
 
 #if defined(__CUDACC__)
+// CTAs of 128 threads per SM the register budget is cut for, measured on B200 (tools/bc1_variants.sh,
+// profiles/r2_bc1_variants.txt): BC1 58.3 us with 4 (128 registers, 16 bytes of spills), 60.2 with 5 (96 registers), 62.3 with 6,
+// 64.7 with 3; BC3 69.2 / 70.6 / 72.8 / 74.8 us.
+#ifndef ITW_BC1_MIN_CTAS
+#define ITW_BC1_MIN_CTAS(alpha) 4
+#endif
 template <bool kAlpha, bool kVec16>
-__global__ void __launch_bounds__(128, 5) bc1_bc3_kernel(SurfaceView s, uint8_t* __restrict__ dst)
+__global__ void __launch_bounds__(128, ITW_BC1_MIN_CTAS(kAlpha)) bc1_bc3_kernel(SurfaceView s, uint8_t* __restrict__ dst)
 {
     const int bw = s.width >> 2, bh = s.height >> 2;
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
