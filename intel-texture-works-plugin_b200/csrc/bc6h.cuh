@@ -14,7 +14,7 @@
 #include "bc67_core.cuh"
 
 #ifndef ITW_BC6_ASSIGN_UNROLL
-#define ITW_BC6_ASSIGN_UNROLL 8           // tuned on B200, tools/tune_unroll.sh
+#define ITW_BC6_ASSIGN_UNROLL 16          // tuned on B200, tools/tune_unroll.sh (profiles/r2_tune_unroll.txt)
 #endif
 
 namespace itw {
