@@ -34,6 +34,13 @@ struct Bc6Entry {
     int qbounds[8];
 };
 struct Bc6Step;
+// Result of one (block, role) chain: quantised endpoints (per channel: A0 | B0 << 16 | A1 << 32 | B1 << 48), indices, shape.
+// Only the winning role of a block is packed into 128 bits (store phase): packing every candidate cost 8 % of the kernel.
+struct Bc6Role {
+    unsigned long long ch[3];
+    u32 idx0, idx1;
+    int shape, pad;
+};
 struct Bc6Warp {
     const Bc6Step* layout;                        // the 14 header layouts: CTA-shared copy on the device (bc6h_kernel), host table in the emulation
     float px[kBc6Slots][64];
@@ -42,14 +49,18 @@ struct Bc6Warp {
     int max_span_idx[kBc6Slots];
     int keys[kBc6Slots][32], order[kBc6Slots][32];
     Bc6Entry two[kBc6Slots][kBc6MaxTwo], one[kBc6Slots][kBc6MaxOne];
-    Bc6Entry tmp[kBc6Slots][10];                  // the ten base modes, filled in parallel by the setup phase
-    int tmp_fits[kBc6Slots][10];                  // 1 if the mode's span test passed under the profile's margin
+    union {
+        struct {
+            Bc6Entry tmp[kBc6Slots][10];          // the ten base modes, filled in parallel by the setup phase
+            int tmp_fits[kBc6Slots][10];          // 1 if the mode's span test passed under the profile's margin
+        } setup;                                  // dead once the select phase has filled two[] / one[]
+        Bc6Role role[kBc6Slots][kBc6MaxTwo + kBc6MaxOne];   // chain phase -> store phase: what the winner is packed from
+    };
     int ntwo[kBc6Slots], none[kBc6Slots];
     float fit[kBc6Slots][32][16];                 // unquantised segments of ranked shape n: [subset][A rgb., B rgb.]
     float cand_err[kBc6Slots][kBc6MaxTwo][32];
     int win_pos[kBc6Slots][kBc6MaxTwo];
     float res_err[kBc6Slots][kBc6MaxTwo + kBc6MaxOne];
-    u32 res_code[kBc6Slots][kBc6MaxTwo + kBc6MaxOne][4];
     int nvalid;
 };
 
@@ -398,11 +409,25 @@ ITW_HD_NOINLINE void bc6_chain(Bc6Warp& W, const Bc6Params& P, int slot, int r)
         if (!two || found.err < best.err) { best_q = q; best = found; }
     }
     W.res_err[slot][r] = best.err;
+    Bc6Role& R = W.role[slot][r];
+#pragma unroll
+    for (int c = 0; c < 3; c++) R.ch[c] = best_q.ch[c];
+    R.idx0 = best.idx0; R.idx1 = best.idx1; R.shape = shape;
+}
+// The 128 bits of role r of a block, from what its chain left in W.role; K:1694-1733, :2392-3031
+ITW_HD_NOINLINE void bc6_encode_role(const Bc6Warp& W, int slot, int r, u32 (&out)[4])
+{
+    const bool two = r < W.ntwo[slot];
+    const Bc6Entry& E = two ? W.two[slot][r] : W.one[slot][r - W.ntwo[slot]];
+    const int bits = two ? 3 : 4;
+    const Bc6Role& R = W.role[slot][r];
+    const int shape = R.shape;
+    unsigned long long ch[3] = {R.ch[0], R.ch[1], R.ch[2]};
     // orientation: the anchor index of every subset must have a clear top bit -- swap that subset's endpoints and
     // mirror its indices (K:1694-1733); the swap is a 32-bit rotate of the packed pair
     const int half = (1 << bits) / 2;
     int flips = 0;
-    u32 idx0 = best.idx0, idx1 = best.idx1;
+    u32 idx0 = R.idx0, idx1 = R.idx1;
     if (two) {                                                  // K:2982-3010
 #pragma unroll
         for (int j = 0; j < 2; j++) {
@@ -411,9 +436,9 @@ ITW_HD_NOINLINE void bc6_chain(Bc6Warp& W, const Bc6Params& P, int slot, int r)
             if (v >= half) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const u32 pair = (u32)(best_q.ch[c] >> (32 * j));
+                    const u32 pair = (u32)(ch[c] >> (32 * j));
                     const u32 swapped = (pair >> 16) | (pair << 16);
-                    best_q.ch[c] = (best_q.ch[c] & ~(0xFFFFFFFFull << (32 * j))) | ((unsigned long long)swapped << (32 * j));
+                    ch[c] = (ch[c] & ~(0xFFFFFFFFull << (32 * j))) | ((unsigned long long)swapped << (32 * j));
                 }
                 flips |= shape_mask(shape, j);
             }
@@ -421,21 +446,20 @@ ITW_HD_NOINLINE void bc6_chain(Bc6Warp& W, const Bc6Params& P, int slot, int r)
     } else if ((int)(idx0 & 15u) >= half) {                    // K:3012-3031
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const u32 pair = (u32)best_q.ch[c];
-            best_q.ch[c] = (best_q.ch[c] & 0xFFFFFFFF00000000ull) | (unsigned long long)((pair >> 16) | (pair << 16));
+            const u32 pair = (u32)ch[c];
+            ch[c] = (ch[c] & 0xFFFFFFFF00000000ull) | (unsigned long long)((pair >> 16) | (pair << 16));
         }
         const u32 all = 0x11111111u * (u32)((1 << bits) - 1);
         idx0 = all - idx0;
         idx1 = all - idx1;
     }
-    BitSink s = bc6_put_header(best_q.ch[0], best_q.ch[1], best_q.ch[2], E.mode, W.layout);
+    BitSink s = bc6_put_header(ch[0], ch[1], ch[2], E.mode, W.layout);
     if (two) {
         s.put(5, (u32)shape);
         put_indices(s, idx0, idx1, 3, flips, shape_anchor(shape, 1), -1);
     } else {
         put_indices(s, idx0, idx1, 4, 0, -1, -1);
     }
-    u32* out = W.res_code[slot][r];
     out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
 }
 
@@ -503,7 +527,7 @@ ITW_HD void bc6_phase_entries(int lane, Bc6Warp& W, const Bc6Params& P)
 {
     for (int t = lane; t < W.nvalid * 10; t += 32) {
         const int slot = t / 10, i = t - slot * 10;
-        W.tmp_fits[slot][i] = bc6_make_entry(W.tmp[slot][i], W, slot, bc6_base_mode(i), bc6_margin(P, i)) ? 1 : 0;
+        W.setup.tmp_fits[slot][i] = bc6_make_entry(W.setup.tmp[slot][i], W, slot, bc6_base_mode(i), bc6_margin(P, i)) ? 1 : 0;
     }
 }
 // the list of modes each block is encoded with; K:3069-3107
@@ -513,25 +537,25 @@ ITW_HD void bc6_phase_select(int lane, Bc6Warp& W, const Bc6Params& P)
         int ntwo = 0, none = 0;
         if (P.slow_mode) {                                       // every mode whose (margin 0) test passes, in order
             for (int i = 0; i < 6; i++)
-                if (W.tmp_fits[slot][i]) W.two[slot][ntwo++] = W.tmp[slot][i];
+                if (W.setup.tmp_fits[slot][i]) W.two[slot][ntwo++] = W.setup.tmp[slot][i];
             for (int i = 6; i < 10; i++)
-                if (W.tmp_fits[slot][i]) W.one[slot][none++] = W.tmp[slot][i];
+                if (W.setup.tmp_fits[slot][i]) W.one[slot][none++] = W.setup.tmp[slot][i];
         } else {
             if (P.fast_skip > 0) {                               // the LAST passing test of 9, [1], 6, 5, 0, 2 wins; K:3090-3095
                 int pick = 5;                                    // mode 9 (margin 0) always passes
-                if (P.fast_mode && W.tmp_fits[slot][1]) pick = 1;
-                if (W.tmp_fits[slot][4]) pick = 4;
-                if (W.tmp_fits[slot][3]) pick = 3;
-                if (W.tmp_fits[slot][0]) pick = 0;
-                if (W.tmp_fits[slot][2]) pick = 2;
-                W.two[slot][0] = W.tmp[slot][pick];
+                if (P.fast_mode && W.setup.tmp_fits[slot][1]) pick = 1;
+                if (W.setup.tmp_fits[slot][4]) pick = 4;
+                if (W.setup.tmp_fits[slot][3]) pick = 3;
+                if (W.setup.tmp_fits[slot][0]) pick = 0;
+                if (W.setup.tmp_fits[slot][2]) pick = 2;
+                W.two[slot][0] = W.setup.tmp[slot][pick];
                 ntwo = 1;
-                if (!P.fast_mode) { W.two[slot][1] = W.tmp[slot][1]; ntwo = 2; }     // mode 1 with margin 0; K:3098
+                if (!P.fast_mode) { W.two[slot][1] = W.setup.tmp[slot][1]; ntwo = 2; }     // mode 1 with margin 0; K:3098
             }
             int pick = 6;                                        // 10, then 11, 12, 13 if they fit; K:3101-3105
             for (int i = 7; i < 10; i++)
-                if (W.tmp_fits[slot][i]) pick = i;
-            W.one[slot][0] = W.tmp[slot][pick];
+                if (W.setup.tmp_fits[slot][i]) pick = i;
+            W.one[slot][0] = W.setup.tmp[slot][pick];
             none = 1;
         }
         W.ntwo[slot] = ntwo;
@@ -608,15 +632,13 @@ ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_
     for (int t = lane; t < W.nvalid; t += 32) {
         const int nroles = W.ntwo[t] + W.none[t];
         float best_err = inf_f();
-        u32 code[4] = {0u, 0u, 0u, 0u};
-        for (int r = 0; r < nroles; r++) {
-            float e = W.res_err[t][r];
-            if (e < best_err) {
-                best_err = e;
-#pragma unroll
-                for (int i = 0; i < 4; i++) code[i] = W.res_code[t][r][i];
-            }
+        int best = -1;
+        for (int r = 0; r < nroles; r++) {                       // first strict minimum in role order; K:2257, :2296
+            const float e = W.res_err[t][r];
+            if (e < best_err) { best_err = e; best = r; }
         }
+        u32 code[4] = {0u, 0u, 0u, 0u};
+        if (best >= 0) bc6_encode_role(W, t, best, code);
         u32* out = reinterpret_cast<u32*>(dst + (size_t)(first_block + t) * 16);
 #pragma unroll
         for (int i = 0; i < 4; i++) out[i] = code[i];
