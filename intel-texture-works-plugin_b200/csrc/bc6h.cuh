@@ -35,11 +35,12 @@ struct Bc6Entry {
 };
 struct Bc6Step;
 // Result of one (block, role) chain: quantised endpoints (per channel: A0 | B0 << 16 | A1 << 32 | B1 << 48), indices, shape.
-// Only the winning role of a block is packed into 128 bits (store phase): packing every candidate cost 8 % of the kernel.
+// Only the winning role of a block is packed into 128 bits, and its ~40 bit fields are packed by as many lanes (pick / pack /
+// store phases): walking the header layout field by field in every candidate's lane cost 8 % of the kernel.
 struct Bc6Role {
     unsigned long long ch[3];
     u32 idx0, idx1;
-    int shape, pad;
+    int shape, flips;                 // flips: texels whose index is mirrored (set by the pick phase for the winner)
 };
 struct Bc6Warp {
     const Bc6Step* layout;                        // the 14 header layouts: CTA-shared copy on the device (bc6h_kernel), host table in the emulation
@@ -61,6 +62,8 @@ struct Bc6Warp {
     float cand_err[kBc6Slots][kBc6MaxTwo][32];
     int win_pos[kBc6Slots][kBc6MaxTwo];
     float res_err[kBc6Slots][kBc6MaxTwo + kBc6MaxOne];
+    int win_role[kBc6Slots];                      // winning role per block, -1 = none (all candidates infinite)
+    u32 code[kBc6Slots][4];                       // the block being assembled: lanes OR their fields in (pack phase)
     int nvalid;
 };
 
@@ -219,30 +222,29 @@ struct Bc6Quant {
 struct Bc6Search { float err; u32 idx0, idx1; };
 ITW_HD u32 bc6_q(const Bc6Quant& Q, int endpoint, int c) { return (u32)(Q.ch[c] >> (16 * endpoint)) & 0xFFFFu; }
 
-// Header bits of `mode` from the quantised endpoints; one 32-bit shared-memory read per layout step.
-ITW_HD_NOINLINE BitSink bc6_put_header(unsigned long long ch0, unsigned long long ch1, unsigned long long ch2, int mode,
-                                       const Bc6Step* layout)
+// Header field `i` of `mode`: its bits (LSB first, as they go into the block), their count and their position; count 0 = no
+// such step.  The position is the sum of the widths of the steps before it.
+ITW_HD void bc6_header_field(u32& bits, int& count, int& pos, int i, const unsigned long long (&ch)[3], int mode, const Bc6Step* layout)
 {
-    BitSink s;
-    s.reset();
-    const bool delta = !(mode == 9 || mode == 10);
     const Bc6Step* steps = layout + mode * kBc6MaxSteps;
-    for (int i = 0; i < kBc6MaxSteps; i++) {
-        const int f = steps[i].f, b = steps[i].b, n = steps[i].n;
-        if (n == 0) break;
-        int value;
-        if (f == 0) value = bc6_prefix(mode);
-        else {
-            const int e = (f - 1) / 3, c = (f - 1) % 3;
-            const unsigned long long sel = (c == 0) ? ch0 : ((c == 1) ? ch1 : ch2);
-            value = (int)((u32)(sel >> (16 * e)) & 0xFFFFu);
-            if (delta && e > 0) value -= (int)((u32)sel & 0xFFFFu);
-        }
-        if (n > 0) s.put(n, (u32)value >> b);
-        else
-            for (int j = 0; j < -n; j++) s.put(1, ((u32)value >> (b - j)) & 1u);
+    pos = 0;
+    for (int j = 0; j < i; j++) { const int w = steps[j].n; pos += (w < 0) ? -w : w; }
+    const int f = steps[i].f, b = steps[i].b, n = steps[i].n;
+    count = (n < 0) ? -n : n;
+    bits = 0u;
+    if (n == 0) return;
+    int value;
+    if (f == 0) value = bc6_prefix(mode);
+    else {
+        const bool delta = !(mode == 9 || mode == 10);
+        const int e = (f - 1) / 3, c = (f - 1) % 3;
+        const unsigned long long sel = (c == 0) ? ch[0] : ((c == 1) ? ch[1] : ch[2]);
+        value = (int)((u32)(sel >> (16 * e)) & 0xFFFFu);
+        if (delta && e > 0) value -= (int)((u32)sel & 0xFFFFu);
     }
-    return s;
+    if (n > 0) bits = ((u32)value >> b) & ((1u << n) - 1u);
+    else
+        for (int k = 0; k < -n; k++) bits |= (((u32)value >> (b - k)) & 1u) << k;      // descending source bits
 }
 
 // ---- index search, three channels, decoded endpoints are integers 0..65535; K:1133-1193 ----
@@ -414,53 +416,36 @@ ITW_HD_NOINLINE void bc6_chain(Bc6Warp& W, const Bc6Params& P, int slot, int r)
     for (int c = 0; c < 3; c++) R.ch[c] = best_q.ch[c];
     R.idx0 = best.idx0; R.idx1 = best.idx1; R.shape = shape;
 }
-// The 128 bits of role r of a block, from what its chain left in W.role; K:1694-1733, :2392-3031
-ITW_HD_NOINLINE void bc6_encode_role(const Bc6Warp& W, int slot, int r, u32 (&out)[4])
+// Orientation of the winning role, in place: the anchor index of every subset must have a clear top bit -- swap that subset's
+// endpoints and mirror its indices (K:1694-1733, :2982-3031); the swap is a 32-bit rotate of the packed pair.
+ITW_HD void bc6_orient_role(Bc6Role& R, bool two)
 {
-    const bool two = r < W.ntwo[slot];
-    const Bc6Entry& E = two ? W.two[slot][r] : W.one[slot][r - W.ntwo[slot]];
-    const int bits = two ? 3 : 4;
-    const Bc6Role& R = W.role[slot][r];
-    const int shape = R.shape;
-    unsigned long long ch[3] = {R.ch[0], R.ch[1], R.ch[2]};
-    // orientation: the anchor index of every subset must have a clear top bit -- swap that subset's endpoints and
-    // mirror its indices (K:1694-1733); the swap is a 32-bit rotate of the packed pair
-    const int half = (1 << bits) / 2;
+    const int bits = two ? 3 : 4, half = (1 << bits) / 2;
     int flips = 0;
-    u32 idx0 = R.idx0, idx1 = R.idx1;
-    if (two) {                                                  // K:2982-3010
+    if (two) {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            const int k0 = shape_anchor(shape, j);
-            const int v = (int)(((k0 < 8 ? idx0 : idx1) >> (4 * (k0 & 7))) & 15u);
+            const int k0 = shape_anchor(R.shape, j);
+            const int v = (int)(((k0 < 8 ? R.idx0 : R.idx1) >> (4 * (k0 & 7))) & 15u);
             if (v >= half) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const u32 pair = (u32)(ch[c] >> (32 * j));
+                    const u32 pair = (u32)(R.ch[c] >> (32 * j));
                     const u32 swapped = (pair >> 16) | (pair << 16);
-                    ch[c] = (ch[c] & ~(0xFFFFFFFFull << (32 * j))) | ((unsigned long long)swapped << (32 * j));
+                    R.ch[c] = (R.ch[c] & ~(0xFFFFFFFFull << (32 * j))) | ((unsigned long long)swapped << (32 * j));
                 }
-                flips |= shape_mask(shape, j);
+                flips |= shape_mask(R.shape, j);
             }
         }
-    } else if ((int)(idx0 & 15u) >= half) {                    // K:3012-3031
+    } else if ((int)(R.idx0 & 15u) >= half) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const u32 pair = (u32)ch[c];
-            ch[c] = (ch[c] & 0xFFFFFFFF00000000ull) | (unsigned long long)((pair >> 16) | (pair << 16));
+            const u32 pair = (u32)R.ch[c];
+            R.ch[c] = (R.ch[c] & 0xFFFFFFFF00000000ull) | (unsigned long long)((pair >> 16) | (pair << 16));
         }
-        const u32 all = 0x11111111u * (u32)((1 << bits) - 1);
-        idx0 = all - idx0;
-        idx1 = all - idx1;
+        flips = 0xFFFF;                                       // every index mirrored
     }
-    BitSink s = bc6_put_header(ch[0], ch[1], ch[2], E.mode, W.layout);
-    if (two) {
-        s.put(5, (u32)shape);
-        put_indices(s, idx0, idx1, 3, flips, shape_anchor(shape, 1), -1);
-    } else {
-        put_indices(s, idx0, idx1, 4, 0, -1, -1);
-    }
-    out[0] = s.w0; out[1] = s.w1; out[2] = s.w2; out[3] = s.w3;
+    R.flips = flips;
 }
 
 // =============================================================================================
@@ -627,22 +612,64 @@ ITW_HD void bc6_phase_chains(int lane, Bc6Warp& W, const Bc6Params& P)
         if (r < W.ntwo[slot] + W.none[slot]) bc6_chain(W, P, slot, r);
     }
 }
-ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_block)
+// the block's winner: first strict minimum in role order (K:2257, :2296), oriented in place
+ITW_HD void bc6_phase_pick(int lane, Bc6Warp& W)
 {
     for (int t = lane; t < W.nvalid; t += 32) {
         const int nroles = W.ntwo[t] + W.none[t];
         float best_err = inf_f();
         int best = -1;
-        for (int r = 0; r < nroles; r++) {                       // first strict minimum in role order; K:2257, :2296
+        for (int r = 0; r < nroles; r++) {
             const float e = W.res_err[t][r];
             if (e < best_err) { best_err = e; best = r; }
         }
-        u32 code[4] = {0u, 0u, 0u, 0u};
-        if (best >= 0) bc6_encode_role(W, t, best, code);
-        u32* out = reinterpret_cast<u32*>(dst + (size_t)(first_block + t) * 16);
+        W.win_role[t] = best;
 #pragma unroll
-        for (int i = 0; i < 4; i++) out[i] = code[i];
+        for (int i = 0; i < 4; i++) W.code[t][i] = 0u;
+        if (best >= 0) bc6_orient_role(W.role[t][best], best < W.ntwo[t]);
     }
+}
+// The 128 bits of the winners, one bit field per lane: up to 24 header steps, the shape id, sixteen indices (K:2392-3031).
+// Lanes OR their fields into W.code (several lanes per word: shared_or).
+constexpr int kBc6PackItems = kBc6MaxSteps + 1 + 16;
+ITW_HD void bc6_phase_pack(int lane, Bc6Warp& W)
+{
+    for (int t = lane; t < W.nvalid * kBc6PackItems; t += 32) {
+        const int slot = t / kBc6PackItems, i = t - slot * kBc6PackItems;
+        const int r = W.win_role[slot];
+        if (r < 0) continue;
+        const bool two = r < W.ntwo[slot];
+        const Bc6Entry& E = two ? W.two[slot][r] : W.one[slot][r - W.ntwo[slot]];
+        const Bc6Role& R = W.role[slot][r];
+        u32 bits = 0u;
+        int count = 0, pos = 0;
+        if (i < kBc6MaxSteps) {
+            const unsigned long long ch[3] = {R.ch[0], R.ch[1], R.ch[2]};
+            bc6_header_field(bits, count, pos, i, ch, E.mode, W.layout);
+        } else if (i == kBc6MaxSteps) {
+            if (two) { bits = (u32)R.shape; count = 5; pos = 77; }                      // 5 + 72 header bits before it
+        } else {
+            const int k = i - kBc6MaxSteps - 1, width = two ? 3 : 4, top = (1 << width) - 1;
+            const int anchor1 = two ? shape_anchor(R.shape, 1) : -1;
+            int q = (int)(((k < 8 ? R.idx0 : R.idx1) >> (4 * (k & 7))) & 15u);
+            if ((R.flips >> k) & 1) q = top - q;
+            const bool narrow = (k == 0) || (k == anchor1);
+            bits = (u32)q;
+            count = narrow ? width - 1 : width;
+            pos = (two ? 82 : 65) + width * k - (k > 0 ? 1 : 0) - ((anchor1 >= 0 && k > anchor1) ? 1 : 0);
+        }
+        if (count == 0) continue;
+        bits &= (1u << count) - 1u;
+        const unsigned long long wide = (unsigned long long)bits << (pos & 31);
+        const int word = pos >> 5;
+        if ((u32)wide) shared_or(&W.code[slot][word], (u32)wide);
+        if ((u32)(wide >> 32) && word < 3) shared_or(&W.code[slot][word + 1], (u32)(wide >> 32));
+    }
+}
+ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_block)
+{
+    for (int t = lane; t < W.nvalid * 4; t += 32)
+        reinterpret_cast<u32*>(dst + (size_t)(first_block + (t >> 2)) * 16)[t & 3] = W.code[t >> 2][t & 3];
 }
 
 #define ITW_BC6_PROGRAM(PHASE)                                             \
@@ -661,6 +688,8 @@ ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_
     }                                                                      \
     PHASE(bc6_phase_winners(lane, W, P));                                  \
     PHASE(bc6_phase_chains(lane, W, P));                                   \
+    PHASE(bc6_phase_pick(lane, W));                                        \
+    PHASE(bc6_phase_pack(lane, W));                                        \
     PHASE(bc6_phase_store(lane, W, dst, first_block));
 
 #if defined(__CUDACC__)
@@ -678,7 +707,7 @@ bc6h_kernel(SurfaceView gsurf, uint8_t* __restrict__ dst, Bc6Params P, long long
     extern __shared__ __align__(16) unsigned char bc6_smem[];
     __shared__ __align__(128) unsigned char stage[kTma ? 2 : 1][kTma ? 4 * kBc6TileRowBytes : 16];
     __shared__ __align__(8) unsigned long long full[2];
-    // header layouts in shared memory: bc6_put_header walks them step by step, and from global memory every step
+    // header layouts in shared memory: the pack phase walks them, and from global memory every step
     // was a dependent L1/L2 round trip (long-scoreboard stalls, profiles/r1_final_bc6h_slow_ncu.txt)
     __shared__ Bc6Step layout[14 * kBc6MaxSteps];
     for (int i = threadIdx.x; i < 14 * kBc6MaxSteps; i += blockDim.x) layout[i] = d_bc6_layout[i / kBc6MaxSteps][i % kBc6MaxSteps];
