@@ -630,56 +630,40 @@ ITW_HD void bc6_phase_pick(int lane, Bc6Warp& W)
     }
 }
 // The 128 bits of the winners, one bit field per lane: up to 24 header steps, the shape id, sixteen indices (K:2392-3031).
-// A pass serves ONE block (two passes per block), so the lanes' contributions to its four words are combined by a warp
-// OR-reduction (REDUX); shared-memory atomics from forty lanes on four words were measured at 5 000 cycles per round.
-constexpr int kBc6PackItems = kBc6MaxSteps + 1 + 16;                                     // 41
+// Lanes OR their fields into W.code (several lanes per word: shared_or).
+constexpr int kBc6PackItems = kBc6MaxSteps + 1 + 16;
 ITW_HD void bc6_phase_pack(int lane, Bc6Warp& W)
 {
-    for (int pass = 0; pass < 2 * W.nvalid; pass++) {                                    // same trip count for every lane
-        const int slot = pass >> 1, i = 32 * (pass & 1) + lane;
+    for (int t = lane; t < W.nvalid * kBc6PackItems; t += 32) {
+        const int slot = t / kBc6PackItems, i = t - slot * kBc6PackItems;
         const int r = W.win_role[slot];
-        u32 w[4] = {0u, 0u, 0u, 0u};
-        if (r >= 0 && i < kBc6PackItems) {
-            const bool two = r < W.ntwo[slot];
-            const Bc6Entry& E = two ? W.two[slot][r] : W.one[slot][r - W.ntwo[slot]];
-            const Bc6Role& R = W.role[slot][r];
-            u32 bits = 0u;
-            int count = 0, pos = 0;
-            if (i < kBc6MaxSteps) {
-                const unsigned long long ch[3] = {R.ch[0], R.ch[1], R.ch[2]};
-                bc6_header_field(bits, count, pos, i, ch, E.mode, W.layout);
-            } else if (i == kBc6MaxSteps) {
-                if (two) { bits = (u32)R.shape; count = 5; pos = 77; }                  // 5 + 72 header bits before it
-            } else {
-                const int k = i - kBc6MaxSteps - 1, width = two ? 3 : 4, top = (1 << width) - 1;
-                const int anchor1 = two ? shape_anchor(R.shape, 1) : -1;
-                int q = (int)(((k < 8 ? R.idx0 : R.idx1) >> (4 * (k & 7))) & 15u);
-                if ((R.flips >> k) & 1) q = top - q;
-                const bool narrow = (k == 0) || (k == anchor1);
-                bits = (u32)q;
-                count = narrow ? width - 1 : width;
-                pos = (two ? 82 : 65) + width * k - (k > 0 ? 1 : 0) - ((anchor1 >= 0 && k > anchor1) ? 1 : 0);
-            }
-            if (count > 0) {
-                bits &= (1u << count) - 1u;
-                const unsigned long long wide = (unsigned long long)bits << (pos & 31);
-                const int word = pos >> 5;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (k == word) w[k] |= (u32)wide;
-                    if (k == word + 1) w[k] |= (u32)(wide >> 32);
-                }
-            }
+        if (r < 0) continue;
+        const bool two = r < W.ntwo[slot];
+        const Bc6Entry& E = two ? W.two[slot][r] : W.one[slot][r - W.ntwo[slot]];
+        const Bc6Role& R = W.role[slot][r];
+        u32 bits = 0u;
+        int count = 0, pos = 0;
+        if (i < kBc6MaxSteps) {
+            const unsigned long long ch[3] = {R.ch[0], R.ch[1], R.ch[2]};
+            bc6_header_field(bits, count, pos, i, ch, E.mode, W.layout);
+        } else if (i == kBc6MaxSteps) {
+            if (two) { bits = (u32)R.shape; count = 5; pos = 77; }                      // 5 + 72 header bits before it
+        } else {
+            const int k = i - kBc6MaxSteps - 1, width = two ? 3 : 4, top = (1 << width) - 1;
+            const int anchor1 = two ? shape_anchor(R.shape, 1) : -1;
+            int q = (int)(((k < 8 ? R.idx0 : R.idx1) >> (4 * (k & 7))) & 15u);
+            if ((R.flips >> k) & 1) q = top - q;
+            const bool narrow = (k == 0) || (k == anchor1);
+            bits = (u32)q;
+            count = narrow ? width - 1 : width;
+            pos = (two ? 82 : 65) + width * k - (k > 0 ? 1 : 0) - ((anchor1 >= 0 && k > anchor1) ? 1 : 0);
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-#if defined(__CUDA_ARCH__)
-            const u32 all = __reduce_or_sync(0xFFFFFFFFu, w[k]);
-            if (lane == 0) W.code[slot][k] |= all;
-#else
-            W.code[slot][k] |= w[k];                                                     // emulation: lanes run one after the other
-#endif
-        }
+        if (count == 0) continue;
+        bits &= (1u << count) - 1u;
+        const unsigned long long wide = (unsigned long long)bits << (pos & 31);
+        const int word = pos >> 5;
+        if ((u32)wide) shared_or(&W.code[slot][word], (u32)wide);
+        if ((u32)(wide >> 32) && word < 3) shared_or(&W.code[slot][word + 1], (u32)(wide >> 32));
     }
 }
 ITW_HD void bc6_phase_store(int lane, Bc6Warp& W, uint8_t* dst, long long first_block)

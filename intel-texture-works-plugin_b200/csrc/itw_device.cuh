@@ -187,6 +187,17 @@ ITW_HD int bc7_weight(int bits, int q)
     return ((64 * q + (n >> 1)) * m) >> 14;
 }
 
+// OR into a shared-memory word that other lanes of the warp OR into during the same phase (device: shared-memory atomic;
+// the CPU emulation runs the lanes of a phase one after the other)
+ITW_HD void shared_or(u32* p, u32 v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+
 // LSB-first writer into one 128-bit block held in four registers
 struct BitSink {
     u32 w0, w1, w2, w3;
