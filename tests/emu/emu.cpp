@@ -63,7 +63,12 @@ void emu_CompressBlocksBC4(const rgba_surface* src, uint8_t* dst)
 void emu_CompressBlocksBC5(const rgba_surface* src, uint8_t* dst)
 { per_block(src, dst, 16, [](const u32 (&t)[16], u32 (&o)[4]) { bc4_bc5_encode_block<true>(t, o); }); }
 
-#define ITW_PHASE_EMU(call) for (int lane = 0; lane < 32; lane++) { call; }
+// Lanes of a phase run one after the other.  On the GPU they run concurrently, so a phase must not depend on the order: the
+// order is selectable (ascending, descending, a fixed shuffle) and tests/test_emu_parity.py requires identical output for all.
+static int g_lane_order = 0;
+void emu_set_lane_order(int mode) { g_lane_order = mode; }
+static inline int emu_lane(int i) { return g_lane_order == 0 ? i : (g_lane_order == 1 ? 31 - i : (int)((i * 13u + 7u) & 31u)); }
+#define ITW_PHASE_EMU(call) for (int lane_i = 0; lane_i < 32; lane_i++) { const int lane = emu_lane(lane_i); call; }
 
 static int g_bc7_per_warp = kBc7Super;
 void emu_set_bc7_per_warp(int n) { g_bc7_per_warp = (n == kBc7Batch) ? kBc7Batch : kBc7Super; }   // what the host picks by surface size

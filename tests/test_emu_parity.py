@@ -51,3 +51,26 @@ def test_bc7_round_sizes(prof, per_warp):
             assert np.array_equal(got, want), (prof, per_warp, nblocks)
     finally:
         setter(16)
+
+
+@pytest.mark.parametrize("order", [1, 2], ids=["descending", "shuffled"])
+@pytest.mark.parametrize("fmt,prof", [("BC7", "slow"), ("BC7", "alpha_basic"), ("BC7", "alpha_veryfast"), ("BC6H", "bc6h_slow"),
+                                      ("BC6H", "bc6h_veryfast")])
+def test_phases_do_not_depend_on_lane_order(fmt, prof, order):
+    """On the GPU the lanes of a phase run concurrently; the emulation runs them one after the other.  A phase that read what
+    another lane of the same phase writes would give order-dependent output: descending and shuffled lane orders must equal
+    the oracle too (13 i + 7 mod 32 is a permutation of the lanes)."""
+    import ctypes
+    emu = T.emu()
+    setter = emu.lib.emu_set_lane_order
+    setter.argtypes = [ctypes.c_int]
+    setter.restype = None
+    bpb = T.binding.FORMATS[fmt][1]
+    try:
+        setter(order)
+        for name, img in T.corpus_for(fmt, 32).items():
+            got = T.run(emu, fmt, img, prof)
+            want = T.run(T.oracle(), fmt, img, prof)
+            assert T.differing_blocks(got, want, bpb) == 0, f"{fmt}/{prof}/{name}/order {order}"
+    finally:
+        setter(0)
