@@ -9,7 +9,8 @@
 //
 // The reference recomputes the 32 split bounds AND the PCA segments of each ranked shape for every
 // two-region mode it tries (K:2257-2273, :2174-2193); both depend only on the texels, so they are
-// computed once per block here (same values) and the six modes share them.
+// computed once per block here (same values) and the six modes share them.  A chain ends with quantised endpoints and
+// indices; only the block's winner is packed into 128 bits, one bit field per lane (pick / pack / store phases).
 #pragma once
 #include "bc67_core.cuh"
 

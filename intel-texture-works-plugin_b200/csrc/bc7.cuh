@@ -1,10 +1,10 @@
 // bc7.cuh -- BC7 encoder (reference: kernel.ispc:616-2037, cited as K:line).
 //
-// Mapping.  One WARP owns a batch of kBc7Batch = 8 consecutive 4x4 blocks, handled as two GROUPS of kBc7Slots = 4 for
-// the shape / ranking phases (their per-group scratch is reused) and as ONE set of 8 in the chain phase, so that the
-// chain phase -- 15 to 18 roles per block, a quarter of the work -- fills the warp (8 x 15 = 120 tasks in 4 passes
-// instead of 4 x 15 = 60 tasks in 2 passes of mixed kinds: 88 % of the lanes busy instead of 60 %).  The 32 lanes are
-// spread over the blocks' independent work items instead of over texels:
+// Mapping.  One WARP owns kBc7Super = 16 consecutive 4x4 blocks per round (kBc7Batch = 8 on surfaces too small to give
+// every SM such a CTA).  The shape / ranking phases hold one HALF of eight blocks at a time, as two GROUPS of kBc7Slots = 4
+// that reuse the per-group scratch; the chain phase -- 14 to 18 roles per block, a quarter of the work -- runs ONCE for all
+// sixteen blocks, two lanes per block, so that a pass is two equally long roles wide (DESIGN.md section 4 has the numbers).
+// The 32 lanes are spread over the blocks' independent work items instead of over texels:
 //   * shape phases: lane <-> (block slot, partition shape).  A lane fits the PCA segments of its
 //     shape ONCE and evaluates both BC7 modes that use that shape (0 and 2 share the three-subset
 //     shapes, 1 and 3 the two-subset shapes; the reference refits per mode, K:1279-1297, with
@@ -22,9 +22,9 @@
 //   * raw moments of a subset (K:763-803): IDP.4A dot products over channel-planar packed bytes;
 //   * index search (K:1133-1193): the projection numerator / denominator are integer dot
 //     products (then ONE float division, evaluated as the FMA-corrected quotient that equals the
-//     IEEE one -- tests/test_exact_division.py, tests/test_gpu_division.py), the two candidate palette
-//     entries are integer interpolations (the reference truncates them through int, K:1172-1173)
-//     and their squared errors are VABSDIFF4 + IDP.4A;
+//     IEEE one -- tests/test_exact_division.py, tests/test_gpu_division.py; the two-bit search of the shape phases by two
+//     integer thresholds instead), the two candidate palette entries are integer interpolations (the reference truncates
+//     them through int, K:1172-1173) and their squared errors are VABSDIFF4 + IDP.4A;
 //   * least-squares sums (K:1198-1230): IDP.4A over index bytes.
 // Everything that rounds (covariance, power iteration, endpoint solve, quantisation) follows the
 // reference's float expression order exactly (DESIGN.md "Canonical float model").
